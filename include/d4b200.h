@@ -1,0 +1,133 @@
+/*
+ * d4b200.h -- C ABI of the B200-native DFT-D4 hot path (libd4b200.so).
+ *
+ * Drop-in boundary: these entry points are what a maintainer of
+ * the reference (tad-dftd4 v0.8.0, pure Python/PyTorch) would bind with
+ * ``ctypes`` to replace, in one call, the chain
+ *
+ *   tad_mctc.ncoord.cn_d4                       (call site src/tad_dftd4/dispersion/base.py:390)
+ *   D4Model.__init__/_get_alpha/trapzd          (src/tad_dftd4/model/base.py:107-151,367-431; utils.py:33-94)
+ *   D4Model.weight_references (q and q=0)       (src/tad_dftd4/model/d4.py:103-228)
+ *   D4Model.get_atomic_c6                       (src/tad_dftd4/model/d4.py:268-289)
+ *   RationalDamping._f / dispersion2            (src/tad_dftd4/damping/functions.py:262-305; dispersion/twobody.py:89-201)
+ *   ATM.calculate / get_atm_dispersion          (src/tad_dftd4/dispersion/threebody.py:54-163,210-256,305-321)
+ *   torch.autograd over all of the above        (examples/forces.py:47-50)
+ *
+ * i.e. the body of ``Disp.calculate`` (dispersion/base.py:389-431) for the
+ * default D4 method.  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *  - plain C, no torch types; every pointer named ``*_dev`` is DEVICE memory
+ *    that the caller owns (borrowed for the duration of the call), pointers
+ *    named ``*_host`` are host memory;
+ *  - ``numbers`` is int64 [nbatch, nat] with 0 = padding, ``positions``
+ *    [nbatch, nat, 3] in Bohr, ``q`` / ``energy`` [nbatch, nat]; real type is
+ *    double (``_f64``) or float (``_f32``);
+ *  - all device entry points are asynchronous on ``stream`` (a cudaStream_t
+ *    passed as void*), allocate nothing and never synchronise;
+ *  - return value: 0 = ok, < 0 = invalid argument (D4B200_E*), > 0 = CUDA
+ *    runtime error code (cudaError_t).  Nothing throws.
+ *  - per-structure problems found on the device (atomic number outside
+ *    1..103, structure larger than the compiled paths support) are recorded
+ *    in the workspace and read back with d4b200_status().
+ */
+#ifndef D4B200_H
+#define D4B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D4B200_VERSION 100
+
+/* invalid-argument codes */
+#define D4B200_EINVAL (-1)      /* null pointer / negative size */
+#define D4B200_EWORKSPACE (-2)  /* workspace too small */
+#define D4B200_EPARAM (-3)      /* a1/a2 missing (NaN) etc. */
+#define D4B200_ETABLE (-4)      /* table blob has the wrong size */
+#define D4B200_EARCH (-5)       /* device is not sm_100 */
+
+/* device-side status bits returned by d4b200_status() */
+#define D4B200_STATUS_BAD_NUMBER 1 /* atomic number outside 1..103 */
+#define D4B200_STATUS_TOO_LARGE 2  /* structure too large for the available kernels */
+
+/* model selector */
+#define D4B200_MODEL_D4 0
+#define D4B200_MODEL_D4S 1
+
+/* Flattened ``Param`` (src/tad_dftd4/damping/parameters/base.py:48-85) +
+ * ``Cutoff`` (src/tad_dftd4/cutoff.py:36-90) + model weighting factor.
+ * Defaults applied by the caller exactly as the reference does:
+ * s6 = 1, s8 = 1 (dispersion/twobody.py:177-178), s9 = 1, alp = 16
+ * (dispersion/threebody.py:233-234); ``has_s10`` mirrors `"s10" in param`
+ * (dispersion/twobody.py:182). */
+typedef struct d4b200_params {
+  double s6, s8, s9, s10, a1, a2, alp;
+  double disp2_cutoff; /* 60 */
+  double disp3_cutoff; /* 40 */
+  double cn_cutoff;    /* 30 (Cutoff.cn is NOT forwarded by the reference) */
+  double wf;           /* Gaussian weighting factor, 6 (model/base.py:53) */
+  int32_t has_s10;
+  int32_t model; /* D4B200_MODEL_* */
+} d4b200_params;
+
+typedef struct d4b200_tables* d4b200_tables_t;
+
+int d4b200_version(void);
+const char* d4b200_error_string(int code);
+
+/* Upload the per-element tables (tad_dftd4_b200/tables.py blob layout) to
+ * ``device``; replaces the per-call model construction of
+ * src/tad_dftd4/dispersion/base.py:363.  ``ga``/``gc`` are the charge-scaling
+ * constants the blob was compiled with (model/base.py:51-52). */
+int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
+                         const int32_t* i32_blob_host, size_t n_i32, double ga, double gc,
+                         d4b200_tables_t* out);
+int d4b200_tables_destroy(d4b200_tables_t tables);
+
+/* Scratch the device entry points need for a [nbatch, nat] problem. */
+size_t d4b200_workspace_bytes(int nbatch, int nat);
+
+/* Atom-resolved dispersion energy, == tad_dftd4.dftd4(numbers, positions,
+ * charge, param, q=q) (src/tad_dftd4/disp.py:44-146).  ``cn_dev`` (optional)
+ * receives the coordination numbers. */
+int d4b200_energy_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                      const int64_t* numbers_dev, const double* positions_dev,
+                      const double* q_dev, double* energy_dev, double* cn_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+int d4b200_energy_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                      const int64_t* numbers_dev, const float* positions_dev, const float* q_dev,
+                      float* energy_dev, float* cn_dev, void* workspace_dev,
+                      size_t workspace_bytes, void* stream);
+
+/* Vector-Jacobian product of the energy: for upstream weights
+ * g = dL/dE [nbatch, nat] (NULL = all ones, i.e. L = sum E) returns
+ * dL/dpositions [nbatch, nat, 3] and dL/dq [nbatch, nat] (either may be
+ * NULL).  Replaces torch.autograd over the reference's dense tape
+ * (examples/forces.py:47-50). */
+int d4b200_gradient_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                        const int64_t* numbers_dev, const double* positions_dev,
+                        const double* q_dev, const double* grad_energy_dev,
+                        double* grad_positions_dev, double* grad_q_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream);
+int d4b200_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                        const int64_t* numbers_dev, const float* positions_dev,
+                        const float* q_dev, const float* grad_energy_dev,
+                        float* grad_positions_dev, float* grad_q_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream);
+
+/* Synchronises ``stream`` and returns the OR of the device status bits that
+ * the calls using ``workspace_dev`` recorded since the last query. */
+int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);
+
+/* Number of kernel launches the last energy/gradient call on this thread
+ * issued (for bench.py's gpu_launches claim). */
+int d4b200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D4B200_H */

@@ -1,0 +1,22 @@
+"""
+tad_dftd4_b200 -- B200-native (sm_100a) implementation of the DFT-D4 hot path
+behind the functional API of ``tad_dftd4``::
+
+    import tad_dftd4_b200 as d4
+    energy = d4.dftd4(numbers, positions, charge, param, q=q)   # (..., nat)
+
+CUDA kernels: ``csrc/`` (C ABI in ``include/d4b200.h``).  No CPU fallback.
+"""
+
+from . import batch, cutoff, damping, defaults
+from .batch import pack
+from .cutoff import Cutoff
+from .damping import Param, RationalDamping, get_params
+from .disp import dftd4, get_properties, last_launch_count, set_checks
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "__version__", "batch", "cutoff", "Cutoff", "damping", "defaults", "dftd4", "get_params",
+    "get_properties", "pack", "Param", "RationalDamping", "set_checks", "last_launch_count",
+]  # fmt: skip

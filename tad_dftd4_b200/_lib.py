@@ -1,0 +1,70 @@
+"""ctypes binding of ``libd4b200.so`` (C ABI: ``include/d4b200.h``).
+
+There is no CPU or PyTorch fallback: if the library is missing or the device
+is not a B200 the import / first call fails loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libd4b200.so"
+
+
+class D4B200Error(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("s6", C.c_double), ("s8", C.c_double), ("s9", C.c_double), ("s10", C.c_double),
+        ("a1", C.c_double), ("a2", C.c_double), ("alp", C.c_double),
+        ("disp2_cutoff", C.c_double), ("disp3_cutoff", C.c_double), ("cn_cutoff", C.c_double),
+        ("wf", C.c_double), ("has_s10", C.c_int32), ("model", C.c_int32),
+    ]  # fmt: skip
+
+
+_lib = None
+
+_VP = C.c_void_p
+_SIGS = {
+    "d4b200_version": (C.c_int, []),
+    "d4b200_error_string": (C.c_char_p, [C.c_int]),
+    "d4b200_tables_create": (C.c_int, [C.c_int, _VP, C.c_size_t, _VP, C.c_size_t, C.c_double, C.c_double, C.POINTER(_VP)]),
+    "d4b200_tables_destroy": (C.c_int, [_VP]),
+    "d4b200_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "d4b200_energy_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_energy_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_status": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
+    "d4b200_last_launch_count": (C.c_int, []),
+}  # fmt: skip
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and declare the signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.is_file():
+        raise D4B200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  tad_dftd4_b200 has no CPU / PyTorch fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().d4b200_error_string(code).decode()
+        raise D4B200Error(f"{what} failed with code {code}: {msg}")

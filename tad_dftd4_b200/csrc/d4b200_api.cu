@@ -1,0 +1,415 @@
+// C-ABI entry points (include/d4b200.h) + batch preparation kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "d4b200_common.cuh"
+#include "d4b200_small.cuh"
+
+using namespace d4b200;
+
+struct d4b200_tables {
+  int device;
+  int num_sms;
+  double ga, gc;
+  double* f64;  // device copy of the double blob
+  float* f32;   // same blob converted to float
+  int* i32;
+  size_t n_f64, n_i32;
+  Tables<double> t64;
+  Tables<float> t32;
+  // cached launch configuration: [dtype][grad][class]
+  int caps[2][2][NCLASS];
+  int threads[2][2][NCLASS];
+  int grid_per_sm[2][2][NCLASS];
+  size_t smem[2][2][NCLASS];
+};
+
+static thread_local int g_launches = 0;
+
+namespace {
+
+// section offsets inside the double blob (must match tables.py F64_LAYOUT)
+struct BlobOffsets {
+  size_t rcov, r4r2, sqrt_r4r2, gamgc, zeff, refcn, refq, zeta0, alpha0, den, alpha_w, wfpair, total;
+  size_t refc, maxcn_ref, itotal;
+};
+BlobOffsets blob_offsets() {
+  BlobOffsets o;
+  size_t p = 0;
+  o.rcov = p, p += NELEM;
+  o.r4r2 = p, p += NELEM;
+  o.sqrt_r4r2 = p, p += NELEM;
+  o.gamgc = p, p += NELEM;
+  o.zeff = p, p += NELEM;
+  o.refcn = p, p += NELEM * NREF;
+  o.refq = p, p += NELEM * NREF;
+  o.zeta0 = p, p += NELEM * NREF;
+  o.alpha0 = p, p += NELEM * NREF;
+  o.den = p, p += NELEM * NELEM;
+  o.alpha_w = p, p += NELEM * NREF * NFREQ;
+  o.wfpair = p, p += NELEM * NELEM;
+  o.total = p;
+  size_t q = 0;
+  o.refc = q, q += NELEM * NREF;
+  o.maxcn_ref = q, q += NELEM;
+  o.itotal = q;
+  return o;
+}
+
+template <typename T>
+Tables<T> make_tables(const T* real, const double* f64, const int* i32) {
+  const BlobOffsets o = blob_offsets();
+  Tables<T> t;
+  t.rcov = real + o.rcov;
+  t.r4r2 = real + o.r4r2;
+  t.sqrt_r4r2 = real + o.sqrt_r4r2;
+  t.den = real + o.den;
+  t.alpha_w = real + o.alpha_w;
+  t.alpha0 = real + o.alpha0;
+  t.gamgc = f64 + o.gamgc;
+  t.zeff = f64 + o.zeff;
+  t.refcn = f64 + o.refcn;
+  t.refq = f64 + o.refq;
+  t.zeta0 = f64 + o.zeta0;
+  t.wfpair = f64 + o.wfpair;
+  t.refc = i32 + o.refc;
+  t.maxcn_ref = i32 + o.maxcn_ref;
+  return t;
+}
+
+__global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// ---- batch preparation: size histogram -> descending-size order ------------
+__global__ void k_count(const int64_t* __restrict__ numbers, int nbatch, int nat, Work wk) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nbatch) return;
+  const int64_t* row = numbers + (size_t)warp * nat;
+  int c = 0;
+  for (int t = lane; t < nat; t += 32) c += row[t] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) {
+    wk.nreal[warp] = c;
+    atomicAdd(&wk.hist[c <= SMALL_MAX ? c : SMALL_MAX + 1], 1);
+  }
+}
+
+struct Caps {
+  int v[NCLASS];
+};
+
+__global__ void k_scan(int nbatch, Work wk, Caps caps) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // start[n] = number of structures with more than n atoms
+  int pos = 0;
+  for (int n = SMALL_MAX + 1; n >= 0; --n) {
+    wk.cursor[n] = pos;
+    pos += wk.hist[n];
+  }
+  // after the loop cursor[n] = start[n]; class c owns sizes (caps[c-1], caps[c]]
+  int end = nbatch;
+  for (int c = 0; c < NCLASS; ++c) {
+    const int begin = wk.cursor[caps.v[c]];
+    wk.class_range[2 * c] = begin;
+    wk.class_range[2 * c + 1] = end;
+    end = begin;
+  }
+  wk.class_range[2 * NCLASS] = 0;  // too large for the small family
+  wk.class_range[2 * NCLASS + 1] = end;
+  if (end > 0) atomicOr(wk.status, D4B200_STATUS_TOO_LARGE);
+}
+
+__global__ void k_scatter(int nbatch, Work wk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbatch) return;
+  const int n = wk.nreal[b];
+  const int pos = atomicAdd(&wk.cursor[n <= SMALL_MAX ? n : SMALL_MAX + 1], 1);
+  wk.order[pos] = b;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int HEADER_INTS = 1 + (NCLASS + 1) + 2 * (NCLASS + 1) + 2 * HIST_BINS;
+
+size_t int_region_bytes(int nbatch) {
+  return align_up(sizeof(int) * (HEADER_INTS + 2 * (size_t)nbatch), 256);
+}
+
+// workspace = [status | queue | class_range | hist | cursor | nreal | order | scratch]
+Work carve_work(void* ws, int nbatch) {
+  Work wk;
+  int* p = reinterpret_cast<int*>(ws);
+  wk.status = p, p += 1;
+  wk.queue = p, p += NCLASS + 1;
+  wk.class_range = p, p += 2 * (NCLASS + 1);
+  wk.hist = p, p += HIST_BINS;
+  wk.cursor = p, p += HIST_BINS;
+  wk.nreal = p, p += nbatch;
+  wk.order = p, p += nbatch;
+  return wk;
+}
+
+constexpr int MAX_SMS = 160;
+// upper bound of resident CTAs per SM we ever launch for a class
+__host__ inline int class_occ_cap(int c) { return c == 0 ? 16 : c == 1 ? 6 : 2; }
+
+size_t scratch_bytes_class(int c, int cap, size_t elem) {
+  return align_up((size_t)MAX_SMS * class_occ_cap(c) * 2 * (cap * (cap - 1) / 2) * elem, 256);
+}
+
+template <typename T>
+Par<T> make_par(const d4b200_params* p, double ga) {
+  Par<T> P;
+  P.s6 = (T)p->s6;
+  P.s8 = (T)p->s8;
+  P.s10k = p->has_s10 ? (T)(p->s10 * 49.0 / 40.0) : T(0);
+  P.a1 = (T)p->a1;
+  P.a2 = (T)p->a2;
+  P.alp3 = (T)(p->alp / 3.0);
+  P.fac9 = (T)cbrt(p->s9 / 6.0);
+  P.disp2_sq = (T)(p->disp2_cutoff * p->disp2_cutoff);
+  P.disp3_sq = (T)(p->disp3_cutoff * p->disp3_cutoff);
+  P.cn_sq = (T)(p->cn_cutoff * p->cn_cutoff);
+  P.wf = p->wf;
+  P.ga = ga;
+  P.has_atm = p->s9 != 0.0;
+  P.model = p->model;
+  return P;
+}
+
+template <typename T, bool GRAD>
+int configure(d4b200_tables* h) {
+  constexpr int dt = sizeof(T) == 8 ? 0 : 1;
+  constexpr int gr = GRAD ? 1 : 0;
+  // class bounds: as large as the 227 KB shared-memory budget allows
+  const int want[NCLASS] = {32, 64, 96, 128};
+  const int thr[NCLASS] = {128, 256, 512, 512};
+  int prev = 0;
+  for (int c = 0; c < NCLASS; ++c) {
+    int cap = want[c];
+    while (cap > prev + 4 && small_layout<T, GRAD>(cap).total > 227 * 1024) cap -= 4;
+    if (small_layout<T, GRAD>(cap).total > 227 * 1024) cap = prev;  // class unusable
+    h->caps[dt][gr][c] = cap;
+    h->threads[dt][gr][c] = thr[c];
+    h->smem[dt][gr][c] = small_layout<T, GRAD>(cap > 2 ? cap : 2).total;
+    prev = cap;
+  }
+  size_t maxs = 0;
+  for (int c = 0; c < NCLASS; ++c) maxs = h->smem[dt][gr][c] > maxs ? h->smem[dt][gr][c] : maxs;
+  cudaError_t e = cudaFuncSetAttribute(small_kernel<T, GRAD>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxs);
+  if (e != cudaSuccess) return (int)e;
+  for (int c = 0; c < NCLASS; ++c) {
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_kernel<T, GRAD>,
+                                                      h->threads[dt][gr][c], h->smem[dt][gr][c]);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) occ = 1;
+    if (occ > class_occ_cap(c)) occ = class_occ_cap(c);
+    h->grid_per_sm[dt][gr][c] = occ;
+  }
+  return 0;
+}
+
+template <typename T, bool GRAD>
+int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
+              const int64_t* numbers, const T* pos, const T* q, const T* gin, T* energy, T* cn_out,
+              T* grad, T* gradq, void* ws, size_t ws_bytes, cudaStream_t st) {
+  constexpr int dt = sizeof(T) == 8 ? 0 : 1;
+  constexpr int gr = GRAD ? 1 : 0;
+  g_launches = 0;
+  if (!h || !par || !numbers || !pos || !q || !ws || nbatch < 0 || nat < 0) return D4B200_EINVAL;
+  if (!GRAD && !energy) return D4B200_EINVAL;
+  if (!(par->a1 == par->a1) || !(par->a2 == par->a2)) return D4B200_EPARAM;
+  if (ws_bytes < d4b200_workspace_bytes(nbatch, nat)) return D4B200_EWORKSPACE;
+  if (nbatch == 0 || nat == 0) return 0;
+
+  Work wk = carve_work(ws, nbatch);
+  cudaError_t e = cudaMemsetAsync(wk.status, 0, sizeof(int) * HEADER_INTS, st);
+  if (e != cudaSuccess) return (int)e;
+  ++g_launches;
+  Caps caps;
+  for (int c = 0; c < NCLASS; ++c) caps.v[c] = h->caps[dt][gr][c];
+  k_count<<<(nbatch + 7) / 8, 256, 0, st>>>(numbers, nbatch, nat, wk);
+  k_scan<<<1, 32, 0, st>>>(nbatch, wk, caps);
+  k_scatter<<<(nbatch + 255) / 256, 256, 0, st>>>(nbatch, wk);
+  g_launches += 3;
+
+  SmallArgs<T> A;
+  A.numbers = numbers;
+  A.pos = pos;
+  A.q = q;
+  A.gin = gin;
+  A.energy = energy;
+  A.cn_out = cn_out;
+  A.grad = grad;
+  A.gradq = gradq;
+  A.nbatch = nbatch;
+  A.nat = nat;
+  for (int c = 0; c < NCLASS; ++c) A.caps[c] = caps.v[c];
+  if constexpr (dt == 0) {
+    A.tab = h->t64;
+  } else {
+    A.tab = h->t32;
+  }
+  A.par = make_par<T>(par, h->ga);
+  A.wk = wk;
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(ws) + int_region_bytes(nbatch);
+  int prev = 0;
+  for (int c = 0; c < NCLASS; ++c) {
+    const int cap = caps.v[c];
+    if (cap <= prev) continue;  // class disabled for this flavour
+    prev = cap;
+    // a class can only be populated if the padded width reaches into it
+    const int lo = c == 0 ? 0 : caps.v[c - 1] + 1;
+    size_t sbytes = scratch_bytes_class(c, cap, sizeof(T));
+    if (nat >= lo) {
+      A.cls = c;
+      A.scratch = reinterpret_cast<T*>(scratch);
+      long grid = (long)h->grid_per_sm[dt][gr][c] * h->num_sms;
+      if (grid > nbatch) grid = nbatch;
+      const long gmax = (long)(h->num_sms < MAX_SMS ? h->num_sms : MAX_SMS) * class_occ_cap(c);
+      if (grid > gmax) grid = gmax;
+      small_kernel<T, GRAD><<<(unsigned)grid, h->threads[dt][gr][c], h->smem[dt][gr][c], st>>>(A);
+      ++g_launches;
+    }
+    scratch += sbytes;
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int d4b200_version(void) { return D4B200_VERSION; }
+
+const char* d4b200_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case D4B200_EINVAL: return "invalid argument (null pointer or negative size)";
+    case D4B200_EWORKSPACE: return "workspace too small";
+    case D4B200_EPARAM: return "damping parameters a1/a2 missing";
+    case D4B200_ETABLE: return "table blob has the wrong size";
+    case D4B200_EARCH: return "device is not sm_100 (B200)";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
+                         const int32_t* i32_blob_host, size_t n_i32, double ga, double gc,
+                         d4b200_tables_t* out) {
+  if (!f64_blob_host || !i32_blob_host || !out) return D4B200_EINVAL;
+  const BlobOffsets o = blob_offsets();
+  if (n_f64 != o.total || n_i32 != o.itotal) return D4B200_ETABLE;
+  int prev_dev = 0;
+  cudaError_t e = cudaGetDevice(&prev_dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return (int)e;
+  if (prop.major != 10) {
+    cudaSetDevice(prev_dev);
+    return D4B200_EARCH;
+  }
+  d4b200_tables* h = new (std::nothrow) d4b200_tables();
+  if (!h) return D4B200_EINVAL;
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->ga = ga;
+  h->gc = gc;
+  h->n_f64 = n_f64;
+  h->n_i32 = n_i32;
+  int rc = 0;
+  do {
+    if ((e = cudaMalloc(&h->f64, n_f64 * sizeof(double))) != cudaSuccess) break;
+    if ((e = cudaMalloc(&h->f32, n_f64 * sizeof(float))) != cudaSuccess) break;
+    if ((e = cudaMalloc(&h->i32, n_i32 * sizeof(int))) != cudaSuccess) break;
+    if ((e = cudaMemcpy(h->f64, f64_blob_host, n_f64 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(h->i32, i32_blob_host, n_i32 * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    k_to_float<<<(unsigned)((n_f64 + 255) / 256), 256>>>(h->f64, h->f32, n_f64);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+    h->t64 = make_tables<double>(h->f64, h->f64, h->i32);
+    h->t32 = make_tables<float>(h->f32, h->f64, h->i32);
+    if ((rc = configure<double, false>(h)) != 0) break;
+    if ((rc = configure<double, true>(h)) != 0) break;
+    if ((rc = configure<float, false>(h)) != 0) break;
+    if ((rc = configure<float, true>(h)) != 0) break;
+  } while (0);
+  cudaSetDevice(prev_dev);
+  if (e != cudaSuccess || rc != 0) {
+    d4b200_tables_destroy(h);
+    return e != cudaSuccess ? (int)e : rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int d4b200_tables_destroy(d4b200_tables_t h) {
+  if (!h) return 0;
+  cudaFree(h->f64);
+  cudaFree(h->f32);
+  cudaFree(h->i32);
+  delete h;
+  return 0;
+}
+
+size_t d4b200_workspace_bytes(int nbatch, int nat) {
+  (void)nat;
+  if (nbatch < 0) return 0;
+  size_t s = int_region_bytes(nbatch);
+  const int caps[NCLASS] = {32, 64, 96, 128};
+  for (int c = 0; c < NCLASS; ++c) s += scratch_bytes_class(c, caps[c], sizeof(double));
+  return s;
+}
+
+int d4b200_energy_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                      const int64_t* numbers, const double* pos, const double* q, double* energy,
+                      double* cn, void* ws, size_t ws_bytes, void* stream) {
+  return run_small<double, false>(t, par, nbatch, nat, numbers, pos, q, nullptr, energy, cn,
+                                  nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_energy_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                      const int64_t* numbers, const float* pos, const float* q, float* energy,
+                      float* cn, void* ws, size_t ws_bytes, void* stream) {
+  return run_small<float, false>(t, par, nbatch, nat, numbers, pos, q, nullptr, energy, cn, nullptr,
+                                 nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                        const int64_t* numbers, const double* pos, const double* q,
+                        const double* gin, double* grad, double* gradq, void* ws, size_t ws_bytes,
+                        void* stream) {
+  return run_small<double, true>(t, par, nbatch, nat, numbers, pos, q, gin, nullptr, nullptr, grad,
+                                 gradq, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                        const int64_t* numbers, const float* pos, const float* q, const float* gin,
+                        float* grad, float* gradq, void* ws, size_t ws_bytes, void* stream) {
+  return run_small<float, true>(t, par, nbatch, nat, numbers, pos, q, gin, nullptr, nullptr, grad,
+                                gradq, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int d4b200_status(void* ws, void* stream, int* bits) {
+  if (!ws || !bits) return D4B200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(bits, ws, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaStreamSynchronize(st);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int d4b200_last_launch_count(void) { return g_launches; }
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+// One-CTA-per-structure kernels for molecules with <= 128 atoms ("small family").
+//
+// A persistent CTA pulls structures of one size class from a device-side queue
+// (sorted by descending atom count), stages the atoms (SoA) and all per-pair
+// quantities of the structure in shared memory and runs the whole D4 pipeline
+// without touching HBM again:
+//
+//   compact -> CN (erfc count) -> Gaussian weights x zeta -> per-atom weighted
+//   polarizability vectors A_i[23] -> pair pass (C6 = A_i.A_j, BJ two-body)
+//   -> ATM pair stash (r^2, sigma/r^3, (R0/r)^(alp/3)) -> triple loop
+//   [-> back-propagation passes for the gradient kernel]
+//
+// Algebra and its derivation: tests/kernel_model.py (checked against the oracle
+// on the CPU); reference formulation: src/tad_dftd4/dispersion/{twobody,
+// threebody}.py, model/d4.py, tad_mctc.ncoord.cn_d4 (see include/d4b200.h).
+#pragma once
+
+#include <math.h>
+
+#include "d4b200_common.cuh"
+
+namespace d4b200 {
+
+template <typename T>
+struct SmallArgs {
+  const int64_t* numbers;
+  const T* pos;
+  const T* q;
+  const T* gin;  // upstream dL/dE (nullable = ones)
+  T* energy;
+  T* cn_out;
+  T* grad;
+  T* gradq;
+  T* scratch;  // [gridDim.x][2][cap(cap-1)/2] per-CTA pair results of the triple loop
+  int nbatch, nat, cls;
+  int caps[NCLASS];  // inclusive size bounds of the classes for this kernel flavour
+  Tables<T> tab;
+  Par<T> par;
+  Work wk;
+};
+
+// ---------------------------------------------------------------- math shims
+__device__ __forceinline__ double d4_erfc(double x) { return erfc(x); }
+__device__ __forceinline__ float d4_erfc(float x) { return erfcf(x); }
+__device__ __forceinline__ double d4_exp(double x) { return exp(x); }
+__device__ __forceinline__ float d4_exp(float x) { return expf(x); }
+__device__ __forceinline__ double d4_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ float d4_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double d4_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float d4_sqrt(float x) { return sqrtf(x); }
+template <typename T>
+__device__ __forceinline__ T d4_eps();
+template <>
+__device__ __forceinline__ double d4_eps<double>() { return 2.220446049250313e-16; }
+template <>
+__device__ __forceinline__ float d4_eps<float>() { return 1.1920929e-07f; }
+
+// ---------------------------------------------------------------- smem layout
+struct SmallLayout {
+  int cap, cpairs;
+  size_t planes, aq, a0, bq, b0, atoms, wts, ints, total;
+};
+
+// per-atom T arrays
+enum { AT_X = 0, AT_Y, AT_Z, AT_Q, AT_CN, AT_E, AT_RCOV, AT_R4R2, AT_SQ, AT_G, AT_DCN, AT_DQ, AT_COUNT };
+// per-atom x 7 T arrays
+enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG, WT_COUNT };
+
+template <typename T, bool GRAD>
+__host__ __device__ inline SmallLayout small_layout(int cap) {
+  SmallLayout L;
+  L.cap = cap;
+  L.cpairs = cap * (cap - 1) / 2;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += (bytes + 15) & ~size_t(15);
+    return r;
+  };
+  L.planes = take(size_t(3) * L.cpairs * sizeof(T));
+  L.aq = take(size_t(NFREQ) * cap * sizeof(T));
+  L.a0 = take(size_t(NFREQ) * cap * sizeof(T));
+  L.bq = GRAD ? take(size_t(NFREQ) * cap * sizeof(T)) : 0;
+  L.b0 = GRAD ? take(size_t(NFREQ) * cap * sizeof(T)) : 0;
+  L.atoms = take(size_t(GRAD ? AT_COUNT : AT_G) * cap * sizeof(T));
+  L.wts = take(size_t(GRAD ? WT_COUNT : WT_ZGD) * NREF * cap * sizeof(T));
+  L.ints = take(size_t(2) * cap * sizeof(int) + 8 * sizeof(int));
+  L.total = o;
+  return L;
+}
+
+// p -> (hi, lo) with hi > lo, p = hi(hi-1)/2 + lo
+__device__ __forceinline__ void pair_decode(int p, int& hi, int& lo) {
+  int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+  while (i * (i - 1) / 2 > p) --i;
+  while ((i + 1) * i / 2 <= p) ++i;
+  hi = i;
+  lo = p - i * (i - 1) / 2;
+}
+
+template <typename T>
+__device__ __forceinline__ T row_sum(const T* __restrict__ plane, int i, int n) {
+  T s = T(0);
+  const int ti = i * (i - 1) / 2;
+  for (int j = 0; j < i; ++j) s += plane[ti + j];
+  for (int j = i + 1; j < n; ++j) s += plane[j * (j - 1) / 2 + i];
+  return s;
+}
+
+// One visit of the pair-owner triple loop: owner pair (j,k) with r^2 = b,
+// third atom i with stash entries of (i,j) and (i,k).
+//   e' = (0.375 s/(abc) + 1) * P_ij P_ik P_jk / (1 + 6 u_ij u_ik u_jk)
+// (threebody.py:113-160 factorised per pair; e' = e_ijk/6 with s9 folded in).
+template <typename T, bool GRAD, bool OPEN>
+__device__ __forceinline__ void triple_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T cjk,
+                                             T Pjk, T ujk, T inv_b, T alp3, T gi, T gj, T gk,
+                                             T& accH, T& accL, T& accG, T& accD) {
+  T a = a_s, c = c_s;
+  T mi = T(2), mj = T(2), mk = T(2);
+  if (OPEN) {
+    const T cij = a_s > T(0) ? T(1) : T(0);
+    const T cik = c_s > T(0) ? T(1) : T(0);
+    a = fabs(a_s);
+    c = fabs(c_s);
+    mi = cjk * (cij + cik);
+    mj = cik * (cij + cjk);
+    mk = cij * (cik + cjk);
+  }
+  const T X = a + b - c, Y = a - b + c, Z = b + c - a;
+  const T s = X * Y * Z;
+  const T abc = a * b * c;
+  const T t = uij * uik * ujk;
+  const T d = T(1) + T(6) * t;
+  const T inv = T(1) / (abc * d);
+  const T Q = inv * d;
+  const T f = inv * abc;
+  const T psf = Pij * Pik * Pjk * f;
+  const T ang = T(0.375) * s * Q + T(1);
+  const T e = ang * psf;
+  if (!GRAD) {
+    accH += mj * e;
+    accL += mk * e;
+  } else {
+    const T W = gi * mi + gj * mj + gk * mk;
+    const T dsdb = Y * Z - X * Z + X * Y;
+    const T common = e * (T(-2.5) + T(3) * alp3 * f * t) + psf;
+    const T de = common * inv_b + T(0.375) * psf * Q * dsdb;
+    accG += W * e;
+    accD += W * de;
+  }
+}
+
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int cap = A.caps[A.cls];
+  const SmallLayout L = small_layout<T, GRAD>(cap);
+  T* const pa = reinterpret_cast<T*>(smem + L.planes);
+  T* const pP = pa + L.cpairs;
+  T* const pu = pP + L.cpairs;
+  double* const wtmp = reinterpret_cast<double*>(smem + L.planes);  // aliases the planes
+  T* const Aq = reinterpret_cast<T*>(smem + L.aq);
+  T* const A0 = reinterpret_cast<T*>(smem + L.a0);
+  T* const Bq = reinterpret_cast<T*>(smem + L.bq);
+  T* const B0 = reinterpret_cast<T*>(smem + L.b0);
+  T* const at = reinterpret_cast<T*>(smem + L.atoms);
+  T* const wt = reinterpret_cast<T*>(smem + L.wts);
+  int* const zs = reinterpret_cast<int*>(smem + L.ints);
+  int* const idx = zs + cap;
+  int* const misc = idx + cap;  // [0]=work item, [1]=n, [2]=any_open, [3]=bad
+#define ATOM(k) (at + (k) * cap)
+#define WT(k) (wt + (k) * NREF * cap)
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31;
+  const Par<T>& P = A.par;
+  const Tables<T>& tab = A.tab;
+  const int range_begin = A.wk.class_range[2 * A.cls];
+  const int range_end = A.wk.class_range[2 * A.cls + 1];
+
+  while (true) {
+    __syncthreads();  // previous structure fully written, misc[] reusable
+    if (tid == 0) misc[0] = atomicAdd(&A.wk.queue[A.cls], 1);
+    __syncthreads();
+    const int item = range_begin + misc[0];
+    if (item >= range_end) break;
+    const int b = A.wk.order[item];
+    const int64_t* zrow = A.numbers + (size_t)b * A.nat;
+
+    // ---- phase 0: compact real atoms (numbers != 0), zero padded outputs ----
+    if (tid < 32) {
+      int count = 0, bad = 0;
+      for (int base = 0; base < A.nat; base += 32) {
+        const int src = base + lane;
+        long long zv = src < A.nat ? zrow[src] : 0;
+        const bool real = zv != 0;
+        if (real && (zv < 0 || zv >= NELEM)) {
+          bad = 1;
+          zv = 1;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, real);
+        const int dst = count + __popc(m & ((1u << lane) - 1u));
+        if (real && dst < cap) {
+          idx[dst] = src;
+          zs[dst] = (int)zv;
+        }
+        count += __popc(m);
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0) {
+        misc[1] = count <= cap ? count : 0;
+        misc[2] = 0;
+        misc[3] = count > cap;
+        if (bad) atomicOr(A.wk.status, D4B200_STATUS_BAD_NUMBER);
+        if (count > cap) atomicOr(A.wk.status, D4B200_STATUS_TOO_LARGE);
+      }
+    }
+    __syncthreads();
+    const bool skip = misc[3] != 0;
+    for (int t = tid; t < A.nat; t += nthr) {
+      if (zrow[t] == 0 || skip) {
+        const size_t o = (size_t)b * A.nat + t;
+        if (!GRAD) {
+          A.energy[o] = T(0);
+          if (A.cn_out) A.cn_out[o] = T(0);
+        } else {
+          if (A.grad) {
+            A.grad[3 * o] = T(0);
+            A.grad[3 * o + 1] = T(0);
+            A.grad[3 * o + 2] = T(0);
+          }
+          if (A.gradq) A.gradq[o] = T(0);
+        }
+      }
+    }
+    __syncthreads();
+    const int n = misc[1];
+    const int np = n * (n - 1) / 2;
+
+    for (int i = tid; i < n; i += nthr) {
+      const size_t o = (size_t)b * A.nat + idx[i];
+      const int z = zs[i];
+      ATOM(AT_X)[i] = A.pos[3 * o];
+      ATOM(AT_Y)[i] = A.pos[3 * o + 1];
+      ATOM(AT_Z)[i] = A.pos[3 * o + 2];
+      ATOM(AT_Q)[i] = A.q[o];
+      ATOM(AT_RCOV)[i] = tab.rcov[z];
+      ATOM(AT_R4R2)[i] = tab.r4r2[z];
+      ATOM(AT_SQ)[i] = tab.sqrt_r4r2[z];
+      if (GRAD) ATOM(AT_G)[i] = A.gin ? A.gin[o] : T(1);
+    }
+    __syncthreads();
+
+    // ---- phase 1: coordination number (tad_mctc cn_d4 / erf_count) ----------
+    for (int p = tid; p < np; p += nthr) {
+      int i, j;
+      pair_decode(p, i, j);
+      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+      const T r2 = dx * dx + dy * dy + dz * dz;
+      T cf = T(0);
+      if (r2 <= P.cn_sq) {
+        const T r = d4_sqrt(r2);
+        const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
+        cf = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(T(7.5) * (r / r0 - T(1)));
+      }
+      pu[p] = cf;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) {
+      const T c = row_sum(pu, i, n);
+      ATOM(AT_CN)[i] = c;
+      if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = c;
+    }
+    __syncthreads();
+
+    // ---- phase 2: Gaussian weights (float64 always) x zeta -----------------
+    // model/d4.py:137-228; max-shifted exponentials instead of pow(exp(-d^2), k wf).
+    double* const warg = wtmp;
+    double* const wS = wtmp + NREF * cap;
+    double* const wdS = wtmp + 2 * NREF * cap;
+    for (int t = tid; t < NREF * n; t += nthr) {
+      const int i = t / NREF, a = t - i * NREF;
+      const int z = zs[i];
+      const double d = (double)ATOM(AT_CN)[i] - tab.refcn[z * NREF + a];
+      warg[t] = tab.refc[z * NREF + a] > 0 ? P.wf * d * d : 1e300;
+    }
+    __syncthreads();
+    for (int t = tid; t < NREF * n; t += nthr) {
+      const int i = t / NREF, a = t - i * NREF;
+      const int z = zs[i];
+      const int rc = tab.refc[z * NREF + a];
+      double shift = 1e300;
+#pragma unroll
+      for (int aa = 0; aa < NREF; ++aa) shift = fmin(shift, warg[i * NREF + aa]);
+      double S = 0.0, dS = 0.0;
+      if (rc > 0) {
+        const double arg = warg[t];
+        const double d = (double)ATOM(AT_CN)[i] - tab.refcn[z * NREF + a];
+        for (int k = 1; k <= rc; ++k) {
+          const double e = exp(-((double)k * arg - shift));
+          S += e;
+          dS += -2.0 * (double)k * P.wf * d * e;
+        }
+      }
+      wS[t] = S;
+      wdS[t] = dS;
+    }
+    __syncthreads();
+    for (int t = tid; t < NREF * n; t += nthr) {
+      const int i = t / NREF, a = t - i * NREF;
+      const int z = zs[i];
+      double norm = 0.0, dnorm = 0.0;
+#pragma unroll
+      for (int aa = 0; aa < NREF; ++aa) {
+        norm += wS[i * NREF + aa];
+        dnorm += wdS[i * NREF + aa];
+      }
+      double gw = 0.0, dgw = 0.0;
+      if (norm > 0.0) {
+        gw = wS[t] / norm;
+        dgw = (wdS[t] - gw * dnorm) / norm;
+      }
+      double zeta = 0.0, dzeta = 0.0;
+      if (tab.refc[z * NREF + a] > 0) {
+        const double gam = tab.gamgc[z];
+        const double qref = tab.refq[z * NREF + a];
+        const double qmod = (double)ATOM(AT_Q)[i] + tab.zeff[z];
+        if (qmod > 0.0) {
+          const double qe = qmod - (double)d4_eps<T>();
+          const double scale = exp(gam * (1.0 - qref / qe));
+          zeta = exp(P.ga * (1.0 - scale));
+          dzeta = -P.ga * gam * scale * zeta * qref / (qe * qe);
+        } else {
+          zeta = exp(P.ga);
+        }
+      }
+      const double z0 = tab.zeta0[z * NREF + a];
+      WT(WT_Q)[t] = (T)(zeta * gw);
+      WT(WT_0)[t] = (T)(z0 * gw);
+      if (GRAD) {
+        WT(WT_ZGD)[t] = (T)(zeta * dgw);
+        WT(WT_Z0GD)[t] = (T)(z0 * dgw);
+        WT(WT_DZG)[t] = (T)(dzeta * gw);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 3: weighted polarizability vectors A_i[w] -------------------
+    for (int t = tid; t < NFREQ * n; t += nthr) {
+      const int i = t / NFREQ, w = t - i * NFREQ;
+      const T* al = tab.alpha_w + (size_t)zs[i] * NREF * NFREQ + w;
+      T sq = T(0), s0 = T(0);
+#pragma unroll
+      for (int a = 0; a < NREF; ++a) {
+        const T av = al[a * NFREQ];
+        sq += WT(WT_Q)[i * NREF + a] * av;
+        s0 += WT(WT_0)[i * NREF + a] * av;
+      }
+      Aq[w * cap + i] = sq;
+      A0[w * cap + i] = s0;
+    }
+    __syncthreads();
+
+    // ---- phase 4: two-body energy (twobody.py:134-201, rational damping) ---
+    if (!GRAD) {
+      for (int p = tid; p < np; p += nthr) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        T e = T(0);
+        if (r2 <= P.disp2_sq) {
+          T c6 = T(0);
+#pragma unroll
+          for (int w = 0; w < NFREQ; ++w) c6 += Aq[w * cap + i] * Aq[w * cap + j];
+          const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
+          const T qq = T(3) * ATOM(AT_R4R2)[i] * ATOM(AT_R4R2)[j];
+          const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+          const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+          T F = P.s6 / (r6 + R6) + P.s8 * qq / (r8 + R8);
+          if (P.s10k != T(0)) F += P.s10k * qq * qq / (r8 * r2 + R8 * R2);
+          e = c6 * F;
+        }
+        pP[p] = e;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nthr) ATOM(AT_E)[i] = T(-0.5) * row_sum(pP, i, n);
+      __syncthreads();
+    }
+
+    // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
+    if (P.has_atm) {
+      for (int p = tid; p < np; p += nthr) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        const T r = d4_sqrt(r2);
+        T c6 = T(0);
+#pragma unroll
+        for (int w = 0; w < NFREQ; ++w) c6 += A0[w * cap + i] * A0[w * cap + j];
+        const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
+        const bool inside = r2 <= P.disp3_sq;
+        if (!inside) misc[2] = 1;
+        pa[p] = inside ? r2 : -r2;
+        pP[p] = P.fac9 * d4_sqrt(fabs(c6)) / (r2 * r);
+        pu[p] = d4_pow(R0 / r, P.alp3);
+      }
+      __syncthreads();
+      const bool open = misc[2] != 0;
+
+      // ---- phase 6: triple loop, one thread per owner pair (j,k) -----------
+      // Every unordered triple is visited from each of its three pairs; the
+      // per-pair sums need no inter-thread communication.
+      // results are parked in an L2-resident per-CTA scratch until every thread
+      // is done reading the stash, then copied over the (now dead) planes
+      T* const out0 = A.scratch + (size_t)blockIdx.x * 2 * L.cpairs;
+      T* const out1 = out0 + L.cpairs;
+      for (int p = tid; p < np; p += nthr) {
+        int j, k;
+        pair_decode(p, j, k);
+        const T bs = pa[p];
+        const T bb = fabs(bs);
+        const T cjk = bs > T(0) ? T(1) : T(0);
+        const T Pjk = pP[p], ujk = pu[p];
+        const T inv_b = T(1) / bb;
+        const T gj = GRAD ? ATOM(AT_G)[j] : T(0), gk = GRAD ? ATOM(AT_G)[k] : T(0);
+        const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
+        T accH = T(0), accL = T(0), accG = T(0), accD = T(0);
+#define VISIT(OPENF, PIJ, PIK)                                                                  \
+  triple_visit<T, GRAD, OPENF>(pa[PIJ], pP[PIJ], pu[PIJ], pa[PIK], pP[PIK], pu[PIK], bb, cjk, \
+                               Pjk, ujk, inv_b, P.alp3, GRAD ? ATOM(AT_G)[i] : T(0), gj, gk,  \
+                               accH, accL, accG, accD)
+        if (!open) {
+          for (int i = 0; i < k; ++i) VISIT(false, tj + i, tk + i);
+          for (int i = k + 1; i < j; ++i) VISIT(false, tj + i, i * (i - 1) / 2 + k);
+          for (int i = j + 1; i < n; ++i) VISIT(false, i * (i - 1) / 2 + j, i * (i - 1) / 2 + k);
+        } else {
+          for (int i = 0; i < k; ++i) VISIT(true, tj + i, tk + i);
+          for (int i = k + 1; i < j; ++i) VISIT(true, tj + i, i * (i - 1) / 2 + k);
+          for (int i = j + 1; i < n; ++i) VISIT(true, i * (i - 1) / 2 + j, i * (i - 1) / 2 + k);
+        }
+#undef VISIT
+        out0[p] = GRAD ? accG : accH;  // !GRAD: share of the higher-index atom
+        out1[p] = GRAD ? accD : accL;  // !GRAD: share of the lower-index atom
+      }
+      __syncthreads();  // all reads of the stash done -> planes become outputs
+      for (int p = tid; p < np; p += nthr) {  // same thread wrote out0/out1[p]
+        pP[p] = out0[p];
+        pu[p] = out1[p];
+      }
+      __syncthreads();
+      if (!GRAD) {
+        for (int i = tid; i < n; i += nthr) {
+          T s = T(0);
+          const int ti = i * (i - 1) / 2;
+          for (int j = 0; j < i; ++j) s += pP[ti + j];
+          for (int j = i + 1; j < n; ++j) s += pu[j * (j - 1) / 2 + i];
+          ATOM(AT_E)[i] += T(0.5) * s;
+        }
+        __syncthreads();
+      }
+    } else if (GRAD) {
+      for (int p = tid; p < np; p += nthr) {
+        pP[p] = T(0);
+        pu[p] = T(0);
+      }
+      __syncthreads();
+    }
+
+    if (!GRAD) {
+      for (int i = tid; i < n; i += nthr) A.energy[(size_t)b * A.nat + idx[i]] = ATOM(AT_E)[i];
+      continue;
+    }
+
+    // =================== gradient back-propagation ===========================
+    // phase 7: per-pair coefficients
+    //   pa <- G2 F          (dL/dC6q)
+    //   pP <- Gamma/(2 C60) (dL/dC60)
+    //   pu <- 2 D + G2 C6q F'/r   (radial force coefficient, CN chain added later)
+    for (int p = tid; p < np; p += nthr) {
+      int i, j;
+      pair_decode(p, i, j);
+      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+      const T r2 = dx * dx + dy * dy + dz * dz;
+      T c6q = T(0), c60 = T(0);
+#pragma unroll
+      for (int w = 0; w < NFREQ; ++w) {
+        c6q += Aq[w * cap + i] * Aq[w * cap + j];
+        c60 += A0[w * cap + i] * A0[w * cap + j];
+      }
+      const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
+      T coefq = T(0), fc = T(2) * pu[p];
+      if (r2 <= P.disp2_sq) {
+        const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
+        const T qq = T(3) * ATOM(AT_R4R2)[i] * ATOM(AT_R4R2)[j];
+        const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+        const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+        const T t6 = T(1) / (r6 + R6), t8 = T(1) / (r8 + R8);
+        T F = P.s6 * t6 + P.s8 * qq * t8;
+        // dF/dr / r
+        T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
+        if (P.s10k != T(0)) {
+          const T t10 = T(1) / (r8 * r2 + R8 * R2);
+          F += P.s10k * qq * qq * t10;
+          dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
+        }
+        coefq = G2 * F;
+        fc += G2 * c6q * dF;
+      }
+      pa[p] = coefq;
+      pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
+      pu[p] = fc;
+    }
+    __syncthreads();
+    // phase 8: B_i[w] = sum_j coef_ij A_j[w]
+    for (int t = tid; t < NFREQ * n; t += nthr) {
+      const int w = t / n, i = t - w * n;
+      const int ti = i * (i - 1) / 2;
+      T sq = T(0), s0 = T(0);
+      for (int j = 0; j < i; ++j) {
+        sq += pa[ti + j] * Aq[w * cap + j];
+        s0 += pP[ti + j] * A0[w * cap + j];
+      }
+      for (int j = i + 1; j < n; ++j) {
+        const int pj = j * (j - 1) / 2 + i;
+        sq += pa[pj] * Aq[w * cap + j];
+        s0 += pP[pj] * A0[w * cap + j];
+      }
+      Bq[w * cap + i] = sq;
+      B0[w * cap + i] = s0;
+    }
+    __syncthreads();
+    // phase 9: project on the references -> dL/dcn_i, dL/dq_i
+    T* const tcn = pa;                // [7n] partial dL/dcn (pa is free again)
+    T* const tq = pa + NREF * cap;    // [7n] partial dL/dq
+    for (int t = tid; t < NREF * n; t += nthr) {
+      const int i = t / NREF, a = t - i * NREF;
+      const T* al = tab.alpha_w + ((size_t)zs[i] * NREF + a) * NFREQ;
+      T pq = T(0), p0 = T(0);
+#pragma unroll
+      for (int w = 0; w < NFREQ; ++w) {
+        const T av = al[w];
+        pq += av * Bq[w * cap + i];
+        p0 += av * B0[w * cap + i];
+      }
+      tcn[t] = WT(WT_ZGD)[t] * pq + WT(WT_Z0GD)[t] * p0;
+      tq[t] = WT(WT_DZG)[t] * pq;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) {
+      T sc = T(0), sq = T(0);
+#pragma unroll
+      for (int a = 0; a < NREF; ++a) {
+        sc += tcn[i * NREF + a];
+        sq += tq[i * NREF + a];
+      }
+      ATOM(AT_DCN)[i] = sc;
+      ATOM(AT_DQ)[i] = sq;
+    }
+    __syncthreads();
+    // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
+    for (int p = tid; p < np; p += nthr) {
+      int i, j;
+      pair_decode(p, i, j);
+      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+      const T r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 <= P.cn_sq) {
+        const T r = d4_sqrt(r2);
+        const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
+        const T xx = T(7.5) * (r / r0 - T(1));
+        const T dcn = -tab.den[zs[i] * NELEM + zs[j]] * T(7.5) * T(0.5641895835477563) / r0 *
+                      d4_exp(-xx * xx);
+        pu[p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn / r;
+      }
+    }
+    __syncthreads();
+    // phase 11: gather forces
+    for (int i = tid; i < n; i += nthr) {
+      const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
+      T fx = T(0), fy = T(0), fz = T(0);
+      const int ti = i * (i - 1) / 2;
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const T c = j < i ? pu[ti + j] : pu[j * (j - 1) / 2 + i];
+        fx += c * (xi - ATOM(AT_X)[j]);
+        fy += c * (yi - ATOM(AT_Y)[j]);
+        fz += c * (zi - ATOM(AT_Z)[j]);
+      }
+      const size_t o = (size_t)b * A.nat + idx[i];
+      if (A.grad) {
+        A.grad[3 * o] = fx;
+        A.grad[3 * o + 1] = fy;
+        A.grad[3 * o + 2] = fz;
+      }
+      if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
+    }
+  }
+#undef ATOM
+#undef WT
+}
+
+}  // namespace d4b200

@@ -1,0 +1,320 @@
+"""
+Functional API: ``dftd4`` and ``get_properties`` with the reference's
+signatures (``/root/reference/src/tad_dftd4/disp.py:44-197``), executed by the
+sm_100a kernels behind the C ABI of ``include/d4b200.h``.
+
+What the reference does in ``Disp.calculate`` (``dispersion/base.py:285-431``)
+-- validation, defaults, model construction, CN, two-body + ATM term loop --
+collapses into input validation (same exception types) plus ONE C call; forces
+come from a custom ``torch.autograd.Function`` whose backward is the fused
+analytic-gradient kernel (the reference differentiates its dense tape,
+``examples/forces.py:47-50``).
+
+There is no CPU path and no PyTorch fallback: tensors must live on a B200.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib, defaults
+from .cutoff import Cutoff
+from .damping import Param, RationalDamping
+from .tables import build_tables
+
+__all__ = ["dftd4", "get_properties", "set_checks", "last_launch_count"]
+
+Tensor = torch.Tensor
+
+_ALLOWED_MODELS = ("d3", "d4", "d4s", "d5")
+_CHECKS = True
+
+
+def set_checks(enabled: bool) -> None:
+    """Enable/disable the per-call device status read-back (one stream sync).
+
+    With checks on (default) an atomic number outside 1..103 or a structure the
+    kernels cannot handle raises; with checks off the call is fully
+    asynchronous."""
+    global _CHECKS
+    _CHECKS = bool(enabled)
+
+
+def last_launch_count() -> int:
+    """Kernel launches issued by the last energy/gradient call of this thread."""
+    return int(_lib.load().d4b200_last_launch_count())
+
+
+# ---------------------------------------------------------------------------
+# per-device engine: tables handle + workspace cache
+# ---------------------------------------------------------------------------
+class _Engine:
+    _cache: dict[tuple[int, float, float], "_Engine"] = {}
+
+    def __init__(self, device: torch.device, ga: float, gc: float):
+        lib = _lib.load()
+        tab = build_tables(ga, gc)
+        f64 = np.ascontiguousarray(tab.f64_blob())
+        i32 = np.ascontiguousarray(tab.i32_blob())
+        handle = C.c_void_p()
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        _lib.check(
+            lib.d4b200_tables_create(
+                index, f64.ctypes.data, f64.size, i32.ctypes.data, i32.size, ga, gc, C.byref(handle)
+            ),
+            "d4b200_tables_create",
+        )
+        self.lib = lib
+        self.handle = handle
+        self.device = torch.device("cuda", index)
+        self._ws: Tensor | None = None
+
+    @classmethod
+    def get(cls, device: torch.device, ga: float, gc: float) -> "_Engine":
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (index, float(ga), float(gc))
+        eng = cls._cache.get(key)
+        if eng is None:
+            eng = cls._cache[key] = cls(device, ga, gc)
+        return eng
+
+    def workspace(self, nbatch: int, nat: int) -> Tensor:
+        need = int(self.lib.d4b200_workspace_bytes(nbatch, nat))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _status(self, ws: Tensor, stream: int) -> None:
+        bits = C.c_int(0)
+        _lib.check(self.lib.d4b200_status(ws.data_ptr(), stream, C.byref(bits)), "d4b200_status")
+        if bits.value & 1:
+            raise ValueError("numbers contains an atomic number outside 1..103 (0 = padding).")
+        if bits.value & 2:
+            raise NotImplementedError(
+                "a structure is larger than the one-CTA-per-structure kernels support "
+                "for this dtype; the tiled large-system path handles it"
+            )
+
+    def energy(self, par: _lib.Params, numbers: Tensor, positions: Tensor, q: Tensor,
+               want_cn: bool = False) -> tuple[Tensor, Tensor | None]:  # fmt: skip
+        nbatch, nat = numbers.shape
+        energy = torch.empty_like(q)
+        cn = torch.empty_like(q) if want_cn else None
+        ws = self.workspace(nbatch, nat)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = self.lib.d4b200_energy_f64 if positions.dtype == torch.float64 else self.lib.d4b200_energy_f32
+        _lib.check(
+            fn(self.handle, C.byref(par), nbatch, nat, numbers.data_ptr(), positions.data_ptr(),
+               q.data_ptr(), energy.data_ptr(), cn.data_ptr() if cn is not None else None,
+               ws.data_ptr(), ws.numel(), stream),
+            "d4b200_energy",
+        )  # fmt: skip
+        if _CHECKS:
+            self._status(ws, stream)
+        return energy, cn
+
+    def gradient(self, par: _lib.Params, numbers: Tensor, positions: Tensor, q: Tensor,
+                 gout: Tensor | None, want_pos: bool, want_q: bool):  # fmt: skip
+        nbatch, nat = numbers.shape
+        gpos = torch.empty_like(positions) if want_pos else None
+        gq = torch.empty_like(q) if want_q else None
+        ws = self.workspace(nbatch, nat)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = self.lib.d4b200_gradient_f64 if positions.dtype == torch.float64 else self.lib.d4b200_gradient_f32
+        _lib.check(
+            fn(self.handle, C.byref(par), nbatch, nat, numbers.data_ptr(), positions.data_ptr(),
+               q.data_ptr(), gout.data_ptr() if gout is not None else None,
+               gpos.data_ptr() if gpos is not None else None,
+               gq.data_ptr() if gq is not None else None, ws.data_ptr(), ws.numel(), stream),
+            "d4b200_gradient",
+        )  # fmt: skip
+        if _CHECKS:
+            self._status(ws, stream)
+        return gpos, gq
+
+
+class _D4Function(torch.autograd.Function):
+    """energy[b, i] = D4(numbers, positions, q); backward = fused analytic VJP."""
+
+    @staticmethod
+    def forward(ctx, positions: Tensor, q: Tensor, numbers: Tensor, par, engine: _Engine):
+        energy, _ = engine.energy(par, numbers, positions, q)
+        ctx.save_for_backward(positions, q, numbers)
+        ctx.par = par
+        ctx.engine = engine
+        return energy
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):
+        positions, q, numbers = ctx.saved_tensors
+        need_pos, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gpos, gq = ctx.engine.gradient(
+            ctx.par, numbers, positions, q, gout.contiguous(), need_pos, need_q
+        )
+        return gpos, gq, None, None, None
+
+
+# ---------------------------------------------------------------------------
+# argument handling
+# ---------------------------------------------------------------------------
+def _scalar(v: Any, name: str) -> float:
+    if isinstance(v, Tensor):
+        if v.requires_grad:
+            raise NotImplementedError(
+                f"gradients with respect to the damping parameter '{name}' are not provided "
+                "by the fused kernels (SURVEY.md 8f-3)"
+            )
+        return float(v)
+    return float(v)
+
+
+def _flatten_param(param: Param, cutoff: Cutoff | None, model_id: int, wf: float) -> _lib.Params:
+    """``Param`` -> POD with the reference's defaults (twobody.py:177-178,
+    threebody.py:233-234, functions.py:255-259)."""
+    if param.get("a1") is None or param.get("a2") is None:
+        missing = [k for k in ("a1", "a2") if param.get(k) is None]
+        raise TypeError(f"RationalDamping (order 6) requires keyword(s): {', '.join(missing)}")
+    par = _lib.Params()
+    par.s6 = _scalar(param.get("s6", defaults.S6), "s6")
+    par.s8 = _scalar(param.get("s8", defaults.S8), "s8")
+    par.s9 = _scalar(param.get("s9", defaults.S9), "s9")
+    par.has_s10 = 1 if "s10" in param and param["s10"] is not None else 0
+    par.s10 = _scalar(param["s10"], "s10") if par.has_s10 else 0.0
+    par.a1 = _scalar(param["a1"], "a1")
+    par.a2 = _scalar(param["a2"], "a2")
+    par.alp = _scalar(param.get("alp", defaults.ALP), "alp")
+    par.disp2_cutoff = float(cutoff.disp2) if cutoff is not None else defaults.D4_DISP2_CUTOFF
+    par.disp3_cutoff = float(cutoff.disp3) if cutoff is not None else defaults.D4_DISP3_CUTOFF
+    par.cn_cutoff = defaults.D4_CN_CUTOFF  # Cutoff.cn is not forwarded (dispersion/base.py:390)
+    par.wf = wf
+    par.model = model_id
+    return par
+
+
+def _resolve_model(model: Any) -> tuple[int, float, float, float]:
+    """-> (model id, ga, gc, wf)"""
+    if isinstance(model, str):
+        key = model.casefold()
+        if key not in _ALLOWED_MODELS:
+            raise ValueError(f"Unknown model '{key}'. Please use {', '.join(_ALLOWED_MODELS)}.")
+        if key == "d4":
+            return 0, defaults.GA_DEFAULT, defaults.GC_DEFAULT, defaults.WF_DEFAULT
+        if key == "d4s":
+            return 1, defaults.GA_DEFAULT, defaults.GC_DEFAULT, defaults.WF_DEFAULT
+        raise NotImplementedError(f"model '{key}' is outside the accelerated D4 hot path")
+    name = type(model).__name__
+    if name in ("D4Model", "D4SModel"):
+        if getattr(model, "ref_charges", "eeq") != "eeq":
+            raise NotImplementedError("only ref_charges='eeq' is accelerated")
+        wf = getattr(model, "wf", defaults.WF_DEFAULT)
+        wf = float(wf) if name == "D4Model" else defaults.WF_DEFAULT
+        return (0 if name == "D4Model" else 1), float(model.ga), float(model.gc), wf
+    raise NotImplementedError(f"model instance of type {name} is outside the accelerated D4 hot path")
+
+
+def _eeq_charges(numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: Cutoff) -> Tensor:
+    try:
+        from tad_multicharge import get_eeq_charges  # type: ignore
+    except ImportError as e:  # pragma: no cover - depends on the environment
+        raise ImportError(
+            "EEQ charges are not part of the accelerated hot path: install tad-multicharge or "
+            "pass atomic partial charges explicitly via `q=`."
+        ) from e
+    return get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)
+
+
+def dftd4(
+    numbers: Tensor,
+    positions: Tensor,
+    charge: Tensor | float | int,
+    param: Param,
+    *,
+    model: Any = "d4",
+    rcov: Tensor | None = None,
+    r4r2: Tensor | None = None,
+    rvdw: Tensor | None = None,
+    q: Tensor | None = None,
+    cutoff: Cutoff | None = None,
+    cn_function: Any = None,
+    counting_function: Any = None,
+    damping_function: Any = None,
+) -> Tensor:
+    """Atom-resolved DFT-D4 dispersion energy, shape ``(..., nat)``.
+
+    Same arguments, padding convention (``numbers == 0``), return value and
+    exception types as ``tad_dftd4.dftd4`` (``disp.py:44-146``).  Only the
+    default method is accelerated (erf-count ``cn_d4``, rational damping, BJ
+    radii, approximate C9, default element radii); any other plugin raises
+    ``NotImplementedError`` instead of silently falling back.
+    """
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError(
+            f"Shape of positions ({positions.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
+    model_id, ga, gc, wf = _resolve_model(model)
+    for name, val in (("covalent radii", rcov), ("expectation values r4r2", r4r2)):
+        if val is not None and numbers.shape != val.shape:
+            raise ValueError(
+                f"Shape of {name} ({val.shape}) is not consistent with atomic numbers ({numbers.shape})."
+            )
+    if rvdw is not None and numbers.shape != rvdw.shape[:-1]:
+        raise ValueError(
+            f"Shape of van der Waals radii ({rvdw.shape}) is not "
+            f"consistent with atomic numbers ({numbers.shape}).",
+        )
+    if rcov is not None or r4r2 is not None or rvdw is not None:
+        raise NotImplementedError("custom rcov/r4r2/rvdw are outside the accelerated hot path")
+    for name, fn in (("cn_function", cn_function), ("counting_function", counting_function)):
+        if fn is not None and getattr(fn, "__name__", "") not in ("cn_d4", "erf_count", "cn_d4_cuda"):
+            raise NotImplementedError(f"custom {name} is outside the accelerated hot path")
+    if damping_function is not None and type(damping_function).__name__ != "RationalDamping":
+        raise NotImplementedError("only RationalDamping is accelerated")
+    if positions.dtype not in (torch.float64, torch.float32):
+        raise NotImplementedError(f"dtype {positions.dtype} is not supported (float64/float32)")
+    if positions.device.type != "cuda":
+        raise RuntimeError(
+            "tad_dftd4_b200 runs on B200 GPUs only (no CPU fallback): move numbers/positions "
+            f"to a CUDA device (got {positions.device})."
+        )
+    if model_id == 1:
+        raise NotImplementedError("the D4S model is not yet available in the fused kernels")
+
+    if cutoff is None:
+        cutoff = Cutoff(device=positions.device, dtype=positions.dtype)
+    if q is None:
+        chg = charge if isinstance(charge, Tensor) else torch.tensor(charge)
+        q = _eeq_charges(numbers, positions, chg.to(positions.device, positions.dtype), cutoff)
+    if numbers.shape != q.shape:
+        raise ValueError(
+            f"Shape of atomic charges ({q.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
+    par = _flatten_param(param, cutoff, model_id, wf)
+
+    engine = _Engine.get(positions.device, ga, gc)
+    nat = numbers.shape[-1]
+    batch_shape = numbers.shape[:-1]
+    num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
+    pos2 = positions.reshape(-1, nat, 3).contiguous()
+    q2 = q.to(positions.dtype).reshape(-1, nat).contiguous()
+    with torch.cuda.device(positions.device):
+        energy = _D4Function.apply(pos2, q2, num2, par, engine)
+    return energy.reshape(*batch_shape, nat)
+
+
+def get_properties(
+    numbers: Tensor,
+    positions: Tensor,
+    charge: Tensor | float | int | None = None,
+    cutoff: Cutoff | None = None,
+    *,
+    q: Tensor | None = None,
+):
+    """(cn, q, c6, alpha) as ``tad_dftd4.get_properties`` (``disp.py:149-197``)."""
+    raise NotImplementedError("get_properties: device kernel not built yet (SURVEY.md 8f-1)")

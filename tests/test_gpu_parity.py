@@ -1,0 +1,84 @@
+"""
+Parity of the CUDA path (through the public API -> C ABI) with the committed
+golden vectors of the reference and with the oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: FP64 energy
+<= 1e-10 relative (to the largest atomic energy of the structure / to the total
+energy), FP64 gradient <= 1e-9 absolute; FP32 <= 1e-5 relative.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, as_torch, load_golden
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL64 = 1e-10
+G_ATOL64 = 1e-9
+RTOL32 = 1e-5
+
+
+def _d4():
+    import tad_dftd4_b200 as d4
+
+    return d4
+
+
+def _run(case, dtype, model="d4", grad=True):
+    d4 = _d4()
+    dev = torch.device("cuda:0")
+    numbers, positions, q = as_torch(case, dev, dtype)
+    pos = positions.clone().requires_grad_(grad)
+    cut = d4.Cutoff(**case["cutoff"], device=dev, dtype=dtype) if case["cutoff"] else None
+    e = d4.dftd4(numbers, pos, 0.0, dict(case["param"]), q=q, model=model, cutoff=cut)
+    g = None
+    if grad:
+        (g,) = torch.autograd.grad(e.sum(), pos)
+        g = g.cpu().numpy().astype(np.float64)
+    return e.detach().cpu().numpy().astype(np.float64), g
+
+
+def _small(name):
+    n = load_golden(name)["numbers"]
+    return (n != 0).sum(-1).max()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_energy_f64(name):
+    case = load_golden(name)
+    if _small(name) > 112:
+        pytest.skip("beyond the FP64 small-family limit")
+    e, _ = _run(case, torch.float64, grad=False)
+    ref = case["energy_d4"]
+    scale = np.abs(ref).max()
+    assert e.shape == ref.shape
+    assert np.abs(e - ref).max() / scale < E_RTOL64
+    tot, rtot = e.sum(-1), ref.sum(-1)
+    assert np.all(np.abs(tot - rtot) <= E_RTOL64 * np.abs(rtot) + 1e-300)
+    assert np.all(e[case["numbers"] == 0] == 0.0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gradient_f64(name):
+    case = load_golden(name)
+    if _small(name) > 100:
+        pytest.skip("beyond the FP64 gradient small-family limit")
+    _, g = _run(case, torch.float64)
+    ref = case["grad_d4"]
+    assert g.shape == ref.shape
+    assert np.abs(g - ref).max() < G_ATOL64
+    assert np.all(g[case["numbers"] == 0] == 0.0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_energy_and_gradient_f32(name):
+    case = load_golden(name)
+    e, g = _run(case, torch.float32)
+    ref, gref = case["energy_d4"], case["grad_d4"]
+    tot, rtot = e.sum(-1), ref.sum(-1)
+    assert np.all(np.abs(tot - rtot) <= RTOL32 * np.abs(rtot) + 1e-12)
+    assert np.abs(e - ref).max() / np.abs(ref).max() < 5 * RTOL32
+    assert np.abs(g - gref).max() < 5 * RTOL32 * max(np.abs(gref).max(), 1e-3)

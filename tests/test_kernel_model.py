@@ -1,0 +1,40 @@
+"""The algebra used by the CUDA kernels (tests/kernel_model.py) vs the oracle."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import d4_oracle as orc
+from helpers import as_torch, load_golden
+from kernel_model import energy_and_gradient
+
+CASES = ["sih4_tpssh", "lih_tpssh", "single_pbe0", "single_tpssh_s10", "nan17", "organic_5",
+         "organic_20", "tight_cutoffs", "big_charges", "chain150"]  # fmt: skip
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_model_matches_golden(name):
+    case = load_golden(name)
+    e, grad, dq, cn = energy_and_gradient(
+        case["numbers"], case["positions"], case["q"], case["param"], **case["cutoff"]
+    )
+    eref, gref = case["energy_d4"], case["grad_d4"]
+    assert np.abs(cn - case["cn"]).max() < 1e-12
+    assert np.abs(e - eref).max() / np.abs(eref).max() < 1e-10
+    assert np.abs(grad - gref).max() < 1e-9
+
+
+def test_dq_and_weighted_upstream():
+    """dL/dq and arbitrary upstream weights g_i vs oracle autograd."""
+    case = load_golden("organic_20")
+    numbers, positions, q = as_torch(case)
+    rng = np.random.default_rng(5)
+    g = rng.normal(size=len(case["numbers"]))
+    pos = positions.clone().requires_grad_(True)
+    qq = q.clone().requires_grad_(True)
+    e = orc.dftd4(numbers, pos, case["param"], qq)
+    gp, gq = torch.autograd.grad((e * torch.from_numpy(g)).sum(), (pos, qq))
+    _, grad, dq, _ = energy_and_gradient(case["numbers"], case["positions"], case["q"], case["param"], g=g)
+    assert np.abs(grad - gp.numpy()).max() < 1e-9
+    assert np.abs(dq - gq.numpy()).max() < 1e-9
