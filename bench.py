@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline measurement of the B200-native DFT-D4 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload c2|c3] [--dtype f64|f32]
+
+A *step* is one pass of the hot path over one batch of synthetic structures:
+
+* ``c2`` (default, BASELINE.json configs[1]): 4096 synthetic 20-60 atom
+  organics, atom-resolved D4 energy (two-body + ATM), PBE0-D4 parameters, FP64;
+* ``c3`` (configs[2]): 1024 synthetic 100-atom molecules, energy + analytic
+  gradient (``autograd.grad(E.sum(), positions)``).
+
+With ``--gpus N`` (launched under torchrun, one rank per GPU) every rank works
+on its own batch of the same shape (structures are independent: no data-path
+collective, weak scaling); the reported value is all structures of all ranks
+divided by the slowest rank's device time.
+
+Output: ONE JSON line on rank 0 (see DESIGN.md "Measurement").  ``value`` is
+measured with inputs resident in HBM, ``e2e`` through the public API from
+pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+
+``--impl reference`` times the CPU implementation of the same path on the
+host cores: the reference itself cannot be installed here (its dependencies
+tad-mctc / tad-multicharge are not in the image), so this arm runs the oracle
+restatement (``oracle/d4_oracle.py``, the reference's dense torch formulation,
+bit-identical to the reference on every golden case) and says so.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+PBE0 = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)  # d4.toml:269 of the reference
+
+# algorithmic flop per unit of work (contract figures)
+F_PCN, F_P2, F_T, F_W = 18, 248, 30, 120
+F_PCN_G, F_P2_G, F_T_G = 30, 320, 90
+
+WORKLOADS = {
+    "c2": dict(nbatch=4096, lo=20, hi=60, seed=2, grad=False,
+               name="4096 synthetic 20-60-atom organics, D4 energy (two-body + ATM), padded to 60"),
+    "c3": dict(nbatch=1024, lo=100, hi=100, seed=3, grad=True,
+               name="1024 synthetic 100-atom molecules, D4 energy + analytic gradient incl. ATM"),
+}  # fmt: skip
+
+
+def oracle():
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import d4_oracle  # noqa: E402  (bench's cpu_baseline / reference arm only)
+
+    return d4_oracle
+
+
+def make_batch(wl: dict, rank: int):
+    orc = oracle()
+    rng = np.random.default_rng(wl["seed"] + 1000 * rank)
+    sizes = rng.integers(wl["lo"], wl["hi"] + 1, size=wl["nbatch"])
+    return orc.organic_batch_parallel(sizes, seed=wl["seed"] + 1000 * rank)
+
+
+def work_counts(numbers: torch.Tensor, grad: bool):
+    n = (numbers != 0).sum(-1).to(torch.float64)
+    pairs = n * (n - 1) / 2
+    triples = n * (n - 1) * (n - 2) / 6
+    flop = (F_PCN + F_P2) * pairs + F_T * triples + F_W * n
+    if grad:
+        flop = flop + (F_PCN_G + F_P2_G) * pairs + F_T_G * triples
+    return n, pairs, triples, flop
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}  # fmt: skip
+
+
+# --------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------
+def cpu_time_sample(wl: dict, numbers, positions, q, nsample: int, chunk: int):
+    """Seconds the dense CPU formulation needs for ``nsample`` structures of the
+    workload (model rebuilt per call like the reference, dispersion/base.py:363)."""
+    orc = oracle()
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    for s in range(0, nsample, chunk):
+        sl = slice(s, min(s + chunk, nsample))
+        if wl["grad"]:
+            orc.energy_and_gradient(numbers[sl], positions[sl], PBE0, q[sl])
+        else:
+            orc.dftd4(numbers[sl], positions[sl], PBE0, q[sl])
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    numbers, positions, q = make_batch(wl, 0)
+    chunk = 8 if wl["grad"] else 64
+    nsample = chunk * (2 if wl["grad"] else 2)
+    times = []
+    for it in range(args.warmup + args.steps):
+        dt = cpu_time_sample(wl, numbers, positions, q, nsample, chunk)
+        if it >= args.warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    value = nsample / sec
+    cores = os.cpu_count() or 1
+    sample = (f"{nsample} structures of the workload per step in chunks of {chunk} "
+              f"(dense N^3 temporaries), float64, torch threads = {torch.get_num_threads()}")  # fmt: skip
+    line = {
+        "impl": "reference",
+        "metric": "D4 dispersion throughput (batched molecules/s)",
+        "value": value, "unit": "molecules/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "parallelism": "host cores"},
+        "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "molecules/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": "reference (tad-dftd4 0.8.0) is not installable here (tad-mctc / tad-multicharge "
+                "absent); timed: oracle/d4_oracle.py, the same dense torch formulation",
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+def run_b200(args, wl, rank, world, local_rank):
+    import tad_dftd4_b200 as d4
+    from tad_dftd4_b200 import _lib
+    from tad_dftd4_b200.disp import _Engine
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    numbers_h, positions_h, q_h = make_batch(wl, rank)
+    positions_h, q_h = positions_h.to(dtype), q_h.to(dtype)
+    nat, pairs, triples, flop = work_counts(numbers_h, wl["grad"])
+    numbers_h, positions_h, q_h = numbers_h.pin_memory(), positions_h.pin_memory(), q_h.pin_memory()
+    numbers, positions, q = numbers_h.to(dev), positions_h.to(dev), q_h.to(dev)
+    d4.set_checks(False)  # fully asynchronous steps; parity is the tests' job
+
+    def step_resident():
+        if wl["grad"]:
+            pos = positions.detach().requires_grad_(True)
+            e = d4.dftd4(numbers, pos, 0.0, PBE0, q=q)
+            (g,) = torch.autograd.grad(e.sum(), pos)
+            return e, g
+        return d4.dftd4(numbers, positions, 0.0, PBE0, q=q), None
+
+    out_e = torch.empty(numbers_h.shape, dtype=dtype).pin_memory()
+    out_g = torch.empty(positions_h.shape, dtype=dtype).pin_memory() if wl["grad"] else None
+
+    def step_e2e():
+        n = numbers_h.to(dev, non_blocking=True)
+        p = positions_h.to(dev, non_blocking=True)
+        qq = q_h.to(dev, non_blocking=True)
+        if wl["grad"]:
+            p.requires_grad_(True)
+            e = d4.dftd4(n, p, 0.0, PBE0, q=qq)
+            (g,) = torch.autograd.grad(e.sum(), p)
+            out_g.copy_(g, non_blocking=True)
+        else:
+            e = d4.dftd4(n, p, 0.0, PBE0, q=qq)
+        out_e.copy_(e.detach(), non_blocking=True)
+
+    h2d = numbers_h.numel() * 8 + (positions_h.numel() + q_h.numel()) * positions_h.element_size()
+    d2h = out_e.numel() * out_e.element_size() + (out_g.numel() * out_g.element_size() if wl["grad"] else 0)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches = 0
+        for s in range(steps):
+            flush.fill_(float(s))  # evict inputs/tables from L2 between timed iterations
+            ev[s][0].record()
+            fn()
+            ev[s][1].record()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = [a.elapsed_time(b) for a, b in ev]
+        return sum(ms), launches
+
+    engine = _Engine.get(dev, 3.0, 2.0)
+    lib = _lib.load()
+    step_resident()  # builds tables / workspace
+    launches_per_step = d4.last_launch_count()
+    if wl["grad"]:
+        # forward + backward: count both calls
+        d4.dftd4(numbers, positions, 0.0, PBE0, q=q)
+        launches_per_step = d4.last_launch_count()
+        pos = positions.detach().requires_grad_(True)
+        e = d4.dftd4(numbers, pos, 0.0, PBE0, q=q)
+        torch.autograd.grad(e.sum(), pos)
+        launches_per_step += d4.last_launch_count()
+
+    with ClockSampler(local_rank) as clocks:
+        total_ms, _ = timed(step_resident, args.steps, args.warmup)
+        e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    clk = clocks.summary()
+
+    # ---- dominant kernel: per-launch duration measured live with CUDA events
+    lib.d4b200_profile_enable(engine.handle, 1)
+    caps = (C.c_int * 4)()
+    lib.d4b200_class_caps(engine.handle, int(dtype == torch.float32), int(wl["grad"]), caps)
+    per_class = [[] for _ in range(4)]
+    for s in range(max(3, min(args.steps, 10))):
+        flush.fill_(1.0)
+        step_resident()
+        ms = (C.c_float * 4)()
+        lib.d4b200_profile_read(engine.handle, ms)
+        for c in range(4):
+            if ms[c] >= 0:
+                per_class[c].append(ms[c])
+    lib.d4b200_profile_enable(engine.handle, 0)
+    class_ms = [statistics.mean(v[1:] if len(v) > 1 else v) if v else 0.0 for v in per_class]
+    lo = 0
+    class_flop = []
+    for c in range(4):
+        sel = (nat >= lo) & (nat <= caps[c]) if caps[c] >= lo else torch.zeros_like(nat, dtype=torch.bool)
+        class_flop.append(float(flop[sel].sum()))
+        lo = caps[c] + 1
+    dom = max(range(4), key=lambda c: class_ms[c])
+
+    peak_tf = C.c_double(0.0)
+    scratch = torch.empty(64 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    lib.d4b200_measure_fp64_peak(engine.handle, scratch.data_ptr(), scratch.numel(),
+                                 torch.cuda.current_stream(dev).cuda_stream, C.byref(peak_tf))  # fmt: skip
+    nominal_tf = 37.2 if dtype == torch.float64 else 74.4
+    peak = peak_tf.value if dtype == torch.float64 else 2 * peak_tf.value
+
+    # ---- reduce over ranks (max time, summed work)
+    stats = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(numbers.shape[0]), float(pairs.sum()), float(triples.sum()),
+                         float(flop.sum())], dtype=torch.float64, device=dev)  # fmt: skip
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms = stats.tolist()
+    nmol, npair, ntrip, nflop = work.tolist()
+    sec_per_step = total_ms / args.steps * 1e-3
+    e2e_sec = e2e_ms / args.steps * 1e-3
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        chunk = 8 if wl["grad"] else 64
+        nsample = chunk * 2
+        sec = cpu_time_sample(wl, numbers_h, positions_h.double(), q_h.double(), nsample, chunk)
+        cpu = {"value": nsample / sec, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {nsample} structures of the workload, chunks of {chunk}, float64, "
+                         f"torch threads = {torch.get_num_threads()} (oracle/d4_oracle.py: the reference's "
+                         "dense torch formulation; the reference itself is not installable here)"}  # fmt: skip
+
+    if rank == 0:
+        achieved = class_flop[dom] / (class_ms[dom] * 1e-3) / 1e12 if class_ms[dom] > 0 else 0.0
+        line = {
+            "metric": "D4 dispersion throughput (batched molecules/s)",
+            "value": nmol / sec_per_step, "unit": "molecules/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": wl["name"], "structures_per_gpu": int(numbers.shape[0]),
+                       "global_batch": int(nmol), "parallelism": f"structure-sharded x{world}, no collective",
+                       "l2": "flushed (256 MB write) between timed iterations",
+                       "param": "PBE0-D4 (s8 1.20065498, a1 0.40085597, a2 5.02928789), explicit charges q"},
+            "pair_terms_per_s": npair / sec_per_step, "triple_terms_per_s": ntrip / sec_per_step,
+            "algorithmic_tflops": nflop / sec_per_step / 1e12,
+            "e2e": {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {
+                "bound": "fp64" if dtype == torch.float64 else "fp32",
+                "kernel": f"small_kernel<{'double' if dtype == torch.float64 else 'float'},"
+                          f"{'grad' if wl['grad'] else 'energy'}> size class <= {caps[dom]} atoms",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": "measured in this run: DFMA chain microbenchmark (d4b200_measure_fp64_peak); "
+                               f"nominal {nominal_tf} TFLOP/s; MEASURED_PEAKS.json has no FP64 entry",
+                "kernel_ms": class_ms[dom], "kernel_algorithmic_flop": class_flop[dom],
+                "all_class_ms": class_ms, "step_share": class_ms[dom] / (sec_per_step * 1e3),
+                "hbm_gbs_algorithmic": (h2d + d2h) / sec_per_step / 1e9,
+            },
+            "cpu_baseline": cpu,
+            "clocks": clk,
+        }  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_b200(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

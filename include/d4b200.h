@@ -119,13 +119,24 @@ int d4b200_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nb
                         float* grad_positions_dev, float* grad_q_dev, void* workspace_dev,
                         size_t workspace_bytes, void* stream);
 
-/* Synchronises ``stream`` and returns the OR of the device status bits that
- * the calls using ``workspace_dev`` recorded since the last query. */
+/* Synchronises ``stream`` and returns the device status bits recorded by the
+ * last energy/gradient call that used ``workspace_dev``. */
 int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);
 
 /* Number of kernel launches the last energy/gradient call on this thread
  * issued (for bench.py's gpu_launches claim). */
 int d4b200_last_launch_count(void);
+
+/* --- measurement hooks used by bench.py (no effect on results) ----------- */
+/* Record CUDA events around every hot-kernel launch of the following calls. */
+int d4b200_profile_enable(d4b200_tables_t tables, int enable);
+/* Duration (ms) of the last call's hot kernel per size class; -1 = not launched. */
+int d4b200_profile_read(d4b200_tables_t tables, float* ms_per_class /*[4]*/);
+/* Inclusive atom-count bounds of the four size classes for a kernel flavour. */
+int d4b200_class_caps(d4b200_tables_t tables, int fp32, int grad, int* caps_out /*[4]*/);
+/* Measured FP64 FMA throughput (TFLOP/s) of the device: roofline denominator. */
+int d4b200_measure_fp64_peak(d4b200_tables_t tables, void* scratch_dev, size_t scratch_bytes,
+                             void* stream, double* tflops_out);
 
 #ifdef __cplusplus
 }

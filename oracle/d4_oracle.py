@@ -491,3 +491,31 @@ def organic_batch(sizes, seed: int):
         z, xyz, qq = organic_blob(int(nat), rng)
         numbers[n, :nat], pos[n, :nat], q[n, :nat] = z, xyz, qq
     return torch.from_numpy(numbers), torch.from_numpy(pos), torch.from_numpy(q)
+
+
+def _blob_job(args):
+    nat, seedseq = args
+    return organic_blob(int(nat), np.random.default_rng(seedseq))
+
+
+def organic_batch_parallel(sizes, seed: int, workers: int | None = None):
+    """Like :func:`organic_batch` but every structure has its own spawned seed,
+    so the batch is reproducible for any worker count (used by bench.py)."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+
+    sizes = [int(s) for s in sizes]
+    seeds = np.random.SeedSequence(seed).spawn(len(sizes))
+    workers = workers or min(32, os.cpu_count() or 1)
+    if workers > 1 and len(sizes) >= 64:
+        with ProcessPoolExecutor(workers) as ex:
+            blobs = list(ex.map(_blob_job, zip(sizes, seeds), chunksize=32))
+    else:
+        blobs = [_blob_job(a) for a in zip(sizes, seeds)]
+    nmax = max(sizes)
+    numbers = np.zeros((len(sizes), nmax), dtype=np.int64)
+    pos = np.zeros((len(sizes), nmax, 3))
+    q = np.zeros((len(sizes), nmax))
+    for n, (z, xyz, qq) in enumerate(blobs):
+        numbers[n, : len(z)], pos[n, : len(z)], q[n, : len(z)] = z, xyz, qq
+    return torch.from_numpy(numbers), torch.from_numpy(pos), torch.from_numpy(q)

@@ -26,6 +26,10 @@ struct d4b200_tables {
   int threads[2][2][NCLASS];
   int grid_per_sm[2][2][NCLASS];
   size_t smem[2][2][NCLASS];
+  // optional per-launch timing (bench.py roofline): events around each class kernel
+  int profile;
+  cudaEvent_t ev[2 * NCLASS];
+  int ev_used[NCLASS];
 };
 
 static thread_local int g_launches = 0;
@@ -243,6 +247,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   k_scatter<<<(nbatch + 255) / 256, 256, 0, st>>>(nbatch, wk);
   g_launches += 3;
 
+  for (int c = 0; c < NCLASS; ++c) h->ev_used[c] = 0;
   SmallArgs<T> A;
   A.numbers = numbers;
   A.pos = pos;
@@ -278,7 +283,10 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
       if (grid > nbatch) grid = nbatch;
       const long gmax = (long)(h->num_sms < MAX_SMS ? h->num_sms : MAX_SMS) * class_occ_cap(c);
       if (grid > gmax) grid = gmax;
+      if (h->profile) cudaEventRecord(h->ev[2 * c], st);
       small_kernel<T, GRAD><<<(unsigned)grid, h->threads[dt][gr][c], h->smem[dt][gr][c], st>>>(A);
+      if (h->profile) cudaEventRecord(h->ev[2 * c + 1], st);
+      h->ev_used[c] = h->profile;
       ++g_launches;
     }
     scratch += sbytes;
@@ -359,6 +367,8 @@ int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
 
 int d4b200_tables_destroy(d4b200_tables_t h) {
   if (!h) return 0;
+  for (int i = 0; i < 2 * NCLASS; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   cudaFree(h->f64);
   cudaFree(h->f32);
   cudaFree(h->i32);
@@ -411,5 +421,78 @@ int d4b200_status(void* ws, void* stream, int* bits) {
 }
 
 int d4b200_last_launch_count(void) { return g_launches; }
+
+int d4b200_profile_enable(d4b200_tables_t h, int enable) {
+  if (!h) return D4B200_EINVAL;
+  if (enable) {
+    for (int i = 0; i < 2 * NCLASS; ++i) {
+      if (!h->ev[i]) {
+        cudaError_t e = cudaEventCreate(&h->ev[i]);
+        if (e != cudaSuccess) return (int)e;
+      }
+    }
+  }
+  h->profile = enable != 0;
+  return 0;
+}
+
+int d4b200_profile_read(d4b200_tables_t h, float* ms_per_class) {
+  if (!h || !ms_per_class) return D4B200_EINVAL;
+  for (int c = 0; c < NCLASS; ++c) {
+    ms_per_class[c] = -1.0f;
+    if (!h->ev_used[c]) continue;
+    cudaError_t e = cudaEventSynchronize(h->ev[2 * c + 1]);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaEventElapsedTime(&ms_per_class[c], h->ev[2 * c], h->ev[2 * c + 1]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+int d4b200_class_caps(d4b200_tables_t h, int fp32, int grad, int* caps_out) {
+  if (!h || !caps_out) return D4B200_EINVAL;
+  for (int c = 0; c < NCLASS; ++c) caps_out[c] = h->caps[fp32 ? 1 : 0][grad ? 1 : 0][c];
+  return 0;
+}
+
+// FP64 vector (DFMA) throughput of the device, measured: the roofline
+// denominator for the FP64-bound kernels (MEASURED_PEAKS.json has no FP64 entry).
+__global__ void k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int d4b200_measure_fp64_peak(d4b200_tables_t h, void* scratch_dev, size_t scratch_bytes,
+                             void* stream, double* tflops_out) {
+  if (!h || !scratch_dev || !tflops_out) return D4B200_EINVAL;
+  const int blocks = h->num_sms * 8, threads = 256, iters = 1 << 15;
+  if (scratch_bytes < (size_t)blocks * threads * sizeof(double)) return D4B200_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    k_dfma_peak<<<blocks, threads, 0, st>>>((double*)scratch_dev, iters);
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) return (int)e;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_out = best;
+  return 0;
+}
 
 }  // extern "C"
