@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
   T* const wt = reinterpret_cast<T*>(smem + L.wts);
   int* const zs = reinterpret_cast<int*>(smem + L.ints);
   int* const idx = zs + cap;
-  int* const misc = idx + cap;  // [0]=work item, [1]=n, [2]=any_open, [3]=bad
+  int* const misc = idx + cap;  // [0]=work item, [1]=n, [2]=any_open, [3]=bad, [4]=chunk counter
 #define ATOM(k) (at + (k) * cap)
 #define WT(k) (wt + (k) * NREF * cap)
 
@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
         misc[1] = count <= cap ? count : 0;
         misc[2] = 0;
         misc[3] = count > cap;
+        misc[4] = 0;
         if (bad) atomicOr(A.wk.status, D4B200_STATUS_BAD_NUMBER);
         if (count > cap) atomicOr(A.wk.status, D4B200_STATUS_TOO_LARGE);
       }
@@ -415,54 +416,140 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       __syncthreads();
       const bool open = misc[2] != 0;
 
-      // ---- phase 6: triple loop, one thread per owner pair (j,k) -----------
-      // Every unordered triple is visited from each of its three pairs; the
-      // per-pair sums need no inter-thread communication.
-      // results are parked in an L2-resident per-CTA scratch until every thread
-      // is done reading the stash, then copied over the (now dead) planes
+      // ---- phase 6: triple loop ---------------------------------------------
+      // per-CTA, L2-resident scratch for per-pair results (the smem planes are
+      // still being read by other warps while results are produced)
       T* const out0 = A.scratch + (size_t)blockIdx.x * 2 * L.cpairs;
       T* const out1 = out0 + L.cpairs;
-      for (int p = tid; p < np; p += nthr) {
-        int j, k;
-        pair_decode(p, j, k);
-        const T bs = pa[p];
-        const T bb = fabs(bs);
-        const T cjk = bs > T(0) ? T(1) : T(0);
-        const T Pjk = pP[p], ujk = pu[p];
-        const T inv_b = T(1) / bb;
-        const T gj = GRAD ? ATOM(AT_G)[j] : T(0), gk = GRAD ? ATOM(AT_G)[k] : T(0);
-        const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
-        T accH = T(0), accL = T(0), accG = T(0), accD = T(0);
-#define VISIT(OPENF, PIJ, PIK)                                                                  \
-  triple_visit<T, GRAD, OPENF>(pa[PIJ], pP[PIJ], pu[PIJ], pa[PIK], pP[PIK], pu[PIK], bb, cjk, \
-                               Pjk, ujk, inv_b, P.alp3, GRAD ? ATOM(AT_G)[i] : T(0), gj, gk,  \
-                               accH, accL, accG, accD)
-        if (!open) {
-          for (int i = 0; i < k; ++i) VISIT(false, tj + i, tk + i);
-          for (int i = k + 1; i < j; ++i) VISIT(false, tj + i, i * (i - 1) / 2 + k);
-          for (int i = j + 1; i < n; ++i) VISIT(false, i * (i - 1) / 2 + j, i * (i - 1) / 2 + k);
-        } else {
-          for (int i = 0; i < k; ++i) VISIT(true, tj + i, tk + i);
-          for (int i = k + 1; i < j; ++i) VISIT(true, tj + i, i * (i - 1) / 2 + k);
-          for (int i = j + 1; i < n; ++i) VISIT(true, i * (i - 1) / 2 + j, i * (i - 1) / 2 + k);
+      if constexpr (GRAD) {
+        // Gradient: one thread per owner pair (j,k), all third atoms i.  Every
+        // triple is visited from each of its three pairs, so the per-pair sums
+        // Gamma (dL/dC60 numerator) and D (dL/d r^2) need no communication.
+        for (int p = tid; p < np; p += nthr) {
+          int j, k;
+          pair_decode(p, j, k);
+          const T bs = pa[p];
+          const T bb = fabs(bs);
+          const T cjk = bs > T(0) ? T(1) : T(0);
+          const T Pjk = pP[p], ujk = pu[p];
+          const T inv_b = T(1) / bb;
+          const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
+          const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
+          T accH = T(0), accL = T(0), accG = T(0), accD = T(0);
+          for (int i = 0; i < n; ++i) {
+            if (i == j || i == k) continue;
+            const int ti = i * (i - 1) / 2;
+            const int pij = i > j ? ti + j : tj + i;
+            const int pik = i > k ? ti + k : tk + i;
+            if (open)
+              triple_visit<T, true, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb,
+                                          cjk, Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk,
+                                          accH, accL, accG, accD);
+            else
+              triple_visit<T, true, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik],
+                                           bb, cjk, Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk,
+                                           accH, accL, accG, accD);
+          }
+          out0[p] = accG;
+          out1[p] = accD;
         }
-#undef VISIT
-        out0[p] = GRAD ? accG : accH;  // !GRAD: share of the higher-index atom
-        out1[p] = GRAD ? accD : accL;  // !GRAD: share of the lower-index atom
-      }
-      __syncthreads();  // all reads of the stash done -> planes become outputs
-      for (int p = tid; p < np; p += nthr) {  // same thread wrote out0/out1[p]
-        pP[p] = out0[p];
-        pu[p] = out1[p];
-      }
-      __syncthreads();
-      if (!GRAD) {
+        __syncthreads();  // all reads of the stash done -> planes become outputs
+        for (int p = tid; p < np; p += nthr) {  // same thread wrote out0/out1[p]
+          pP[p] = out0[p];
+          pu[p] = out1[p];
+        }
+        __syncthreads();
+      } else {
+        // Energy: every unordered triple i > j > k is evaluated exactly once.
+        // A warp takes 32 consecutive "bottom" pairs (j,k) (one per lane, stash
+        // entry in registers) and sweeps the top atom i; the shares of atoms j
+        // and k accumulate in lane registers, the share of atom i is reduced
+        // over the lanes with a batched (transposed) shuffle reduction.
+        T* const Tw = Aq + (size_t)(tid >> 5) * cap;  // A vectors are dead: per-warp E_i partials
+        for (int i = lane; i < n; i += 32) Tw[i] = T(0);
+        __syncwarp();
+        const int nchunks = (np + 31) >> 5;
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        while (true) {
+          int chunk = 0;
+          if (lane == 0) chunk = atomicAdd(&misc[4], 1);
+          chunk = __shfl_sync(0xffffffffu, chunk, 0);
+          if (chunk >= nchunks) break;
+          const int p = chunk * 32 + lane;
+          const bool valid = p < np;
+          int j = 1 << 20, k = 0;
+          if (valid) pair_decode(p, j, k);
+          const int jmin = __shfl_sync(0xffffffffu, j, 0);
+          const T bs = valid ? pa[p] : T(1);
+          const T Pjk = valid ? pP[p] : T(0), ujk = valid ? pu[p] : T(0);
+          const T bb = fabs(bs);
+          const T cjk = bs > T(0) ? T(1) : T(0);
+          T accJ = T(0), accK = T(0);
+          for (int i0 = jmin + 1; i0 < n; i0 += 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = i0 + u;
+              T ei = T(0);
+              if (i < n && i > j) {
+                const int ti = i * (i - 1) / 2;
+                const T a_s = pa[ti + j], c_s = pa[ti + k];
+                T a = a_s, c = c_s, mi = T(1), mj = T(1), mk = T(1);
+                if (open) {
+                  const T cij = a_s > T(0) ? T(1) : T(0);
+                  const T cik = c_s > T(0) ? T(1) : T(0);
+                  a = fabs(a_s);
+                  c = fabs(c_s);
+                  mi = cjk * (cij + cik);
+                  mj = cik * (cij + cjk);
+                  mk = cij * (cik + cjk);
+                }
+                const T X = a + bb - c, Y = a - bb + c, Z = bb + c - a;
+                const T abc = a * bb * c;
+                const T t = pu[ti + j] * pu[ti + k] * ujk;
+                const T d = T(1) + T(6) * t;
+                const T inv = T(1) / (abc * d);
+                const T psf = pP[ti + j] * pP[ti + k] * Pjk * (inv * abc);
+                const T e = (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) * psf;
+                accJ += mj * e;
+                accK += mk * e;
+                ei = mi * e;
+              }
+              v[u] = ei;
+            }
+            // transposed reduction: 8 values x 32 lanes -> lane group (lane>>2) holds sum u
+            T w0, w1, w2, w3;
+            {
+              const T s0 = b4 ? v[0] : v[4], s1 = b4 ? v[1] : v[5], s2 = b4 ? v[2] : v[6],
+                      s3 = b4 ? v[3] : v[7];
+              w0 = (b4 ? v[4] : v[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
+              w1 = (b4 ? v[5] : v[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
+              w2 = (b4 ? v[6] : v[2]) + __shfl_xor_sync(0xffffffffu, s2, 16);
+              w3 = (b4 ? v[7] : v[3]) + __shfl_xor_sync(0xffffffffu, s3, 16);
+            }
+            const T x0 = (b3 ? w2 : w0) + __shfl_xor_sync(0xffffffffu, b3 ? w0 : w2, 8);
+            const T x1 = (b3 ? w3 : w1) + __shfl_xor_sync(0xffffffffu, b3 ? w1 : w3, 8);
+            T y = (b2 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, b2 ? x0 : x1, 4);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            const int iw = i0 + (lane >> 2);
+            if ((lane & 3) == 0 && iw < n) Tw[iw] += y;
+          }
+          if (valid) {
+            out0[p] = accJ;
+            out1[p] = accK;
+          }
+        }
+        __syncthreads();
+        const T scale = open ? T(1) : T(2);  // closed triples: every atom has multiplicity 2
+        const int nwarps = nthr >> 5;
         for (int i = tid; i < n; i += nthr) {
           T s = T(0);
           const int ti = i * (i - 1) / 2;
-          for (int j = 0; j < i; ++j) s += pP[ti + j];
-          for (int j = i + 1; j < n; ++j) s += pu[j * (j - 1) / 2 + i];
-          ATOM(AT_E)[i] += T(0.5) * s;
+          for (int j = 0; j < i; ++j) s += out0[ti + j];
+          for (int j = i + 1; j < n; ++j) s += out1[j * (j - 1) / 2 + i];
+          for (int w = 0; w < nwarps; ++w) s += Aq[(size_t)w * cap + i];
+          ATOM(AT_E)[i] += scale * s;
         }
         __syncthreads();
       }
@@ -474,10 +561,9 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       __syncthreads();
     }
 
-    if (!GRAD) {
+    if constexpr (!GRAD) {
       for (int i = tid; i < n; i += nthr) A.energy[(size_t)b * A.nat + idx[i]] = ATOM(AT_E)[i];
-      continue;
-    }
+    } else {
 
     // =================== gradient back-propagation ===========================
     // phase 7: per-pair coefficients
@@ -605,6 +691,7 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       }
       if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
     }
+    }  // GRAD
   }
 #undef ATOM
 #undef WT
