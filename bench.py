@@ -52,6 +52,7 @@ PBE0 = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)  # d4.toml:269 of the r
 # algorithmic flop per unit of work (contract figures)
 F_PCN, F_P2, F_T, F_W = 18, 248, 30, 120
 F_PCN_G, F_P2_G, F_T_G = 30, 320, 90
+NCLS = 5  # D4B200_NCLASS
 
 WORKLOADS = {
     "c2": dict(nbatch=4096, lo=20, hi=60, seed=2, grad=False,
@@ -282,26 +283,29 @@ def run_b200(args, wl, rank, world, local_rank):
 
     # ---- dominant kernel: per-launch duration measured live with CUDA events
     lib.d4b200_profile_enable(engine.handle, 1)
-    caps = (C.c_int * 4)()
+    caps = (C.c_int * NCLS)()
     lib.d4b200_class_caps(engine.handle, int(dtype == torch.float32), int(wl["grad"]), caps)
-    per_class = [[] for _ in range(4)]
+    per_class = [[] for _ in range(NCLS)]
+    prep_ms, call_ms = [], []
     for s in range(max(3, min(args.steps, 10))):
         flush.fill_(1.0)
         step_resident()
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * (NCLS + 2))()
         lib.d4b200_profile_read(engine.handle, ms)
-        for c in range(4):
+        for c in range(NCLS):
             if ms[c] >= 0:
                 per_class[c].append(ms[c])
+        prep_ms.append(ms[NCLS])
+        call_ms.append(ms[NCLS + 1])
     lib.d4b200_profile_enable(engine.handle, 0)
     class_ms = [statistics.mean(v[1:] if len(v) > 1 else v) if v else 0.0 for v in per_class]
     lo = 0
     class_flop = []
-    for c in range(4):
+    for c in range(NCLS):
         sel = (nat >= lo) & (nat <= caps[c]) if caps[c] >= lo else torch.zeros_like(nat, dtype=torch.bool)
         class_flop.append(float(flop[sel].sum()))
         lo = caps[c] + 1
-    dom = max(range(4), key=lambda c: class_ms[c])
+    dom = max(range(NCLS), key=lambda c: class_ms[c])
 
     peak_tf = C.c_double(0.0)
     scratch = torch.empty(64 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -358,7 +362,8 @@ def run_b200(args, wl, rank, world, local_rank):
                 "peak_source": "measured in this run: DFMA chain microbenchmark (d4b200_measure_fp64_peak); "
                                f"nominal {nominal_tf} TFLOP/s; MEASURED_PEAKS.json has no FP64 entry",
                 "kernel_ms": class_ms[dom], "kernel_algorithmic_flop": class_flop[dom],
-                "all_class_ms": class_ms, "step_share": class_ms[dom] / (sec_per_step * 1e3),
+                "all_class_ms": class_ms, "prep_ms": statistics.mean(prep_ms[1:]),
+                "serialised_call_ms": statistics.mean(call_ms[1:]), "step_share": class_ms[dom] / (sec_per_step * 1e3),
                 "hbm_gbs_algorithmic": (h2d + d2h) / sec_per_step / 1e9,
             },
             "cpu_baseline": cpu,

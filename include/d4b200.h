@@ -58,6 +58,9 @@ extern "C" {
 #define D4B200_MODEL_D4 0
 #define D4B200_MODEL_D4S 1
 
+/* number of size classes of the one-CTA-per-structure kernels */
+#define D4B200_NCLASS 5
+
 /* Flattened ``Param`` (src/tad_dftd4/damping/parameters/base.py:48-85) +
  * ``Cutoff`` (src/tad_dftd4/cutoff.py:36-90) + model weighting factor.
  * Defaults applied by the caller exactly as the reference does:
@@ -130,10 +133,11 @@ int d4b200_last_launch_count(void);
 /* --- measurement hooks used by bench.py (no effect on results) ----------- */
 /* Record CUDA events around every hot-kernel launch of the following calls. */
 int d4b200_profile_enable(d4b200_tables_t tables, int enable);
-/* Duration (ms) of the last call's hot kernel per size class; -1 = not launched. */
-int d4b200_profile_read(d4b200_tables_t tables, float* ms_per_class /*[4]*/);
-/* Inclusive atom-count bounds of the four size classes for a kernel flavour. */
-int d4b200_class_caps(d4b200_tables_t tables, int fp32, int grad, int* caps_out /*[4]*/);
+/* Duration (ms) of the last call's hot kernel per size class (-1 = not launched),
+ * followed by the batch-preparation time and the whole call's device time. */
+int d4b200_profile_read(d4b200_tables_t tables, float* ms_out /*[D4B200_NCLASS + 2]*/);
+/* Inclusive atom-count bounds of the size classes for a kernel flavour. */
+int d4b200_class_caps(d4b200_tables_t tables, int fp32, int grad, int* caps_out /*[D4B200_NCLASS]*/);
 /* Measured FP64 FMA throughput (TFLOP/s) of the device: roofline denominator. */
 int d4b200_measure_fp64_peak(d4b200_tables_t tables, void* scratch_dev, size_t scratch_bytes,
                              void* stream, double* tflops_out);

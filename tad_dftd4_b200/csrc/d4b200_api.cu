@@ -26,9 +26,13 @@ struct d4b200_tables {
   int threads[2][2][NCLASS];
   int grid_per_sm[2][2][NCLASS];
   size_t smem[2][2][NCLASS];
+  // classes are independent: they run concurrently on a small stream pool
+  cudaStream_t cstream[NCLASS];
+  cudaEvent_t ev_fork, ev_join[NCLASS];
   // optional per-launch timing (bench.py roofline): events around each class kernel
   int profile;
   cudaEvent_t ev[2 * NCLASS];
+  cudaEvent_t ev_call[3];  // call start, prep done, call end
   int ev_used[NCLASS];
 };
 
@@ -163,7 +167,7 @@ Work carve_work(void* ws, int nbatch) {
 
 constexpr int MAX_SMS = 160;
 // upper bound of resident CTAs per SM we ever launch for a class
-__host__ inline int class_occ_cap(int c) { return c == 0 ? 16 : c == 1 ? 6 : 2; }
+__host__ inline int class_occ_cap(int c) { return c == 0 ? 10 : c == 1 ? 5 : c == 2 ? 4 : 2; }
 
 size_t scratch_bytes_class(int c, int cap, size_t elem) {
   return align_up((size_t)MAX_SMS * class_occ_cap(c) * 2 * (cap * (cap - 1) / 2) * elem, 256);
@@ -185,42 +189,77 @@ Par<T> make_par(const d4b200_params* p, double ga) {
   P.wf = p->wf;
   P.ga = ga;
   P.has_atm = p->s9 != 0.0;
+  P.alp16 = p->alp == 16.0;
   P.model = p->model;
   return P;
 }
+
+// Size classes per kernel flavour: X(class, CAP, threads, min CTAs/SM for launch bounds).
+// Caps are bounded by the 227 KB shared-memory budget (Lay<>::total).
+#define D4_CLASSES_F64_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 3) X(3, 96, 512, 1) X(4, 128, 512, 1)
+#define D4_CLASSES_F64_G(X) X(0, 32, 128, 4) X(1, 48, 256, 2) X(2, 64, 512, 1) X(3, 80, 512, 1) X(4, 100, 512, 1)
+#define D4_CLASSES_F32_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 4) X(3, 96, 512, 2) X(4, 128, 512, 1)
+#define D4_CLASSES_F32_G(X) X(0, 32, 128, 6) X(1, 48, 256, 3) X(2, 64, 512, 2) X(3, 96, 512, 1) X(4, 128, 512, 1)
+
+template <typename T, bool GRAD>
+struct Flavour;
+#define D4_FLAVOUR(TYPE, GRADV, LIST)                                                              \
+  template <>                                                                                      \
+  struct Flavour<TYPE, GRADV> {                                                                    \
+    static int configure(d4b200_tables* h, int dt, int gr) {                                       \
+      cudaError_t e = cudaSuccess;                                                                 \
+      int occ = 0;                                                                                 \
+      LIST(D4_CFG_ONE)                                                                             \
+      return 0;                                                                                    \
+    }                                                                                              \
+    static void launch(int c, unsigned grid, cudaStream_t st, const SmallArgs<TYPE>& A) {          \
+      switch (c) { LIST(D4_LAUNCH_ONE) }                                                           \
+    }                                                                                              \
+  };
+#define D4_CFG_ONE(C, CAPV, NTV, MINBV)                                                            \
+  {                                                                                                \
+    using LL = Lay<type_t, grad_v, CAPV>;                                                          \
+    static_assert(LL::total <= 227 * 1024, "class does not fit the shared-memory budget");         \
+    auto kern = small_kernel<type_t, grad_v, CAPV, NTV, MINBV>;                                    \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL::total);   \
+    if (e != cudaSuccess) return (int)e;                                                           \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTV, LL::total);                 \
+    if (e != cudaSuccess) return (int)e;                                                           \
+    if (occ < 1) occ = 1;                                                                          \
+    if (occ > class_occ_cap(C)) occ = class_occ_cap(C);                                            \
+    h->caps[dt][gr][C] = CAPV;                                                                     \
+    h->threads[dt][gr][C] = NTV;                                                                   \
+    h->smem[dt][gr][C] = LL::total;                                                                \
+    h->grid_per_sm[dt][gr][C] = occ;                                                               \
+  }
+#define D4_LAUNCH_ONE(C, CAPV, NTV, MINBV)                                                         \
+  case C:                                                                                          \
+    small_kernel<type_t, grad_v, CAPV, NTV, MINBV>                                                 \
+        <<<grid, NTV, Lay<type_t, grad_v, CAPV>::total, st>>>(A);                                  \
+    break;
+
+#define type_t double
+#define grad_v false
+D4_FLAVOUR(double, false, D4_CLASSES_F64_E)
+#undef grad_v
+#define grad_v true
+D4_FLAVOUR(double, true, D4_CLASSES_F64_G)
+#undef grad_v
+#undef type_t
+#define type_t float
+#define grad_v false
+D4_FLAVOUR(float, false, D4_CLASSES_F32_E)
+#undef grad_v
+#define grad_v true
+D4_FLAVOUR(float, true, D4_CLASSES_F32_G)
+#undef grad_v
+#undef type_t
 
 template <typename T, bool GRAD>
 int configure(d4b200_tables* h) {
   constexpr int dt = sizeof(T) == 8 ? 0 : 1;
   constexpr int gr = GRAD ? 1 : 0;
-  // class bounds: as large as the 227 KB shared-memory budget allows
-  const int want[NCLASS] = {32, 64, 96, 128};
-  const int thr[NCLASS] = {128, 256, 512, 512};
-  int prev = 0;
-  for (int c = 0; c < NCLASS; ++c) {
-    int cap = want[c];
-    while (cap > prev + 4 && small_layout<T, GRAD>(cap).total > 227 * 1024) cap -= 4;
-    if (small_layout<T, GRAD>(cap).total > 227 * 1024) cap = prev;  // class unusable
-    h->caps[dt][gr][c] = cap;
-    h->threads[dt][gr][c] = thr[c];
-    h->smem[dt][gr][c] = small_layout<T, GRAD>(cap > 2 ? cap : 2).total;
-    prev = cap;
-  }
-  size_t maxs = 0;
-  for (int c = 0; c < NCLASS; ++c) maxs = h->smem[dt][gr][c] > maxs ? h->smem[dt][gr][c] : maxs;
-  cudaError_t e = cudaFuncSetAttribute(small_kernel<T, GRAD>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxs);
-  if (e != cudaSuccess) return (int)e;
-  for (int c = 0; c < NCLASS; ++c) {
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_kernel<T, GRAD>,
-                                                      h->threads[dt][gr][c], h->smem[dt][gr][c]);
-    if (e != cudaSuccess) return (int)e;
-    if (occ < 1) occ = 1;
-    if (occ > class_occ_cap(c)) occ = class_occ_cap(c);
-    h->grid_per_sm[dt][gr][c] = occ;
-  }
-  return 0;
+  return Flavour<T, GRAD>::configure(h, dt, gr);
 }
 
 template <typename T, bool GRAD>
@@ -237,6 +276,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   if (nbatch == 0 || nat == 0) return 0;
 
   Work wk = carve_work(ws, nbatch);
+  if (h->profile) cudaEventRecord(h->ev_call[0], st);
   cudaError_t e = cudaMemsetAsync(wk.status, 0, sizeof(int) * HEADER_INTS, st);
   if (e != cudaSuccess) return (int)e;
   ++g_launches;
@@ -259,7 +299,6 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   A.gradq = gradq;
   A.nbatch = nbatch;
   A.nat = nat;
-  for (int c = 0; c < NCLASS; ++c) A.caps[c] = caps.v[c];
   if constexpr (dt == 0) {
     A.tab = h->t64;
   } else {
@@ -268,29 +307,38 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   A.par = make_par<T>(par, h->ga);
   A.wk = wk;
   unsigned char* scratch = reinterpret_cast<unsigned char*>(ws) + int_region_bytes(nbatch);
+  // fork: every populated class runs on its own stream, ordered after the prep kernels
+  if (h->profile) cudaEventRecord(h->ev_call[1], st);
+  cudaEventRecord(h->ev_fork, st);
   int prev = 0;
   for (int c = 0; c < NCLASS; ++c) {
     const int cap = caps.v[c];
-    if (cap <= prev) continue;  // class disabled for this flavour
-    prev = cap;
     // a class can only be populated if the padded width reaches into it
-    const int lo = c == 0 ? 0 : caps.v[c - 1] + 1;
+    const int lo = prev + 1;
+    prev = cap;
     size_t sbytes = scratch_bytes_class(c, cap, sizeof(T));
-    if (nat >= lo) {
+    if (nat >= lo || c == 0) {
       A.cls = c;
       A.scratch = reinterpret_cast<T*>(scratch);
       long grid = (long)h->grid_per_sm[dt][gr][c] * h->num_sms;
       if (grid > nbatch) grid = nbatch;
       const long gmax = (long)(h->num_sms < MAX_SMS ? h->num_sms : MAX_SMS) * class_occ_cap(c);
       if (grid > gmax) grid = gmax;
+      cudaStream_t cs = h->profile ? st : h->cstream[c];  // profiling: serialise on the caller's stream
+      if (!h->profile) cudaStreamWaitEvent(cs, h->ev_fork, 0);
       if (h->profile) cudaEventRecord(h->ev[2 * c], st);
-      small_kernel<T, GRAD><<<(unsigned)grid, h->threads[dt][gr][c], h->smem[dt][gr][c], st>>>(A);
+      Flavour<T, GRAD>::launch(c, (unsigned)grid, cs, A);
       if (h->profile) cudaEventRecord(h->ev[2 * c + 1], st);
       h->ev_used[c] = h->profile;
+      if (!h->profile) {
+        cudaEventRecord(h->ev_join[c], cs);
+        cudaStreamWaitEvent(st, h->ev_join[c], 0);
+      }
       ++g_launches;
     }
     scratch += sbytes;
   }
+  if (h->profile) cudaEventRecord(h->ev_call[2], st);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -349,6 +397,12 @@ int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
     if ((e = cudaMemcpy(h->i32, i32_blob_host, n_i32 * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) break;
     k_to_float<<<(unsigned)((n_f64 + 255) / 256), 256>>>(h->f64, h->f32, n_f64);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+    for (int c = 0; c < NCLASS && e == cudaSuccess; ++c) {
+      e = cudaStreamCreateWithFlags(&h->cstream[c], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) break;
     h->t64 = make_tables<double>(h->f64, h->f64, h->i32);
     h->t32 = make_tables<float>(h->f32, h->f64, h->i32);
     if ((rc = configure<double, false>(h)) != 0) break;
@@ -369,6 +423,13 @@ int d4b200_tables_destroy(d4b200_tables_t h) {
   if (!h) return 0;
   for (int i = 0; i < 2 * NCLASS; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 3; ++i)
+    if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
+  for (int c = 0; c < NCLASS; ++c) {
+    if (h->cstream[c]) cudaStreamDestroy(h->cstream[c]);
+    if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   cudaFree(h->f64);
   cudaFree(h->f32);
   cudaFree(h->i32);
@@ -380,7 +441,7 @@ size_t d4b200_workspace_bytes(int nbatch, int nat) {
   (void)nat;
   if (nbatch < 0) return 0;
   size_t s = int_region_bytes(nbatch);
-  const int caps[NCLASS] = {32, 64, 96, 128};
+  const int caps[NCLASS] = {32, 48, 64, 96, 128};
   for (int c = 0; c < NCLASS; ++c) s += scratch_bytes_class(c, caps[c], sizeof(double));
   return s;
 }
@@ -431,6 +492,12 @@ int d4b200_profile_enable(d4b200_tables_t h, int enable) {
         if (e != cudaSuccess) return (int)e;
       }
     }
+    for (int i = 0; i < 3; ++i) {
+      if (!h->ev_call[i]) {
+        cudaError_t e = cudaEventCreate(&h->ev_call[i]);
+        if (e != cudaSuccess) return (int)e;
+      }
+    }
   }
   h->profile = enable != 0;
   return 0;
@@ -446,6 +513,10 @@ int d4b200_profile_read(d4b200_tables_t h, float* ms_per_class) {
     e = cudaEventElapsedTime(&ms_per_class[c], h->ev[2 * c], h->ev[2 * c + 1]);
     if (e != cudaSuccess) return (int)e;
   }
+  cudaError_t e = cudaEventSynchronize(h->ev_call[2]);
+  if (e != cudaSuccess) return (int)e;
+  cudaEventElapsedTime(&ms_per_class[NCLASS], h->ev_call[0], h->ev_call[1]);
+  cudaEventElapsedTime(&ms_per_class[NCLASS + 1], h->ev_call[0], h->ev_call[2]);
   return 0;
 }
 

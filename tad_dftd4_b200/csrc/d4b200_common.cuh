@@ -12,7 +12,7 @@ constexpr int NELEM = 104;  // reference tables: Z = 0 (dummy) .. 103
 constexpr int NREF = 7;
 constexpr int NFREQ = 23;
 constexpr int SMALL_MAX = 128;  // largest structure of the one-CTA-per-structure family
-constexpr int NCLASS = 4;       // size classes of the small family
+constexpr int NCLASS = 5;       // size classes of the small family
 constexpr int HIST_BINS = SMALL_MAX + 2;
 
 // Per-element tables in device memory (layout: tad_dftd4_b200/tables.py).
@@ -44,6 +44,7 @@ struct Par {
   T disp2_sq, disp3_sq, cn_sq;
   double wf, ga;
   int has_atm;  // s9 != 0
+  int alp16;    // alp == 16 (default): (R0/r)^(16/3) = x^5 cbrt(x)
   int model;
 };
 

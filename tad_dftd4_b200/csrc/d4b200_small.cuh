@@ -10,9 +10,11 @@
 //   -> ATM pair stash (r^2, sigma/r^3, (R0/r)^(alp/3)) -> triple loop
 //   [-> back-propagation passes for the gradient kernel]
 //
-// Algebra and its derivation: tests/kernel_model.py (checked against the oracle
-// on the CPU); reference formulation: src/tad_dftd4/dispersion/{twobody,
-// threebody}.py, model/d4.py, tad_mctc.ncoord.cn_d4 (see include/d4b200.h).
+// The kernel is templated on the class capacity CAP so that every shared-memory
+// plane offset is an immediate.  Algebra and its derivation:
+// tests/kernel_model.py (checked against the oracle on the CPU); reference
+// formulation: src/tad_dftd4/dispersion/{twobody,threebody}.py, model/d4.py,
+// tad_mctc.ncoord.cn_d4 (see include/d4b200.h).
 #pragma once
 
 #include <math.h>
@@ -31,9 +33,8 @@ struct SmallArgs {
   T* cn_out;
   T* grad;
   T* gradq;
-  T* scratch;  // [gridDim.x][2][cap(cap-1)/2] per-CTA pair results of the triple loop
+  T* scratch;  // [gridDim.x][2][CAP(CAP-1)/2] per-CTA pair results of the triple loop
   int nbatch, nat, cls;
-  int caps[NCLASS];  // inclusive size bounds of the classes for this kernel flavour
   Tables<T> tab;
   Par<T> par;
   Work wk;
@@ -44,10 +45,28 @@ __device__ __forceinline__ double d4_erfc(double x) { return erfc(x); }
 __device__ __forceinline__ float d4_erfc(float x) { return erfcf(x); }
 __device__ __forceinline__ double d4_exp(double x) { return exp(x); }
 __device__ __forceinline__ float d4_exp(float x) { return expf(x); }
-__device__ __forceinline__ double d4_pow(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ float d4_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double d4_log(double x) { return log(x); }
+__device__ __forceinline__ float d4_log(float x) { return logf(x); }
+__device__ __forceinline__ double d4_cbrt(double x) { return cbrt(x); }
+__device__ __forceinline__ float d4_cbrt(float x) { return cbrtf(x); }
 __device__ __forceinline__ double d4_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float d4_sqrt(float x) { return sqrtf(x); }
+// erfc(x) is below one ulp of the coordination number beyond this argument
+__device__ __forceinline__ double d4_erfc_cut(double) { return 6.2; }
+__device__ __forceinline__ float d4_erfc_cut(float) { return 4.6f; }
+
+// Reciprocal without the slow-path branch of IEEE division: all operands here
+// are normal, positive numbers.  MUFU.RCP64H seed + two Newton steps (<= 1 ulp).
+__device__ __forceinline__ double d4_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ float d4_rcp(float x) { return __frcp_rn(x); }
+
 template <typename T>
 __device__ __forceinline__ T d4_eps();
 template <>
@@ -55,48 +74,64 @@ __device__ __forceinline__ double d4_eps<double>() { return 2.220446049250313e-1
 template <>
 __device__ __forceinline__ float d4_eps<float>() { return 1.1920929e-07f; }
 
+// (R0/r)^(alp/3): x^5 cbrt(x) for the default alp = 16, exp(y log x) otherwise
+template <typename T>
+__device__ __forceinline__ T d4_zero_damp_arg(T x, T alp3, bool alp16) {
+  if (alp16) {
+    const T x2 = x * x;
+    return x2 * x2 * x * d4_cbrt(x);
+  }
+  return d4_exp(alp3 * d4_log(x));
+}
+
 // ---------------------------------------------------------------- smem layout
-struct SmallLayout {
-  int cap, cpairs;
-  size_t planes, aq, a0, bq, b0, atoms, wts, ints, total;
-};
+constexpr size_t al16(size_t b) { return (b + 15) & ~size_t(15); }
 
 // per-atom T arrays
-enum { AT_X = 0, AT_Y, AT_Z, AT_Q, AT_CN, AT_E, AT_RCOV, AT_R4R2, AT_SQ, AT_G, AT_DCN, AT_DQ, AT_COUNT };
+enum { AT_X = 0, AT_Y, AT_Z, AT_Q, AT_CN, AT_E, AT_RCOV, AT_SQ, AT_G, AT_DCN, AT_DQ };
 // per-atom x 7 T arrays
-enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG, WT_COUNT };
+enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG };
 
-template <typename T, bool GRAD>
-__host__ __device__ inline SmallLayout small_layout(int cap) {
-  SmallLayout L;
-  L.cap = cap;
-  L.cpairs = cap * (cap - 1) / 2;
-  size_t o = 0;
-  auto take = [&](size_t bytes) {
-    size_t r = o;
-    o += (bytes + 15) & ~size_t(15);
-    return r;
-  };
-  L.planes = take(size_t(3) * L.cpairs * sizeof(T));
-  L.aq = take(size_t(NFREQ) * cap * sizeof(T));
-  L.a0 = take(size_t(NFREQ) * cap * sizeof(T));
-  L.bq = GRAD ? take(size_t(NFREQ) * cap * sizeof(T)) : 0;
-  L.b0 = GRAD ? take(size_t(NFREQ) * cap * sizeof(T)) : 0;
-  L.atoms = take(size_t(GRAD ? AT_COUNT : AT_G) * cap * sizeof(T));
-  L.wts = take(size_t(GRAD ? WT_COUNT : WT_ZGD) * NREF * cap * sizeof(T));
-  L.ints = take(size_t(2) * cap * sizeof(int) + 8 * sizeof(int));
-  L.total = o;
-  return L;
-}
+template <typename T, bool GRAD, int CAP>
+struct Lay {
+  static constexpr int CP = CAP * (CAP - 1) / 2;
+  static constexpr size_t plane_bytes = size_t(3) * CP * sizeof(T);
+  static constexpr size_t wtmp_bytes = size_t(3) * NREF * CAP * sizeof(double);
+  // energy kernel: the weights live on top of the (not yet used) planes, right
+  // after their float64 temporaries, when they fit; the gradient kernel needs
+  // the weights until the end
+  static constexpr bool wt_alias =
+      !GRAD && wtmp_bytes + size_t(2) * NREF * CAP * sizeof(T) <= plane_bytes;
+  static constexpr int n_abuf = GRAD ? 4 : 1;  // energy: Aq, then A0 in the same buffer
+  static constexpr int n_atom = GRAD ? 11 : 8;
+  static constexpr int n_wt = GRAD ? 5 : (wt_alias ? 0 : 2);
+  static constexpr size_t planes = 0;
+  static constexpr size_t abuf = al16(plane_bytes > wtmp_bytes ? plane_bytes : wtmp_bytes);
+  static constexpr size_t atoms = abuf + al16(size_t(n_abuf) * NFREQ * CAP * sizeof(T));
+  static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
+  static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
+  static constexpr size_t total = ints + al16((2 * CAP + 8) * sizeof(int));
+};
 
-// p -> (hi, lo) with hi > lo, p = hi(hi-1)/2 + lo
-__device__ __forceinline__ void pair_decode(int p, int& hi, int& lo) {
-  int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-  while (i * (i - 1) / 2 > p) --i;
-  while ((i + 1) * i / 2 <= p) ++i;
-  hi = i;
-  lo = p - i * (i - 1) / 2;
-}
+// triangular pair index walker: p = hi(hi-1)/2 + lo, hi > lo
+struct PairIt {
+  int p, hi, lo;
+  __device__ __forceinline__ explicit PairIt(int p0) : p(p0) {
+    int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p0)) * 0.5f);
+    while (i * (i - 1) / 2 > p0) --i;
+    while ((i + 1) * i / 2 <= p0) ++i;
+    hi = i;
+    lo = p0 - i * (i - 1) / 2;
+  }
+  __device__ __forceinline__ void advance(int step) {
+    p += step;
+    lo += step;
+    while (lo >= hi) {
+      lo -= hi;
+      ++hi;
+    }
+  }
+};
 
 template <typename T>
 __device__ __forceinline__ T row_sum(const T* __restrict__ plane, int i, int n) {
@@ -107,71 +142,65 @@ __device__ __forceinline__ T row_sum(const T* __restrict__ plane, int i, int n) 
   return s;
 }
 
-// One visit of the pair-owner triple loop: owner pair (j,k) with r^2 = b,
-// third atom i with stash entries of (i,j) and (i,k).
+// Gradient triple visit: owner pair (j,k) with r^2 = b, third atom i with the
+// stash entries of (i,j) and (i,k).
 //   e' = (0.375 s/(abc) + 1) * P_ij P_ik P_jk / (1 + 6 u_ij u_ik u_jk)
 // (threebody.py:113-160 factorised per pair; e' = e_ijk/6 with s9 folded in).
-template <typename T, bool GRAD, bool OPEN>
-__device__ __forceinline__ void triple_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T cjk,
-                                             T Pjk, T ujk, T inv_b, T alp3, T gi, T gj, T gk,
-                                             T& accH, T& accL, T& accG, T& accD) {
+template <typename T, bool OPEN>
+__device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T cjk,
+                                           T Pjk, T ujk, T inv_b, T alp3, T gi, T gj, T gk,
+                                           T& accG, T& accD) {
   T a = a_s, c = c_s;
-  T mi = T(2), mj = T(2), mk = T(2);
+  T W = gi + gj + gk;
   if (OPEN) {
     const T cij = a_s > T(0) ? T(1) : T(0);
     const T cik = c_s > T(0) ? T(1) : T(0);
     a = fabs(a_s);
     c = fabs(c_s);
-    mi = cjk * (cij + cik);
-    mj = cik * (cij + cjk);
-    mk = cij * (cik + cjk);
+    W = gi * (cjk * (cij + cik)) + gj * (cik * (cij + cjk)) + gk * (cij * (cik + cjk));
+  } else {
+    W = W + W;  // closed triple: multiplicity 2 for every atom
   }
   const T X = a + b - c, Y = a - b + c, Z = b + c - a;
   const T s = X * Y * Z;
   const T abc = a * b * c;
   const T t = uij * uik * ujk;
   const T d = T(1) + T(6) * t;
-  const T inv = T(1) / (abc * d);
+  const T inv = d4_rcp(abc * d);
   const T Q = inv * d;
   const T f = inv * abc;
   const T psf = Pij * Pik * Pjk * f;
-  const T ang = T(0.375) * s * Q + T(1);
-  const T e = ang * psf;
-  if (!GRAD) {
-    accH += mj * e;
-    accL += mk * e;
-  } else {
-    const T W = gi * mi + gj * mj + gk * mk;
-    const T dsdb = Y * Z - X * Z + X * Y;
-    const T common = e * (T(-2.5) + T(3) * alp3 * f * t) + psf;
-    const T de = common * inv_b + T(0.375) * psf * Q * dsdb;
-    accG += W * e;
-    accD += W * de;
-  }
+  const T e = (T(0.375) * s * Q + T(1)) * psf;
+  const T dsdb = Y * Z - X * Z + X * Y;
+  const T common = e * (T(-2.5) + T(3) * alp3 * f * t) + psf;
+  const T de = common * inv_b + T(0.375) * psf * Q * dsdb;
+  accG += W * e;
+  accD += W * de;
 }
 
-template <typename T, bool GRAD>
-__global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
+template <typename T, bool GRAD, int CAP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
+  using L = Lay<T, GRAD, CAP>;
+  constexpr int CP = L::CP;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int cap = A.caps[A.cls];
-  const SmallLayout L = small_layout<T, GRAD>(cap);
-  T* const pa = reinterpret_cast<T*>(smem + L.planes);
-  T* const pP = pa + L.cpairs;
-  T* const pu = pP + L.cpairs;
-  double* const wtmp = reinterpret_cast<double*>(smem + L.planes);  // aliases the planes
-  T* const Aq = reinterpret_cast<T*>(smem + L.aq);
-  T* const A0 = reinterpret_cast<T*>(smem + L.a0);
-  T* const Bq = reinterpret_cast<T*>(smem + L.bq);
-  T* const B0 = reinterpret_cast<T*>(smem + L.b0);
-  T* const at = reinterpret_cast<T*>(smem + L.atoms);
-  T* const wt = reinterpret_cast<T*>(smem + L.wts);
-  int* const zs = reinterpret_cast<int*>(smem + L.ints);
-  int* const idx = zs + cap;
-  int* const misc = idx + cap;  // [0]=work item, [1]=n, [2]=any_open, [3]=bad, [4]=chunk counter
-#define ATOM(k) (at + (k) * cap)
-#define WT(k) (wt + (k) * NREF * cap)
+  T* const pa = reinterpret_cast<T*>(smem + L::planes);
+  T* const pP = pa + CP;
+  T* const pu = pP + CP;
+  double* const wtmp = reinterpret_cast<double*>(smem + L::planes);  // aliases the planes
+  T* const Aq = reinterpret_cast<T*>(smem + L::abuf);
+  T* const A0 = GRAD ? Aq + NFREQ * CAP : Aq;
+  T* const Bq = Aq + 2 * NFREQ * CAP;  // GRAD only
+  T* const B0 = Aq + 3 * NFREQ * CAP;  // GRAD only
+  T* const at = reinterpret_cast<T*>(smem + L::atoms);
+  T* const wt = L::wt_alias ? reinterpret_cast<T*>(smem + L::planes + L::wtmp_bytes)
+                            : reinterpret_cast<T*>(smem + L::wts);
+  int* const zs = reinterpret_cast<int*>(smem + L::ints);
+  int* const idx = zs + CAP;
+  int* const misc = idx + CAP;  // [0]=work item, [1]=n, [2]=any_open, [3]=skip, [4]=chunk counter
+#define ATOM(k) (at + (k) * CAP)
+#define WT(k) (wt + (k) * NREF * CAP)
 
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x;
   const int lane = tid & 31;
   const Par<T>& P = A.par;
   const Tables<T>& tab = A.tab;
@@ -200,7 +229,7 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
         }
         const unsigned m = __ballot_sync(0xffffffffu, real);
         const int dst = count + __popc(m & ((1u << lane) - 1u));
-        if (real && dst < cap) {
+        if (real && dst < CAP) {
           idx[dst] = src;
           zs[dst] = (int)zv;
         }
@@ -208,17 +237,17 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       }
       bad = __any_sync(0xffffffffu, bad);
       if (lane == 0) {
-        misc[1] = count <= cap ? count : 0;
+        misc[1] = count <= CAP ? count : 0;
         misc[2] = 0;
-        misc[3] = count > cap;
+        misc[3] = count > CAP;
         misc[4] = 0;
         if (bad) atomicOr(A.wk.status, D4B200_STATUS_BAD_NUMBER);
-        if (count > cap) atomicOr(A.wk.status, D4B200_STATUS_TOO_LARGE);
+        if (count > CAP) atomicOr(A.wk.status, D4B200_STATUS_TOO_LARGE);
       }
     }
     __syncthreads();
     const bool skip = misc[3] != 0;
-    for (int t = tid; t < A.nat; t += nthr) {
+    for (int t = tid; t < A.nat; t += NT) {
       if (zrow[t] == 0 || skip) {
         const size_t o = (size_t)b * A.nat + t;
         if (!GRAD) {
@@ -234,11 +263,10 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
         }
       }
     }
-    __syncthreads();
     const int n = misc[1];
     const int np = n * (n - 1) / 2;
 
-    for (int i = tid; i < n; i += nthr) {
+    for (int i = tid; i < n; i += NT) {
       const size_t o = (size_t)b * A.nat + idx[i];
       const int z = zs[i];
       ATOM(AT_X)[i] = A.pos[3 * o];
@@ -246,30 +274,32 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       ATOM(AT_Z)[i] = A.pos[3 * o + 2];
       ATOM(AT_Q)[i] = A.q[o];
       ATOM(AT_RCOV)[i] = tab.rcov[z];
-      ATOM(AT_R4R2)[i] = tab.r4r2[z];
       ATOM(AT_SQ)[i] = tab.sqrt_r4r2[z];
       if (GRAD) ATOM(AT_G)[i] = A.gin ? A.gin[o] : T(1);
     }
     __syncthreads();
 
     // ---- phase 1: coordination number (tad_mctc cn_d4 / erf_count) ----------
-    for (int p = tid; p < np; p += nthr) {
-      int i, j;
-      pair_decode(p, i, j);
-      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-      const T r2 = dx * dx + dy * dy + dz * dz;
-      T cf = T(0);
-      if (r2 <= P.cn_sq) {
-        const T r = d4_sqrt(r2);
-        const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
-        cf = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(T(7.5) * (r / r0 - T(1)));
+    if (tid < np) {
+      for (PairIt it(tid); it.p < np; it.advance(NT)) {
+        const int i = it.hi, j = it.lo;
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        T cf = T(0);
+        if (r2 <= P.cn_sq) {
+          const T r = d4_sqrt(r2);
+          const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
+          const T xx = T(7.5) * (r * d4_rcp(r0) - T(1));
+          if (xx < d4_erfc_cut(T(0)))
+            cf = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(xx);
+        }
+        pu[it.p] = cf;
       }
-      pu[p] = cf;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += nthr) {
+    for (int i = tid; i < n; i += NT) {
       const T c = row_sum(pu, i, n);
       ATOM(AT_CN)[i] = c;
       if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = c;
@@ -279,16 +309,16 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
     // ---- phase 2: Gaussian weights (float64 always) x zeta -----------------
     // model/d4.py:137-228; max-shifted exponentials instead of pow(exp(-d^2), k wf).
     double* const warg = wtmp;
-    double* const wS = wtmp + NREF * cap;
-    double* const wdS = wtmp + 2 * NREF * cap;
-    for (int t = tid; t < NREF * n; t += nthr) {
+    double* const wS = wtmp + NREF * CAP;
+    double* const wdS = wtmp + 2 * NREF * CAP;
+    for (int t = tid; t < NREF * n; t += NT) {
       const int i = t / NREF, a = t - i * NREF;
       const int z = zs[i];
       const double d = (double)ATOM(AT_CN)[i] - tab.refcn[z * NREF + a];
       warg[t] = tab.refc[z * NREF + a] > 0 ? P.wf * d * d : 1e300;
     }
     __syncthreads();
-    for (int t = tid; t < NREF * n; t += nthr) {
+    for (int t = tid; t < NREF * n; t += NT) {
       const int i = t / NREF, a = t - i * NREF;
       const int z = zs[i];
       const int rc = tab.refc[z * NREF + a];
@@ -309,7 +339,7 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       wdS[t] = dS;
     }
     __syncthreads();
-    for (int t = tid; t < NREF * n; t += nthr) {
+    for (int t = tid; t < NREF * n; t += NT) {
       const int i = t / NREF, a = t - i * NREF;
       const int z = zs[i];
       double norm = 0.0, dnorm = 0.0;
@@ -349,7 +379,9 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
     __syncthreads();
 
     // ---- phase 3: weighted polarizability vectors A_i[w] -------------------
-    for (int t = tid; t < NFREQ * n; t += nthr) {
+    // energy kernel: only the charge-scaled flavour now; the q = 0 flavour for
+    // the ATM term is built into the same buffer after the two-body pass
+    for (int t = tid; t < NFREQ * n; t += NT) {
       const int i = t / NFREQ, w = t - i * NFREQ;
       const T* al = tab.alpha_w + (size_t)zs[i] * NREF * NFREQ + w;
       T sq = T(0), s0 = T(0);
@@ -357,61 +389,96 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       for (int a = 0; a < NREF; ++a) {
         const T av = al[a * NFREQ];
         sq += WT(WT_Q)[i * NREF + a] * av;
-        s0 += WT(WT_0)[i * NREF + a] * av;
+        if (GRAD) s0 += WT(WT_0)[i * NREF + a] * av;
       }
-      Aq[w * cap + i] = sq;
-      A0[w * cap + i] = s0;
+      Aq[w * CAP + i] = sq;
+      if (GRAD) A0[w * CAP + i] = s0;
+    }
+    // aliased weights: the q = 0 flavour must survive the two-body pass, which
+    // uses one plane as scratch -> park it in registers
+    constexpr int KEEP = L::wt_alias ? (NREF * CAP + NT - 1) / NT : 1;
+    T w0keep[KEEP];
+    if (L::wt_alias) {
+#pragma unroll
+      for (int m = 0; m < KEEP; ++m) {
+        const int t = tid + m * NT;
+        w0keep[m] = t < NREF * n ? WT(WT_0)[t] : T(0);
+      }
     }
     __syncthreads();
 
     // ---- phase 4: two-body energy (twobody.py:134-201, rational damping) ---
-    if (!GRAD) {
-      for (int p = tid; p < np; p += nthr) {
-        int i, j;
-        pair_decode(p, i, j);
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
-        T e = T(0);
-        if (r2 <= P.disp2_sq) {
-          T c6 = T(0);
+    if constexpr (!GRAD) {
+      if (tid < np) {
+        for (PairIt it(tid); it.p < np; it.advance(NT)) {
+          const int i = it.hi, j = it.lo;
+          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+          const T r2 = dx * dx + dy * dy + dz * dz;
+          T e = T(0);
+          if (r2 <= P.disp2_sq) {
+            T c6 = T(0);
 #pragma unroll
-          for (int w = 0; w < NFREQ; ++w) c6 += Aq[w * cap + i] * Aq[w * cap + j];
-          const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
-          const T qq = T(3) * ATOM(AT_R4R2)[i] * ATOM(AT_R4R2)[j];
-          const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
-          const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
-          T F = P.s6 / (r6 + R6) + P.s8 * qq / (r8 + R8);
-          if (P.s10k != T(0)) F += P.s10k * qq * qq / (r8 * r2 + R8 * R2);
-          e = c6 * F;
+            for (int w = 0; w < NFREQ; ++w) c6 += Aq[w * CAP + i] * Aq[w * CAP + j];
+            const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+            const T R0 = P.a1 * ss + P.a2;
+            const T qq = ss * ss;  // = 3 r4r2_i r4r2_j
+            const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+            const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+            T F = P.s6 * d4_rcp(r6 + R6) + P.s8 * qq * d4_rcp(r8 + R8);
+            if (P.s10k != T(0)) F += P.s10k * qq * qq * d4_rcp(r8 * r2 + R8 * R2);
+            e = c6 * F;
+          }
+          pP[it.p] = e;
         }
-        pP[p] = e;
       }
       __syncthreads();
-      for (int i = tid; i < n; i += nthr) ATOM(AT_E)[i] = T(-0.5) * row_sum(pP, i, n);
+      for (int i = tid; i < n; i += NT) ATOM(AT_E)[i] = T(-0.5) * row_sum(pP, i, n);
+      if (P.has_atm) {
+        __syncthreads();  // row sums done: planes are free again
+        if (L::wt_alias) {
+#pragma unroll
+          for (int m = 0; m < KEEP; ++m) {
+            const int t = tid + m * NT;
+            if (t < NREF * n) WT(WT_0)[t] = w0keep[m];
+          }
+          __syncthreads();
+        }
+        for (int t = tid; t < NFREQ * n; t += NT) {
+          const int i = t / NFREQ, w = t - i * NFREQ;
+          const T* al = tab.alpha_w + (size_t)zs[i] * NREF * NFREQ + w;
+          T s0 = T(0);
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) s0 += WT(WT_0)[i * NREF + a] * al[a * NFREQ];
+          A0[w * CAP + i] = s0;
+        }
+      }
       __syncthreads();
     }
 
     // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
     if (P.has_atm) {
-      for (int p = tid; p < np; p += nthr) {
-        int i, j;
-        pair_decode(p, i, j);
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
-        const T r = d4_sqrt(r2);
-        T c6 = T(0);
+      if (tid < np) {
+        for (PairIt it(tid); it.p < np; it.advance(NT)) {
+          const int i = it.hi, j = it.lo;
+          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+          const T r2 = dx * dx + dy * dy + dz * dz;
+          const T r = d4_sqrt(r2);
+          const T rinv = d4_rcp(r);
+          T c6 = T(0);
 #pragma unroll
-        for (int w = 0; w < NFREQ; ++w) c6 += A0[w * cap + i] * A0[w * cap + j];
-        const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
-        const bool inside = r2 <= P.disp3_sq;
-        if (!inside) misc[2] = 1;
-        pa[p] = inside ? r2 : -r2;
-        pP[p] = P.fac9 * d4_sqrt(fabs(c6)) / (r2 * r);
-        pu[p] = d4_pow(R0 / r, P.alp3);
+          for (int w = 0; w < NFREQ; ++w) c6 += A0[w * CAP + i] * A0[w * CAP + j];
+          const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
+          const bool inside = r2 <= P.disp3_sq;
+          if (!inside) misc[2] = 1;
+          // NB: in the aliased layout this overwrites the (dead) weights
+          pa[it.p] = inside ? r2 : -r2;
+          pP[it.p] = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+          pu[it.p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
+        }
       }
       __syncthreads();
       const bool open = misc[2] != 0;
@@ -419,42 +486,42 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
       // ---- phase 6: triple loop ---------------------------------------------
       // per-CTA, L2-resident scratch for per-pair results (the smem planes are
       // still being read by other warps while results are produced)
-      T* const out0 = A.scratch + (size_t)blockIdx.x * 2 * L.cpairs;
-      T* const out1 = out0 + L.cpairs;
+      T* const out0 = A.scratch + (size_t)blockIdx.x * 2 * CP;
+      T* const out1 = out0 + CP;
       if constexpr (GRAD) {
         // Gradient: one thread per owner pair (j,k), all third atoms i.  Every
         // triple is visited from each of its three pairs, so the per-pair sums
         // Gamma (dL/dC60 numerator) and D (dL/d r^2) need no communication.
-        for (int p = tid; p < np; p += nthr) {
-          int j, k;
-          pair_decode(p, j, k);
-          const T bs = pa[p];
-          const T bb = fabs(bs);
-          const T cjk = bs > T(0) ? T(1) : T(0);
-          const T Pjk = pP[p], ujk = pu[p];
-          const T inv_b = T(1) / bb;
-          const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
-          const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
-          T accH = T(0), accL = T(0), accG = T(0), accD = T(0);
-          for (int i = 0; i < n; ++i) {
-            if (i == j || i == k) continue;
-            const int ti = i * (i - 1) / 2;
-            const int pij = i > j ? ti + j : tj + i;
-            const int pik = i > k ? ti + k : tk + i;
-            if (open)
-              triple_visit<T, true, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb,
-                                          cjk, Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk,
-                                          accH, accL, accG, accD);
-            else
-              triple_visit<T, true, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik],
-                                           bb, cjk, Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk,
-                                           accH, accL, accG, accD);
+        if (tid < np) {
+          for (PairIt it(tid); it.p < np; it.advance(NT)) {
+            const int j = it.hi, k = it.lo, p = it.p;
+            const T bs = pa[p];
+            const T bb = fabs(bs);
+            const T cjk = bs > T(0) ? T(1) : T(0);
+            const T Pjk = pP[p], ujk = pu[p];
+            const T inv_b = d4_rcp(bb);
+            const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
+            const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
+            T accG = T(0), accD = T(0);
+            for (int i = 0; i < n; ++i) {
+              if (i == j || i == k) continue;
+              const int ti = i * (i - 1) / 2;
+              const int pij = i > j ? ti + j : tj + i;
+              const int pik = i > k ? ti + k : tk + i;
+              if (open)
+                grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
+                                    Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD);
+              else
+                grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb,
+                                     cjk, Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG,
+                                     accD);
+            }
+            out0[p] = accG;
+            out1[p] = accD;
           }
-          out0[p] = accG;
-          out1[p] = accD;
         }
         __syncthreads();  // all reads of the stash done -> planes become outputs
-        for (int p = tid; p < np; p += nthr) {  // same thread wrote out0/out1[p]
+        for (int p = tid; p < np; p += NT) {  // same thread wrote out0/out1[p]
           pP[p] = out0[p];
           pu[p] = out1[p];
         }
@@ -465,7 +532,7 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
         // entry in registers) and sweeps the top atom i; the shares of atoms j
         // and k accumulate in lane registers, the share of atom i is reduced
         // over the lanes with a batched (transposed) shuffle reduction.
-        T* const Tw = Aq + (size_t)(tid >> 5) * cap;  // A vectors are dead: per-warp E_i partials
+        T* const Tw = Aq + (tid >> 5) * CAP;  // A vectors are dead: per-warp E_i partials
         for (int i = lane; i < n; i += 32) Tw[i] = T(0);
         __syncwarp();
         const int nchunks = (np + 31) >> 5;
@@ -478,7 +545,11 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
           const int p = chunk * 32 + lane;
           const bool valid = p < np;
           int j = 1 << 20, k = 0;
-          if (valid) pair_decode(p, j, k);
+          if (valid) {
+            PairIt it(p);
+            j = it.hi;
+            k = it.lo;
+          }
           const int jmin = __shfl_sync(0xffffffffu, j, 0);
           const T bs = valid ? pa[p] : T(1);
           const T Pjk = valid ? pP[p] : T(0), ujk = valid ? pu[p] : T(0);
@@ -492,9 +563,12 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
               const int i = i0 + u;
               T ei = T(0);
               if (i < n && i > j) {
-                const int ti = i * (i - 1) / 2;
-                const T a_s = pa[ti + j], c_s = pa[ti + k];
-                T a = a_s, c = c_s, mi = T(1), mj = T(1), mk = T(1);
+                const T* row = pa + i * (i - 1) / 2;
+                const T a_s = row[j], c_s = row[k];
+                T a = a_s, c = c_s;
+                const T t = row[2 * CP + j] * row[2 * CP + k] * ujk;
+                const T pp = row[CP + j] * row[CP + k] * Pjk;
+                T mi = T(1), mj = T(1), mk = T(1);
                 if (open) {
                   const T cij = a_s > T(0) ? T(1) : T(0);
                   const T cik = c_s > T(0) ? T(1) : T(0);
@@ -506,14 +580,17 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
                 }
                 const T X = a + bb - c, Y = a - bb + c, Z = bb + c - a;
                 const T abc = a * bb * c;
-                const T t = pu[ti + j] * pu[ti + k] * ujk;
                 const T d = T(1) + T(6) * t;
-                const T inv = T(1) / (abc * d);
-                const T psf = pP[ti + j] * pP[ti + k] * Pjk * (inv * abc);
-                const T e = (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) * psf;
-                accJ += mj * e;
-                accK += mk * e;
-                ei = mi * e;
+                const T inv = d4_rcp(abc * d);
+                const T e = (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) * (pp * (inv * abc));
+                if (open) {
+                  accJ += mj * e;
+                  accK += mk * e;
+                  ei = mi * e;
+                } else {
+                  accJ += e;
+                  ei = e;
+                }
               }
               v[u] = ei;
             }
@@ -537,24 +614,24 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
           }
           if (valid) {
             out0[p] = accJ;
-            out1[p] = accK;
+            out1[p] = open ? accK : accJ;
           }
         }
         __syncthreads();
         const T scale = open ? T(1) : T(2);  // closed triples: every atom has multiplicity 2
-        const int nwarps = nthr >> 5;
-        for (int i = tid; i < n; i += nthr) {
+        for (int i = tid; i < n; i += NT) {
           T s = T(0);
           const int ti = i * (i - 1) / 2;
           for (int j = 0; j < i; ++j) s += out0[ti + j];
           for (int j = i + 1; j < n; ++j) s += out1[j * (j - 1) / 2 + i];
-          for (int w = 0; w < nwarps; ++w) s += Aq[(size_t)w * cap + i];
+#pragma unroll
+          for (int w = 0; w < NT / 32; ++w) s += Aq[w * CAP + i];
           ATOM(AT_E)[i] += scale * s;
         }
         __syncthreads();
       }
     } else if (GRAD) {
-      for (int p = tid; p < np; p += nthr) {
+      for (int p = tid; p < np; p += NT) {
         pP[p] = T(0);
         pu[p] = T(0);
       }
@@ -562,136 +639,140 @@ __global__ void __launch_bounds__(512) small_kernel(SmallArgs<T> A) {
     }
 
     if constexpr (!GRAD) {
-      for (int i = tid; i < n; i += nthr) A.energy[(size_t)b * A.nat + idx[i]] = ATOM(AT_E)[i];
+      for (int i = tid; i < n; i += NT) A.energy[(size_t)b * A.nat + idx[i]] = ATOM(AT_E)[i];
     } else {
-
-    // =================== gradient back-propagation ===========================
-    // phase 7: per-pair coefficients
-    //   pa <- G2 F          (dL/dC6q)
-    //   pP <- Gamma/(2 C60) (dL/dC60)
-    //   pu <- 2 D + G2 C6q F'/r   (radial force coefficient, CN chain added later)
-    for (int p = tid; p < np; p += nthr) {
-      int i, j;
-      pair_decode(p, i, j);
-      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-      const T r2 = dx * dx + dy * dy + dz * dz;
-      T c6q = T(0), c60 = T(0);
+      // =================== gradient back-propagation =========================
+      // phase 7: per-pair coefficients
+      //   pa <- G2 F          (dL/dC6q)
+      //   pP <- Gamma/(2 C60) (dL/dC60)
+      //   pu <- 2 D + G2 C6q F'/r   (radial force coefficient, CN chain added later)
+      if (tid < np) {
+        for (PairIt it(tid); it.p < np; it.advance(NT)) {
+          const int i = it.hi, j = it.lo, p = it.p;
+          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+          const T r2 = dx * dx + dy * dy + dz * dz;
+          T c6q = T(0), c60 = T(0);
 #pragma unroll
-      for (int w = 0; w < NFREQ; ++w) {
-        c6q += Aq[w * cap + i] * Aq[w * cap + j];
-        c60 += A0[w * cap + i] * A0[w * cap + j];
-      }
-      const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
-      T coefq = T(0), fc = T(2) * pu[p];
-      if (r2 <= P.disp2_sq) {
-        const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
-        const T qq = T(3) * ATOM(AT_R4R2)[i] * ATOM(AT_R4R2)[j];
-        const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
-        const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
-        const T t6 = T(1) / (r6 + R6), t8 = T(1) / (r8 + R8);
-        T F = P.s6 * t6 + P.s8 * qq * t8;
-        // dF/dr / r
-        T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
-        if (P.s10k != T(0)) {
-          const T t10 = T(1) / (r8 * r2 + R8 * R2);
-          F += P.s10k * qq * qq * t10;
-          dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
+          for (int w = 0; w < NFREQ; ++w) {
+            c6q += Aq[w * CAP + i] * Aq[w * CAP + j];
+            c60 += A0[w * CAP + i] * A0[w * CAP + j];
+          }
+          const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
+          T coefq = T(0), fc = T(2) * pu[p];
+          if (r2 <= P.disp2_sq) {
+            const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+            const T R0 = P.a1 * ss + P.a2;
+            const T qq = ss * ss;
+            const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+            const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+            const T t6 = d4_rcp(r6 + R6), t8 = d4_rcp(r8 + R8);
+            T F = P.s6 * t6 + P.s8 * qq * t8;
+            // dF/dr / r
+            T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
+            if (P.s10k != T(0)) {
+              const T t10 = d4_rcp(r8 * r2 + R8 * R2);
+              F += P.s10k * qq * qq * t10;
+              dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
+            }
+            coefq = G2 * F;
+            fc += G2 * c6q * dF;
+          }
+          pa[p] = coefq;
+          pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
+          pu[p] = fc;
         }
-        coefq = G2 * F;
-        fc += G2 * c6q * dF;
       }
-      pa[p] = coefq;
-      pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
-      pu[p] = fc;
-    }
-    __syncthreads();
-    // phase 8: B_i[w] = sum_j coef_ij A_j[w]
-    for (int t = tid; t < NFREQ * n; t += nthr) {
-      const int w = t / n, i = t - w * n;
-      const int ti = i * (i - 1) / 2;
-      T sq = T(0), s0 = T(0);
-      for (int j = 0; j < i; ++j) {
-        sq += pa[ti + j] * Aq[w * cap + j];
-        s0 += pP[ti + j] * A0[w * cap + j];
+      __syncthreads();
+      // phase 8: B_i[w] = sum_j coef_ij A_j[w]
+      for (int t = tid; t < NFREQ * n; t += NT) {
+        const int w = t / n, i = t - w * n;
+        const int ti = i * (i - 1) / 2;
+        T sq = T(0), s0 = T(0);
+        for (int j = 0; j < i; ++j) {
+          sq += pa[ti + j] * Aq[w * CAP + j];
+          s0 += pP[ti + j] * A0[w * CAP + j];
+        }
+        for (int j = i + 1; j < n; ++j) {
+          const int pj = j * (j - 1) / 2 + i;
+          sq += pa[pj] * Aq[w * CAP + j];
+          s0 += pP[pj] * A0[w * CAP + j];
+        }
+        Bq[w * CAP + i] = sq;
+        B0[w * CAP + i] = s0;
       }
-      for (int j = i + 1; j < n; ++j) {
-        const int pj = j * (j - 1) / 2 + i;
-        sq += pa[pj] * Aq[w * cap + j];
-        s0 += pP[pj] * A0[w * cap + j];
-      }
-      Bq[w * cap + i] = sq;
-      B0[w * cap + i] = s0;
-    }
-    __syncthreads();
-    // phase 9: project on the references -> dL/dcn_i, dL/dq_i
-    T* const tcn = pa;                // [7n] partial dL/dcn (pa is free again)
-    T* const tq = pa + NREF * cap;    // [7n] partial dL/dq
-    for (int t = tid; t < NREF * n; t += nthr) {
-      const int i = t / NREF, a = t - i * NREF;
-      const T* al = tab.alpha_w + ((size_t)zs[i] * NREF + a) * NFREQ;
-      T pq = T(0), p0 = T(0);
+      __syncthreads();
+      // phase 9: project on the references -> dL/dcn_i, dL/dq_i
+      T* const tcn = pa;              // [7n] partial dL/dcn (pa is free again)
+      T* const tq = pa + NREF * CAP;  // [7n] partial dL/dq
+      for (int t = tid; t < NREF * n; t += NT) {
+        const int i = t / NREF, a = t - i * NREF;
+        const T* al = tab.alpha_w + ((size_t)zs[i] * NREF + a) * NFREQ;
+        T pq = T(0), p0 = T(0);
 #pragma unroll
-      for (int w = 0; w < NFREQ; ++w) {
-        const T av = al[w];
-        pq += av * Bq[w * cap + i];
-        p0 += av * B0[w * cap + i];
+        for (int w = 0; w < NFREQ; ++w) {
+          const T av = al[w];
+          pq += av * Bq[w * CAP + i];
+          p0 += av * B0[w * CAP + i];
+        }
+        tcn[t] = WT(WT_ZGD)[t] * pq + WT(WT_Z0GD)[t] * p0;
+        tq[t] = WT(WT_DZG)[t] * pq;
       }
-      tcn[t] = WT(WT_ZGD)[t] * pq + WT(WT_Z0GD)[t] * p0;
-      tq[t] = WT(WT_DZG)[t] * pq;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += nthr) {
-      T sc = T(0), sq = T(0);
+      __syncthreads();
+      for (int i = tid; i < n; i += NT) {
+        T sc = T(0), sq = T(0);
 #pragma unroll
-      for (int a = 0; a < NREF; ++a) {
-        sc += tcn[i * NREF + a];
-        sq += tq[i * NREF + a];
+        for (int a = 0; a < NREF; ++a) {
+          sc += tcn[i * NREF + a];
+          sq += tq[i * NREF + a];
+        }
+        ATOM(AT_DCN)[i] = sc;
+        ATOM(AT_DQ)[i] = sq;
       }
-      ATOM(AT_DCN)[i] = sc;
-      ATOM(AT_DQ)[i] = sq;
+      __syncthreads();
+      // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
+      if (tid < np) {
+        for (PairIt it(tid); it.p < np; it.advance(NT)) {
+          const int i = it.hi, j = it.lo;
+          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+          const T r2 = dx * dx + dy * dy + dz * dz;
+          if (r2 <= P.cn_sq) {
+            const T r = d4_sqrt(r2);
+            const T r0inv = d4_rcp(ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j]);
+            const T xx = T(7.5) * (r * r0inv - T(1));
+            if (fabs(xx) < T(8.7)) {  // exp(-x^2) < 1e-32 beyond
+              const T dcn = -tab.den[zs[i] * NELEM + zs[j]] * T(7.5) * T(0.5641895835477563) *
+                            r0inv * d4_exp(-xx * xx);
+              pu[it.p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn * d4_rcp(r);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // phase 11: gather forces
+      for (int i = tid; i < n; i += NT) {
+        const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
+        T fx = T(0), fy = T(0), fz = T(0);
+        const int ti = i * (i - 1) / 2;
+        for (int j = 0; j < n; ++j) {
+          if (j == i) continue;
+          const T c = j < i ? pu[ti + j] : pu[j * (j - 1) / 2 + i];
+          fx += c * (xi - ATOM(AT_X)[j]);
+          fy += c * (yi - ATOM(AT_Y)[j]);
+          fz += c * (zi - ATOM(AT_Z)[j]);
+        }
+        const size_t o = (size_t)b * A.nat + idx[i];
+        if (A.grad) {
+          A.grad[3 * o] = fx;
+          A.grad[3 * o + 1] = fy;
+          A.grad[3 * o + 2] = fz;
+        }
+        if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
+      }
     }
-    __syncthreads();
-    // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
-    for (int p = tid; p < np; p += nthr) {
-      int i, j;
-      pair_decode(p, i, j);
-      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-      const T r2 = dx * dx + dy * dy + dz * dz;
-      if (r2 <= P.cn_sq) {
-        const T r = d4_sqrt(r2);
-        const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
-        const T xx = T(7.5) * (r / r0 - T(1));
-        const T dcn = -tab.den[zs[i] * NELEM + zs[j]] * T(7.5) * T(0.5641895835477563) / r0 *
-                      d4_exp(-xx * xx);
-        pu[p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn / r;
-      }
-    }
-    __syncthreads();
-    // phase 11: gather forces
-    for (int i = tid; i < n; i += nthr) {
-      const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
-      T fx = T(0), fy = T(0), fz = T(0);
-      const int ti = i * (i - 1) / 2;
-      for (int j = 0; j < n; ++j) {
-        if (j == i) continue;
-        const T c = j < i ? pu[ti + j] : pu[j * (j - 1) / 2 + i];
-        fx += c * (xi - ATOM(AT_X)[j]);
-        fy += c * (yi - ATOM(AT_Y)[j]);
-        fz += c * (zi - ATOM(AT_Z)[j]);
-      }
-      const size_t o = (size_t)b * A.nat + idx[i];
-      if (A.grad) {
-        A.grad[3 * o] = fx;
-        A.grad[3 * o + 1] = fy;
-        A.grad[3 * o + 2] = fz;
-      }
-      if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
-    }
-    }  // GRAD
   }
 #undef ATOM
 #undef WT

@@ -22,10 +22,16 @@ def _t(x, device, dtype):
     return torch.tensor(x, device=device, dtype=dtype)
 
 
+def _f(x):
+    """Python float of a cutoff given as a number (tensors are converted lazily,
+    a device tensor costs one synchronisation)."""
+    return None if isinstance(x, torch.Tensor) else float(x)
+
+
 class Cutoff:
     """Collection of real-space cutoffs (Bohr)."""
 
-    __slots__ = ("disp2", "disp3", "cn", "cn_eeq", "_device", "_dtype")
+    __slots__ = ("disp2", "disp3", "cn", "cn_eeq", "_device", "_dtype", "_floats")
 
     def __init__(
         self,
@@ -42,6 +48,15 @@ class Cutoff:
         self.disp3 = _t(disp3, device, dtype)
         self.cn = _t(cn, device, dtype)
         self.cn_eeq = _t(cn_eeq, device, dtype)
+        self._floats = {"disp2": _f(disp2), "disp3": _f(disp3), "cn": _f(cn), "cn_eeq": _f(cn_eeq)}
+
+    def as_float(self, name: str) -> float:
+        """Host value of a cutoff without touching the device when it was given
+        as a Python number."""
+        v = self._floats.get(name)
+        if v is None:
+            v = self._floats[name] = float(getattr(self, name))
+        return v
 
     @property
     def device(self):

@@ -16,6 +16,7 @@ There is no CPU path and no PyTorch fallback: tensors must live on a B200.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Any
 
 import numpy as np
@@ -162,14 +163,29 @@ class _D4Function(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 # argument handling
 # ---------------------------------------------------------------------------
+_SCALAR_CACHE: dict[int, tuple[Any, int, float]] = {}
+
+
 def _scalar(v: Any, name: str) -> float:
+    """Host value of a damping parameter.  Device tensors (the reference's
+    examples build them with ``positions.new_tensor``) cost one synchronisation
+    the first time they are seen; the value is cached per tensor version."""
     if isinstance(v, Tensor):
         if v.requires_grad:
             raise NotImplementedError(
                 f"gradients with respect to the damping parameter '{name}' are not provided "
                 "by the fused kernels (SURVEY.md 8f-3)"
             )
-        return float(v)
+        if v.device.type == "cpu":
+            return float(v)
+        hit = _SCALAR_CACHE.get(id(v))
+        if hit is not None and hit[0]() is v and hit[1] == v._version:
+            return hit[2]
+        val = float(v)
+        if len(_SCALAR_CACHE) > 256:
+            _SCALAR_CACHE.clear()
+        _SCALAR_CACHE[id(v)] = (weakref.ref(v), v._version, val)
+        return val
     return float(v)
 
 
@@ -188,8 +204,12 @@ def _flatten_param(param: Param, cutoff: Cutoff | None, model_id: int, wf: float
     par.a1 = _scalar(param["a1"], "a1")
     par.a2 = _scalar(param["a2"], "a2")
     par.alp = _scalar(param.get("alp", defaults.ALP), "alp")
-    par.disp2_cutoff = float(cutoff.disp2) if cutoff is not None else defaults.D4_DISP2_CUTOFF
-    par.disp3_cutoff = float(cutoff.disp3) if cutoff is not None else defaults.D4_DISP3_CUTOFF
+    if cutoff is None:
+        par.disp2_cutoff, par.disp3_cutoff = defaults.D4_DISP2_CUTOFF, defaults.D4_DISP3_CUTOFF
+    elif hasattr(cutoff, "as_float"):
+        par.disp2_cutoff, par.disp3_cutoff = cutoff.as_float("disp2"), cutoff.as_float("disp3")
+    else:  # e.g. the reference's own Cutoff object
+        par.disp2_cutoff, par.disp3_cutoff = float(cutoff.disp2), float(cutoff.disp3)
     par.cn_cutoff = defaults.D4_CN_CUTOFF  # Cutoff.cn is not forwarded (dispersion/base.py:390)
     par.wf = wf
     par.model = model_id
@@ -285,11 +305,10 @@ def dftd4(
     if model_id == 1:
         raise NotImplementedError("the D4S model is not yet available in the fused kernels")
 
-    if cutoff is None:
-        cutoff = Cutoff(device=positions.device, dtype=positions.dtype)
     if q is None:
         chg = charge if isinstance(charge, Tensor) else torch.tensor(charge)
-        q = _eeq_charges(numbers, positions, chg.to(positions.device, positions.dtype), cutoff)
+        eeq_cut = cutoff if cutoff is not None else Cutoff(device=positions.device, dtype=positions.dtype)
+        q = _eeq_charges(numbers, positions, chg.to(positions.device, positions.dtype), eeq_cut)
     if numbers.shape != q.shape:
         raise ValueError(
             f"Shape of atomic charges ({q.shape}) is not consistent "

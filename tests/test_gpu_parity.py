@@ -49,7 +49,7 @@ def _small(name):
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_energy_f64(name):
     case = load_golden(name)
-    if _small(name) > 112:
+    if _small(name) > 128:
         pytest.skip("beyond the FP64 small-family limit")
     e, _ = _run(case, torch.float64, grad=False)
     ref = case["energy_d4"]
