@@ -142,6 +142,11 @@ int d4b200_class_caps(d4b200_tables_t tables, int fp32, int grad, int* caps_out 
 int d4b200_measure_fp64_peak(d4b200_tables_t tables, void* scratch_dev, size_t scratch_bytes,
                              void* stream, double* tflops_out);
 
+/* Development profiling: accumulate clock64() cycles per kernel phase (16 slots per
+ * size class); ``out`` (optional) receives and resets the counters. */
+int d4b200_phase_profile(d4b200_tables_t tables, int enable,
+                         unsigned long long* out /*[D4B200_NCLASS * 16] or NULL*/);
+
 #ifdef __cplusplus
 }
 #endif

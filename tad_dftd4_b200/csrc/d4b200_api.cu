@@ -33,6 +33,8 @@ struct d4b200_tables {
   int profile;
   cudaEvent_t ev[2 * NCLASS];
   cudaEvent_t ev_call[3];  // call start, prep done, call end
+  unsigned long long* phase_dev;  // [NCLASS][16] per-phase cycle counters (development)
+  int phase_on;
   int ev_used[NCLASS];
 };
 
@@ -298,6 +300,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   A.grad = grad;
   A.gradq = gradq;
   A.nbatch = nbatch;
+  A.phase = nullptr;
   A.nat = nat;
   if constexpr (dt == 0) {
     A.tab = h->t64;
@@ -319,6 +322,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
     size_t sbytes = scratch_bytes_class(c, cap, sizeof(T));
     if (nat >= lo || c == 0) {
       A.cls = c;
+      A.phase = h->phase_on ? h->phase_dev + 16 * c : nullptr;
       A.scratch = reinterpret_cast<T*>(scratch);
       long grid = (long)h->grid_per_sm[dt][gr][c] * h->num_sms;
       if (grid > nbatch) grid = nbatch;
@@ -430,6 +434,7 @@ int d4b200_tables_destroy(d4b200_tables_t h) {
     if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  cudaFree(h->phase_dev);
   cudaFree(h->f64);
   cudaFree(h->f32);
   cudaFree(h->i32);
@@ -482,6 +487,24 @@ int d4b200_status(void* ws, void* stream, int* bits) {
 }
 
 int d4b200_last_launch_count(void) { return g_launches; }
+
+// development profiling: per-phase cycle counters of the small-family kernels
+int d4b200_phase_profile(d4b200_tables_t h, int enable, unsigned long long* out /*[NCLASS*16] or NULL*/) {
+  if (!h) return D4B200_EINVAL;
+  if (!h->phase_dev) {
+    cudaError_t e = cudaMalloc(&h->phase_dev, sizeof(unsigned long long) * 16 * NCLASS);
+    if (e != cudaSuccess) return (int)e;
+    cudaMemset(h->phase_dev, 0, sizeof(unsigned long long) * 16 * NCLASS);
+  }
+  if (out) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    cudaMemcpy(out, h->phase_dev, sizeof(unsigned long long) * 16 * NCLASS, cudaMemcpyDeviceToHost);
+    cudaMemset(h->phase_dev, 0, sizeof(unsigned long long) * 16 * NCLASS);
+  }
+  h->phase_on = enable != 0;
+  return 0;
+}
 
 int d4b200_profile_enable(d4b200_tables_t h, int enable) {
   if (!h) return D4B200_EINVAL;

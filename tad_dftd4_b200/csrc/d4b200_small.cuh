@@ -33,8 +33,9 @@ struct SmallArgs {
   T* cn_out;
   T* grad;
   T* gradq;
-  T* scratch;  // [gridDim.x][2][CAP(CAP-1)/2] per-CTA pair results of the triple loop
+  T* scratch;  // [gridDim.x][2 or 3][CAP(CAP-1)/2] per-CTA, L2-resident per-pair results
   int nbatch, nat, cls;
+  unsigned long long* phase;  // optional [16] per-phase cycle counters (development profiling)
   Tables<T> tab;
   Par<T> par;
   Work wk;
@@ -96,50 +97,78 @@ template <typename T, bool GRAD, int CAP>
 struct Lay {
   static constexpr int CP = CAP * (CAP - 1) / 2;
   static constexpr size_t plane_bytes = size_t(3) * CP * sizeof(T);
-  static constexpr size_t wtmp_bytes = size_t(3) * NREF * CAP * sizeof(double);
-  // energy kernel: the weights live on top of the (not yet used) planes, right
-  // after their float64 temporaries, when they fit; the gradient kernel needs
-  // the weights until the end
-  static constexpr bool wt_alias =
-      !GRAD && wtmp_bytes + size_t(2) * NREF * CAP * sizeof(T) <= plane_bytes;
+  // energy kernel: the weights live on top of the (not yet used) planes when they
+  // fit; the gradient kernel needs the weights until the end
+  static constexpr bool wt_alias = !GRAD && size_t(2) * NREF * CAP * sizeof(T) <= plane_bytes;
   static constexpr int n_abuf = GRAD ? 4 : 1;  // energy: Aq, then A0 in the same buffer
   static constexpr int n_atom = GRAD ? 11 : 8;
   static constexpr int n_wt = GRAD ? 5 : (wt_alias ? 0 : 2);
   static constexpr size_t planes = 0;
-  static constexpr size_t abuf = al16(plane_bytes > wtmp_bytes ? plane_bytes : wtmp_bytes);
+  static constexpr size_t abuf = al16(plane_bytes);
   static constexpr size_t atoms = abuf + al16(size_t(n_abuf) * NFREQ * CAP * sizeof(T));
   static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
   static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
   static constexpr size_t total = ints + al16((2 * CAP + 8) * sizeof(int));
+  static constexpr int scratch_planes = 2;
 };
 
-// triangular pair index walker: p = hi(hi-1)/2 + lo, hi > lo
-struct PairIt {
-  int p, hi, lo;
-  __device__ __forceinline__ explicit PairIt(int p0) : p(p0) {
-    int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p0)) * 0.5f);
-    while (i * (i - 1) / 2 > p0) --i;
-    while ((i + 1) * i / 2 <= p0) ++i;
-    hi = i;
-    lo = p0 - i * (i - 1) / 2;
+// p -> (hi, lo) with hi > lo and p = hi(hi-1)/2 + lo
+__device__ __forceinline__ void pair_decode(int p, int& hi, int& lo) {
+  int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+  if (i * (i - 1) / 2 > p) --i;
+  if ((i + 1) * i / 2 <= p) ++i;
+  hi = i;
+  lo = p - i * (i - 1) / 2;
+}
+
+// A_i . A_j over the 23 frequencies with four independent accumulators (a single
+// chain of 23 dependent FMAs is latency bound)
+template <typename T, int CAP>
+__device__ __forceinline__ T dot23(const T* __restrict__ A, int i, int j) {
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll
+  for (int w = 0; w + 4 <= NFREQ; w += 4) {
+    s0 += A[w * CAP + i] * A[w * CAP + j];
+    s1 += A[(w + 1) * CAP + i] * A[(w + 1) * CAP + j];
+    s2 += A[(w + 2) * CAP + i] * A[(w + 2) * CAP + j];
+    s3 += A[(w + 3) * CAP + i] * A[(w + 3) * CAP + j];
   }
-  __device__ __forceinline__ void advance(int step) {
-    p += step;
-    lo += step;
-    while (lo >= hi) {
-      lo -= hi;
-      ++hi;
-    }
-  }
-};
+  s0 += A[20 * CAP + i] * A[20 * CAP + j];
+  s1 += A[21 * CAP + i] * A[21 * CAP + j];
+  s2 += A[22 * CAP + i] * A[22 * CAP + j];
+  return (s0 + s1) + (s2 + s3);
+}
 
 template <typename T>
-__device__ __forceinline__ T row_sum(const T* __restrict__ plane, int i, int n) {
-  T s = T(0);
-  const int ti = i * (i - 1) / 2;
-  for (int j = 0; j < i; ++j) s += plane[ti + j];
-  for (int j = i + 1; j < n; ++j) s += plane[j * (j - 1) / 2 + i];
-  return s;
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum_j lo[pair(i,j)] over j < i  +  sum_j hi[pair(j,i)] over j > i, one thread per
+// row with four independent accumulators (the row phases are latency bound)
+template <typename T>
+__device__ __forceinline__ T row_sum2(const T* __restrict__ lo, const T* __restrict__ hi, int i, int n) {
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+  const T* r = lo + i * (i - 1) / 2;
+  int j = 0;
+  for (; j + 4 <= i; j += 4) {
+    s0 += r[j];
+    s1 += r[j + 1];
+    s2 += r[j + 2];
+    s3 += r[j + 3];
+  }
+  for (; j < i; ++j) s0 += r[j];
+  j = i + 1;
+  int tj = j * (j - 1) / 2 + i;
+  for (; j + 2 <= n; j += 2) {
+    s1 += hi[tj];
+    s2 += hi[tj + j];
+    tj += 2 * j + 1;
+  }
+  if (j < n) s3 += hi[tj];
+  return (s0 + s1) + (s2 + s3);
 }
 
 // Gradient triple visit: owner pair (j,k) with r^2 = b, third atom i with the
@@ -178,21 +207,84 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   accD += W * de;
 }
 
+// One block of 8 consecutive top atoms i0..i0+7 for the lane's bottom pair (j,k);
+// `all` = every lane is active for all eight rows (warp-uniform), otherwise rows
+// are predicated per lane.  One instantiation per mask flavour keeps the hot loop
+// inside the instruction cache.
+template <typename T, int CP, bool OPEN>
+__device__ __forceinline__ void triple_block8(const T* __restrict__ colj, const T* __restrict__ colk,
+                                              int i0, int j, int n, bool all, T bb, T cjk, T Pjk,
+                                              T ujk, T& accJ, T& accK, T (&v)[8]) {
+  int ti = i0 * (i0 - 1) / 2;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = i0 + u;
+    T ei = T(0);
+    if (all || (i < n && i > j)) {
+      const T a_s = colj[ti], c_s = colk[ti];
+      const T t = colj[ti + 2 * CP] * colk[ti + 2 * CP] * ujk;
+      const T pp = colj[ti + CP] * colk[ti + CP] * Pjk;
+      T a = a_s, c = c_s;
+      T mi = T(1), mj = T(1), mk = T(1);
+      if (OPEN) {
+        const T cij = a_s > T(0) ? T(1) : T(0);
+        const T cik = c_s > T(0) ? T(1) : T(0);
+        a = fabs(a_s);
+        c = fabs(c_s);
+        mi = cjk * (cij + cik);
+        mj = cik * (cij + cjk);
+        mk = cij * (cik + cjk);
+      }
+      const T X = a + bb - c, Y = a - bb + c, Z = bb + c - a;
+      const T abc = a * bb * c;
+      const T d = T(1) + T(6) * t;
+      const T inv = d4_rcp(abc * d);
+      const T e = (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) * (pp * (inv * abc));
+      if (OPEN) {
+        accJ += mj * e;
+        accK += mk * e;
+        ei = mi * e;
+      } else {
+        accJ += e;
+        ei = e;
+      }
+    }
+    v[u] = ei;
+    ti += i;
+  }
+}
+
+// transposed reduction: 8 values x 32 lanes -> lane group (lane>>2) holds the sum of v[lane>>2]
+template <typename T>
+__device__ __forceinline__ T reduce8x32(const T (&v)[8], bool b4, bool b3, bool b2) {
+  const T s0 = b4 ? v[0] : v[4], s1 = b4 ? v[1] : v[5], s2 = b4 ? v[2] : v[6], s3 = b4 ? v[3] : v[7];
+  const T w0 = (b4 ? v[4] : v[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
+  const T w1 = (b4 ? v[5] : v[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
+  const T w2 = (b4 ? v[6] : v[2]) + __shfl_xor_sync(0xffffffffu, s2, 16);
+  const T w3 = (b4 ? v[7] : v[3]) + __shfl_xor_sync(0xffffffffu, s3, 16);
+  const T x0 = (b3 ? w2 : w0) + __shfl_xor_sync(0xffffffffu, b3 ? w0 : w2, 8);
+  const T x1 = (b3 ? w3 : w1) + __shfl_xor_sync(0xffffffffu, b3 ? w1 : w3, 8);
+  T y = (b2 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, b2 ? x0 : x1, 4);
+  y += __shfl_xor_sync(0xffffffffu, y, 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  return y;
+}
+
 template <typename T, bool GRAD, int CAP, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   using L = Lay<T, GRAD, CAP>;
   constexpr int CP = L::CP;
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem[];
   T* const pa = reinterpret_cast<T*>(smem + L::planes);
   T* const pP = pa + CP;
   T* const pu = pP + CP;
-  double* const wtmp = reinterpret_cast<double*>(smem + L::planes);  // aliases the planes
   T* const Aq = reinterpret_cast<T*>(smem + L::abuf);
   T* const A0 = GRAD ? Aq + NFREQ * CAP : Aq;
   T* const Bq = Aq + 2 * NFREQ * CAP;  // GRAD only
   T* const B0 = Aq + 3 * NFREQ * CAP;  // GRAD only
   T* const at = reinterpret_cast<T*>(smem + L::atoms);
-  T* const wt = L::wt_alias ? reinterpret_cast<T*>(smem + L::planes + L::wtmp_bytes)
+  T* const wt = L::wt_alias ? reinterpret_cast<T*>(smem + L::planes)
                             : reinterpret_cast<T*>(smem + L::wts);
   int* const zs = reinterpret_cast<int*>(smem + L::ints);
   int* const idx = zs + CAP;
@@ -202,10 +294,21 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
   const Par<T>& P = A.par;
   const Tables<T>& tab = A.tab;
   const int range_begin = A.wk.class_range[2 * A.cls];
   const int range_end = A.wk.class_range[2 * A.cls + 1];
+  // per-CTA, L2-resident scratch planes for per-pair results
+  T* const out0 = A.scratch + (size_t)blockIdx.x * L::scratch_planes * CP;
+  T* const out1 = out0 + CP;
+  long long tlast = A.phase ? clock64() : 0;
+#define PHASE(k)                                                        \
+  if (A.phase && tid == 0) {                                            \
+    const long long now = clock64();                                    \
+    atomicAdd(&A.phase[k], (unsigned long long)(now - tlast));          \
+    tlast = now;                                                        \
+  }
 
   while (true) {
     __syncthreads();  // previous structure fully written, misc[] reusable
@@ -278,105 +381,96 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       if (GRAD) ATOM(AT_G)[i] = A.gin ? A.gin[o] : T(1);
     }
     __syncthreads();
+    PHASE(0);
 
     // ---- phase 1: coordination number (tad_mctc cn_d4 / erf_count) ----------
-    if (tid < np) {
-      for (PairIt it(tid); it.p < np; it.advance(NT)) {
-        const int i = it.hi, j = it.lo;
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
-        T cf = T(0);
-        if (r2 <= P.cn_sq) {
-          const T r = d4_sqrt(r2);
-          const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
-          const T xx = T(7.5) * (r * d4_rcp(r0) - T(1));
-          if (xx < d4_erfc_cut(T(0)))
-            cf = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(xx);
-        }
-        pu[it.p] = cf;
+#pragma unroll 2
+    for (int p = tid; p < np; p += NT) {
+      int i, j;
+      pair_decode(p, i, j);
+      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+      const T r2 = dx * dx + dy * dy + dz * dz;
+      T cf = T(0);
+      if (r2 <= P.cn_sq) {
+        const T r = d4_sqrt(r2);
+        const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
+        const T xx = T(7.5) * (r * d4_rcp(r0) - T(1));
+        if (xx < d4_erfc_cut(T(0))) cf = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(xx);
       }
+      pu[p] = cf;
     }
     __syncthreads();
+    PHASE(1);
     for (int i = tid; i < n; i += NT) {
-      const T c = row_sum(pu, i, n);
+      const T c = row_sum2(pu, pu, i, n);
       ATOM(AT_CN)[i] = c;
       if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = c;
     }
     __syncthreads();
+    PHASE(2);
 
     // ---- phase 2: Gaussian weights (float64 always) x zeta -----------------
     // model/d4.py:137-228; max-shifted exponentials instead of pow(exp(-d^2), k wf).
-    double* const warg = wtmp;
-    double* const wS = wtmp + NREF * CAP;
-    double* const wdS = wtmp + 2 * NREF * CAP;
-    for (int t = tid; t < NREF * n; t += NT) {
-      const int i = t / NREF, a = t - i * NREF;
-      const int z = zs[i];
-      const double d = (double)ATOM(AT_CN)[i] - tab.refcn[z * NREF + a];
-      warg[t] = tab.refc[z * NREF + a] > 0 ? P.wf * d * d : 1e300;
-    }
-    __syncthreads();
-    for (int t = tid; t < NREF * n; t += NT) {
-      const int i = t / NREF, a = t - i * NREF;
-      const int z = zs[i];
-      const int rc = tab.refc[z * NREF + a];
-      double shift = 1e300;
+    // Eight lanes per atom (one per reference, one idle): the shift (min exponent)
+    // and the normalisation are 8-lane shuffle reductions, no shared temporaries.
+    for (int t = tid; t < 8 * CAP; t += NT) {
+      const int i = t >> 3, a = t & 7;
+      const bool on = i < n && a < NREF;
+      const int z = on ? zs[i] : 0;
+      const int rc = on ? tab.refc[z * NREF + a] : 0;
+      const double cn_i = on ? (double)ATOM(AT_CN)[i] : 0.0;
+      const double d = on ? cn_i - tab.refcn[z * NREF + a] : 0.0;
+      const double arg = rc > 0 ? P.wf * d * d : 1e300;
+      double shift = arg;
 #pragma unroll
-      for (int aa = 0; aa < NREF; ++aa) shift = fmin(shift, warg[i * NREF + aa]);
+      for (int o = 4; o > 0; o >>= 1) shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, o));
       double S = 0.0, dS = 0.0;
-      if (rc > 0) {
-        const double arg = warg[t];
-        const double d = (double)ATOM(AT_CN)[i] - tab.refcn[z * NREF + a];
-        for (int k = 1; k <= rc; ++k) {
-          const double e = exp(-((double)k * arg - shift));
-          S += e;
-          dS += -2.0 * (double)k * P.wf * d * e;
-        }
+      for (int k = 1; k <= rc; ++k) {
+        const double e = exp(-((double)k * arg - shift));
+        S += e;
+        dS += -2.0 * (double)k * P.wf * d * e;
       }
-      wS[t] = S;
-      wdS[t] = dS;
-    }
-    __syncthreads();
-    for (int t = tid; t < NREF * n; t += NT) {
-      const int i = t / NREF, a = t - i * NREF;
-      const int z = zs[i];
-      double norm = 0.0, dnorm = 0.0;
+      double norm = S, dnorm = dS;
 #pragma unroll
-      for (int aa = 0; aa < NREF; ++aa) {
-        norm += wS[i * NREF + aa];
-        dnorm += wdS[i * NREF + aa];
+      for (int o = 4; o > 0; o >>= 1) {
+        norm += __shfl_xor_sync(0xffffffffu, norm, o);
+        dnorm += __shfl_xor_sync(0xffffffffu, dnorm, o);
       }
-      double gw = 0.0, dgw = 0.0;
-      if (norm > 0.0) {
-        gw = wS[t] / norm;
-        dgw = (wdS[t] - gw * dnorm) / norm;
-      }
-      double zeta = 0.0, dzeta = 0.0;
-      if (tab.refc[z * NREF + a] > 0) {
-        const double gam = tab.gamgc[z];
-        const double qref = tab.refq[z * NREF + a];
-        const double qmod = (double)ATOM(AT_Q)[i] + tab.zeff[z];
-        if (qmod > 0.0) {
-          const double qe = qmod - (double)d4_eps<T>();
-          const double scale = exp(gam * (1.0 - qref / qe));
-          zeta = exp(P.ga * (1.0 - scale));
-          dzeta = -P.ga * gam * scale * zeta * qref / (qe * qe);
-        } else {
-          zeta = exp(P.ga);
+      if (on) {
+        double gw = 0.0, dgw = 0.0;
+        if (norm > 0.0) {
+          gw = S / norm;
+          dgw = (dS - gw * dnorm) / norm;
         }
-      }
-      const double z0 = tab.zeta0[z * NREF + a];
-      WT(WT_Q)[t] = (T)(zeta * gw);
-      WT(WT_0)[t] = (T)(z0 * gw);
-      if (GRAD) {
-        WT(WT_ZGD)[t] = (T)(zeta * dgw);
-        WT(WT_Z0GD)[t] = (T)(z0 * dgw);
-        WT(WT_DZG)[t] = (T)(dzeta * gw);
+        double zeta = 0.0, dzeta = 0.0;
+        if (rc > 0) {
+          const double gam = tab.gamgc[z];
+          const double qref = tab.refq[z * NREF + a];
+          const double qmod = (double)ATOM(AT_Q)[i] + tab.zeff[z];
+          if (qmod > 0.0) {
+            const double qe = qmod - (double)d4_eps<T>();
+            const double scale = exp(gam * (1.0 - qref / qe));
+            zeta = exp(P.ga * (1.0 - scale));
+            dzeta = -P.ga * gam * scale * zeta * qref / (qe * qe);
+          } else {
+            zeta = exp(P.ga);
+          }
+        }
+        const double z0 = tab.zeta0[z * NREF + a];
+        const int o = i * NREF + a;
+        WT(WT_Q)[o] = (T)(zeta * gw);
+        WT(WT_0)[o] = (T)(z0 * gw);
+        if (GRAD) {
+          WT(WT_ZGD)[o] = (T)(zeta * dgw);
+          WT(WT_Z0GD)[o] = (T)(z0 * dgw);
+          WT(WT_DZG)[o] = (T)(dzeta * gw);
+        }
       }
     }
     __syncthreads();
+    PHASE(3);
 
     // ---- phase 3: weighted polarizability vectors A_i[w] -------------------
     // energy kernel: only the charge-scaled flavour now; the q = 0 flavour for
@@ -394,57 +488,37 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       Aq[w * CAP + i] = sq;
       if (GRAD) A0[w * CAP + i] = s0;
     }
-    // aliased weights: the q = 0 flavour must survive the two-body pass, which
-    // uses one plane as scratch -> park it in registers
-    constexpr int KEEP = L::wt_alias ? (NREF * CAP + NT - 1) / NT : 1;
-    T w0keep[KEEP];
-    if (L::wt_alias) {
-#pragma unroll
-      for (int m = 0; m < KEEP; ++m) {
-        const int t = tid + m * NT;
-        w0keep[m] = t < NREF * n ? WT(WT_0)[t] : T(0);
-      }
-    }
     __syncthreads();
+    PHASE(4);
 
     // ---- phase 4: two-body energy (twobody.py:134-201, rational damping) ---
     if constexpr (!GRAD) {
-      if (tid < np) {
-        for (PairIt it(tid); it.p < np; it.advance(NT)) {
-          const int i = it.hi, j = it.lo;
-          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-          const T r2 = dx * dx + dy * dy + dz * dz;
-          T e = T(0);
-          if (r2 <= P.disp2_sq) {
-            T c6 = T(0);
-#pragma unroll
-            for (int w = 0; w < NFREQ; ++w) c6 += Aq[w * CAP + i] * Aq[w * CAP + j];
-            const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
-            const T R0 = P.a1 * ss + P.a2;
-            const T qq = ss * ss;  // = 3 r4r2_i r4r2_j
-            const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
-            const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
-            T F = P.s6 * d4_rcp(r6 + R6) + P.s8 * qq * d4_rcp(r8 + R8);
-            if (P.s10k != T(0)) F += P.s10k * qq * qq * d4_rcp(r8 * r2 + R8 * R2);
-            e = c6 * F;
-          }
-          pP[it.p] = e;
+#pragma unroll 2
+      for (int p = tid; p < np; p += NT) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        T e = T(0);
+        if (r2 <= P.disp2_sq) {
+          const T c6 = dot23<T, CAP>(Aq, i, j);
+          const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+          const T R0 = P.a1 * ss + P.a2;
+          const T qq = ss * ss;  // = 3 r4r2_i r4r2_j
+          const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+          const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+          T F = P.s6 * d4_rcp(r6 + R6) + P.s8 * qq * d4_rcp(r8 + R8);
+          if (P.s10k != T(0)) F += P.s10k * qq * qq * d4_rcp(r8 * r2 + R8 * R2);
+          e = c6 * F;
         }
+        pu[p] = e;  // the weights (aliased layout) sit at the start of plane `pa`
       }
-      __syncthreads();
-      for (int i = tid; i < n; i += NT) ATOM(AT_E)[i] = T(-0.5) * row_sum(pP, i, n);
+      __syncthreads();  // all reads of Aq done: the buffer becomes A0
+      PHASE(5);
+      for (int i = tid; i < n; i += NT) ATOM(AT_E)[i] = T(-0.5) * row_sum2(pu, pu, i, n);
       if (P.has_atm) {
-        __syncthreads();  // row sums done: planes are free again
-        if (L::wt_alias) {
-#pragma unroll
-          for (int m = 0; m < KEEP; ++m) {
-            const int t = tid + m * NT;
-            if (t < NREF * n) WT(WT_0)[t] = w0keep[m];
-          }
-          __syncthreads();
-        }
         for (int t = tid; t < NFREQ * n; t += NT) {
           const int i = t / NFREQ, w = t - i * NFREQ;
           const T* al = tab.alpha_w + (size_t)zs[i] * NREF * NFREQ + w;
@@ -455,70 +529,66 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         }
       }
       __syncthreads();
+      PHASE(6);
     }
 
     // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
+    bool open = false;
     if (P.has_atm) {
-      if (tid < np) {
-        for (PairIt it(tid); it.p < np; it.advance(NT)) {
-          const int i = it.hi, j = it.lo;
-          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-          const T r2 = dx * dx + dy * dy + dz * dz;
-          const T r = d4_sqrt(r2);
-          const T rinv = d4_rcp(r);
-          T c6 = T(0);
-#pragma unroll
-          for (int w = 0; w < NFREQ; ++w) c6 += A0[w * CAP + i] * A0[w * CAP + j];
-          const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
-          const bool inside = r2 <= P.disp3_sq;
-          if (!inside) misc[2] = 1;
-          // NB: in the aliased layout this overwrites the (dead) weights
-          pa[it.p] = inside ? r2 : -r2;
-          pP[it.p] = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
-          pu[it.p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
-        }
+      // NB: in the aliased layout the stash overwrites the weights, which are
+      // dead by now (WT lives at the start of plane `pa`)
+#pragma unroll 2
+      for (int p = tid; p < np; p += NT) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        const T r = d4_sqrt(r2);
+        const T rinv = d4_rcp(r);
+        const T c6 = dot23<T, CAP>(A0, i, j);
+        const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
+        const bool inside = r2 <= P.disp3_sq;
+        if (!inside) misc[2] = 1;
+        pa[p] = inside ? r2 : -r2;
+        pP[p] = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+        pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
       }
       __syncthreads();
-      const bool open = misc[2] != 0;
+      PHASE(7);
+      open = misc[2] != 0;
 
       // ---- phase 6: triple loop ---------------------------------------------
-      // per-CTA, L2-resident scratch for per-pair results (the smem planes are
-      // still being read by other warps while results are produced)
-      T* const out0 = A.scratch + (size_t)blockIdx.x * 2 * CP;
-      T* const out1 = out0 + CP;
       if constexpr (GRAD) {
         // Gradient: one thread per owner pair (j,k), all third atoms i.  Every
         // triple is visited from each of its three pairs, so the per-pair sums
         // Gamma (dL/dC60 numerator) and D (dL/d r^2) need no communication.
-        if (tid < np) {
-          for (PairIt it(tid); it.p < np; it.advance(NT)) {
-            const int j = it.hi, k = it.lo, p = it.p;
-            const T bs = pa[p];
-            const T bb = fabs(bs);
-            const T cjk = bs > T(0) ? T(1) : T(0);
-            const T Pjk = pP[p], ujk = pu[p];
-            const T inv_b = d4_rcp(bb);
-            const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
-            const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
-            T accG = T(0), accD = T(0);
-            for (int i = 0; i < n; ++i) {
-              if (i == j || i == k) continue;
-              const int ti = i * (i - 1) / 2;
-              const int pij = i > j ? ti + j : tj + i;
-              const int pik = i > k ? ti + k : tk + i;
-              if (open)
-                grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
-                                    Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD);
-              else
-                grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb,
-                                     cjk, Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG,
-                                     accD);
-            }
-            out0[p] = accG;
-            out1[p] = accD;
+        for (int p = tid; p < np; p += NT) {
+          int j, k;
+          pair_decode(p, j, k);
+          const T bs = pa[p];
+          const T bb = fabs(bs);
+          const T cjk = bs > T(0) ? T(1) : T(0);
+          const T Pjk = pP[p], ujk = pu[p];
+          const T inv_b = d4_rcp(bb);
+          const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
+          const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
+          T accG = T(0), accD = T(0);
+          for (int i = 0; i < n; ++i) {
+            if (i == j || i == k) continue;
+            const int ti = i * (i - 1) / 2;
+            const int pij = i > j ? ti + j : tj + i;
+            const int pik = i > k ? ti + k : tk + i;
+            if (open)
+              grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
+                                  Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD);
+            else
+              grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
+                                   Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD);
           }
+          out0[p] = accG;
+          out1[p] = accD;
         }
         __syncthreads();  // all reads of the stash done -> planes become outputs
         for (int p = tid; p < np; p += NT) {  // same thread wrote out0/out1[p]
@@ -526,13 +596,14 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           pu[p] = out1[p];
         }
         __syncthreads();
+        PHASE(8);
       } else {
         // Energy: every unordered triple i > j > k is evaluated exactly once.
         // A warp takes 32 consecutive "bottom" pairs (j,k) (one per lane, stash
-        // entry in registers) and sweeps the top atom i; the shares of atoms j
-        // and k accumulate in lane registers, the share of atom i is reduced
-        // over the lanes with a batched (transposed) shuffle reduction.
-        T* const Tw = Aq + (tid >> 5) * CAP;  // A vectors are dead: per-warp E_i partials
+        // entry in registers) and sweeps the top atom i in blocks of eight; the
+        // shares of atoms j and k accumulate in lane registers, the share of
+        // atom i is reduced over the lanes with a transposed shuffle reduction.
+        T* const Tw = Aq + warp * CAP;  // A vectors are dead: per-warp E_i partials
         for (int i = lane; i < n; i += 32) Tw[i] = T(0);
         __syncwarp();
         const int nchunks = (np + 31) >> 5;
@@ -545,70 +616,26 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const int p = chunk * 32 + lane;
           const bool valid = p < np;
           int j = 1 << 20, k = 0;
-          if (valid) {
-            PairIt it(p);
-            j = it.hi;
-            k = it.lo;
-          }
+          if (valid) pair_decode(p, j, k);
           const int jmin = __shfl_sync(0xffffffffu, j, 0);
+          // last row that is only partially active; an invalid lane keeps the
+          // whole sweep on the predicated path
+          const int jmax = __reduce_max_sync(0xffffffffu, j);
           const T bs = valid ? pa[p] : T(1);
           const T Pjk = valid ? pP[p] : T(0), ujk = valid ? pu[p] : T(0);
           const T bb = fabs(bs);
           const T cjk = bs > T(0) ? T(1) : T(0);
+          const T* colj = pa + (valid ? j : 0);
+          const T* colk = pa + k;
           T accJ = T(0), accK = T(0);
+          T v[8];
           for (int i0 = jmin + 1; i0 < n; i0 += 8) {
-            T v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = i0 + u;
-              T ei = T(0);
-              if (i < n && i > j) {
-                const T* row = pa + i * (i - 1) / 2;
-                const T a_s = row[j], c_s = row[k];
-                T a = a_s, c = c_s;
-                const T t = row[2 * CP + j] * row[2 * CP + k] * ujk;
-                const T pp = row[CP + j] * row[CP + k] * Pjk;
-                T mi = T(1), mj = T(1), mk = T(1);
-                if (open) {
-                  const T cij = a_s > T(0) ? T(1) : T(0);
-                  const T cik = c_s > T(0) ? T(1) : T(0);
-                  a = fabs(a_s);
-                  c = fabs(c_s);
-                  mi = cjk * (cij + cik);
-                  mj = cik * (cij + cjk);
-                  mk = cij * (cik + cjk);
-                }
-                const T X = a + bb - c, Y = a - bb + c, Z = bb + c - a;
-                const T abc = a * bb * c;
-                const T d = T(1) + T(6) * t;
-                const T inv = d4_rcp(abc * d);
-                const T e = (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) * (pp * (inv * abc));
-                if (open) {
-                  accJ += mj * e;
-                  accK += mk * e;
-                  ei = mi * e;
-                } else {
-                  accJ += e;
-                  ei = e;
-                }
-              }
-              v[u] = ei;
-            }
-            // transposed reduction: 8 values x 32 lanes -> lane group (lane>>2) holds sum u
-            T w0, w1, w2, w3;
-            {
-              const T s0 = b4 ? v[0] : v[4], s1 = b4 ? v[1] : v[5], s2 = b4 ? v[2] : v[6],
-                      s3 = b4 ? v[3] : v[7];
-              w0 = (b4 ? v[4] : v[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
-              w1 = (b4 ? v[5] : v[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
-              w2 = (b4 ? v[6] : v[2]) + __shfl_xor_sync(0xffffffffu, s2, 16);
-              w3 = (b4 ? v[7] : v[3]) + __shfl_xor_sync(0xffffffffu, s3, 16);
-            }
-            const T x0 = (b3 ? w2 : w0) + __shfl_xor_sync(0xffffffffu, b3 ? w0 : w2, 8);
-            const T x1 = (b3 ? w3 : w1) + __shfl_xor_sync(0xffffffffu, b3 ? w1 : w3, 8);
-            T y = (b2 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, b2 ? x0 : x1, 4);
-            y += __shfl_xor_sync(0xffffffffu, y, 2);
-            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            const bool all = i0 > jmax && i0 + 8 <= n;  // warp-uniform
+            if (open)
+              triple_block8<T, CP, true>(colj, colk, i0, j, n, all, bb, cjk, Pjk, ujk, accJ, accK, v);
+            else
+              triple_block8<T, CP, false>(colj, colk, i0, j, n, all, bb, cjk, Pjk, ujk, accJ, accK, v);
+            const T y = reduce8x32(v, b4, b3, b2);
             const int iw = i0 + (lane >> 2);
             if ((lane & 3) == 0 && iw < n) Tw[iw] += y;
           }
@@ -618,17 +645,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           }
         }
         __syncthreads();
-        const T scale = open ? T(1) : T(2);  // closed triples: every atom has multiplicity 2
-        for (int i = tid; i < n; i += NT) {
-          T s = T(0);
-          const int ti = i * (i - 1) / 2;
-          for (int j = 0; j < i; ++j) s += out0[ti + j];
-          for (int j = i + 1; j < n; ++j) s += out1[j * (j - 1) / 2 + i];
-#pragma unroll
-          for (int w = 0; w < NT / 32; ++w) s += Aq[w * CAP + i];
-          ATOM(AT_E)[i] += scale * s;
-        }
-        __syncthreads();
+        PHASE(8);
       }
     } else if (GRAD) {
       for (int p = tid; p < np; p += NT) {
@@ -639,52 +656,60 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     }
 
     if constexpr (!GRAD) {
-      for (int i = tid; i < n; i += NT) A.energy[(size_t)b * A.nat + idx[i]] = ATOM(AT_E)[i];
+      // ---- final assembly: E_i = E2_i + scale * (ATM shares) ------------------
+      const T scale = open ? T(1) : T(2);  // closed triples: every atom has multiplicity 2
+      for (int i = tid; i < n; i += NT) {
+        T e = ATOM(AT_E)[i];
+        if (P.has_atm) {
+          T s3 = row_sum2(out0, out1, i, n);
+#pragma unroll
+          for (int w = 0; w < NW; ++w) s3 += Aq[w * CAP + i];
+          e += scale * s3;
+        }
+        A.energy[(size_t)b * A.nat + idx[i]] = e;
+      }
+      __syncthreads();
+      PHASE(9);
     } else {
       // =================== gradient back-propagation =========================
       // phase 7: per-pair coefficients
       //   pa <- G2 F          (dL/dC6q)
       //   pP <- Gamma/(2 C60) (dL/dC60)
       //   pu <- 2 D + G2 C6q F'/r   (radial force coefficient, CN chain added later)
-      if (tid < np) {
-        for (PairIt it(tid); it.p < np; it.advance(NT)) {
-          const int i = it.hi, j = it.lo, p = it.p;
-          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-          const T r2 = dx * dx + dy * dy + dz * dz;
-          T c6q = T(0), c60 = T(0);
-#pragma unroll
-          for (int w = 0; w < NFREQ; ++w) {
-            c6q += Aq[w * CAP + i] * Aq[w * CAP + j];
-            c60 += A0[w * CAP + i] * A0[w * CAP + j];
+      for (int p = tid; p < np; p += NT) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        const T c6q = dot23<T, CAP>(Aq, i, j), c60 = dot23<T, CAP>(A0, i, j);
+        const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
+        T coefq = T(0), fc = T(2) * pu[p];
+        if (r2 <= P.disp2_sq) {
+          const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+          const T R0 = P.a1 * ss + P.a2;
+          const T qq = ss * ss;
+          const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+          const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+          const T t6 = d4_rcp(r6 + R6), t8 = d4_rcp(r8 + R8);
+          T F = P.s6 * t6 + P.s8 * qq * t8;
+          // dF/dr / r
+          T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
+          if (P.s10k != T(0)) {
+            const T t10 = d4_rcp(r8 * r2 + R8 * R2);
+            F += P.s10k * qq * qq * t10;
+            dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
           }
-          const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
-          T coefq = T(0), fc = T(2) * pu[p];
-          if (r2 <= P.disp2_sq) {
-            const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
-            const T R0 = P.a1 * ss + P.a2;
-            const T qq = ss * ss;
-            const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
-            const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
-            const T t6 = d4_rcp(r6 + R6), t8 = d4_rcp(r8 + R8);
-            T F = P.s6 * t6 + P.s8 * qq * t8;
-            // dF/dr / r
-            T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
-            if (P.s10k != T(0)) {
-              const T t10 = d4_rcp(r8 * r2 + R8 * R2);
-              F += P.s10k * qq * qq * t10;
-              dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
-            }
-            coefq = G2 * F;
-            fc += G2 * c6q * dF;
-          }
-          pa[p] = coefq;
-          pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
-          pu[p] = fc;
+          coefq = G2 * F;
+          fc += G2 * c6q * dF;
         }
+        pa[p] = coefq;
+        pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
+        pu[p] = fc;
       }
       __syncthreads();
+      PHASE(10);
       // phase 8: B_i[w] = sum_j coef_ij A_j[w]
       for (int t = tid; t < NFREQ * n; t += NT) {
         const int w = t / n, i = t - w * n;
@@ -703,6 +728,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         B0[w * CAP + i] = s0;
       }
       __syncthreads();
+      PHASE(11);
       // phase 9: project on the references -> dL/dcn_i, dL/dq_i
       T* const tcn = pa;              // [7n] partial dL/dcn (pa is free again)
       T* const tq = pa + NREF * CAP;  // [7n] partial dL/dq
@@ -731,49 +757,58 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         ATOM(AT_DQ)[i] = sq;
       }
       __syncthreads();
+      PHASE(12);
       // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
-      if (tid < np) {
-        for (PairIt it(tid); it.p < np; it.advance(NT)) {
-          const int i = it.hi, j = it.lo;
-          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-          const T r2 = dx * dx + dy * dy + dz * dz;
-          if (r2 <= P.cn_sq) {
-            const T r = d4_sqrt(r2);
-            const T r0inv = d4_rcp(ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j]);
-            const T xx = T(7.5) * (r * r0inv - T(1));
-            if (fabs(xx) < T(8.7)) {  // exp(-x^2) < 1e-32 beyond
-              const T dcn = -tab.den[zs[i] * NELEM + zs[j]] * T(7.5) * T(0.5641895835477563) *
-                            r0inv * d4_exp(-xx * xx);
-              pu[it.p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn * d4_rcp(r);
-            }
+      for (int p = tid; p < np; p += NT) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 <= P.cn_sq) {
+          const T r = d4_sqrt(r2);
+          const T r0inv = d4_rcp(ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j]);
+          const T xx = T(7.5) * (r * r0inv - T(1));
+          if (fabs(xx) < T(8.7)) {  // exp(-x^2) < 1e-32 beyond
+            const T dcn = -tab.den[zs[i] * NELEM + zs[j]] * T(7.5) * T(0.5641895835477563) *
+                          r0inv * d4_exp(-xx * xx);
+            pu[p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn * d4_rcp(r);
           }
         }
       }
       __syncthreads();
-      // phase 11: gather forces
-      for (int i = tid; i < n; i += NT) {
+      PHASE(13);
+      // phase 11: gather forces (one warp per atom)
+      for (int i = warp; i < n; i += NW) {
         const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
         T fx = T(0), fy = T(0), fz = T(0);
         const int ti = i * (i - 1) / 2;
-        for (int j = 0; j < n; ++j) {
+        for (int j = lane; j < n; j += 32) {
           if (j == i) continue;
           const T c = j < i ? pu[ti + j] : pu[j * (j - 1) / 2 + i];
           fx += c * (xi - ATOM(AT_X)[j]);
           fy += c * (yi - ATOM(AT_Y)[j]);
           fz += c * (zi - ATOM(AT_Z)[j]);
         }
-        const size_t o = (size_t)b * A.nat + idx[i];
-        if (A.grad) {
-          A.grad[3 * o] = fx;
-          A.grad[3 * o + 1] = fy;
-          A.grad[3 * o + 2] = fz;
+        fx = warp_sum(fx);
+        fy = warp_sum(fy);
+        fz = warp_sum(fz);
+        if (lane == 0) {
+          const size_t o = (size_t)b * A.nat + idx[i];
+          if (A.grad) {
+            A.grad[3 * o] = fx;
+            A.grad[3 * o + 1] = fy;
+            A.grad[3 * o + 2] = fz;
+          }
+          if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
         }
-        if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
       }
+      __syncthreads();
+      PHASE(14);
     }
   }
+#undef PHASE
 #undef ATOM
 #undef WT
 }
