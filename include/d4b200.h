@@ -122,6 +122,21 @@ int d4b200_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nb
                         float* grad_positions_dev, float* grad_q_dev, void* workspace_dev,
                         size_t workspace_bytes, void* stream);
 
+/* Model properties, == tad_dftd4.get_properties (src/tad_dftd4/disp.py:149-197) with
+ * explicit charges: coordination numbers [nbatch, nat], pair C6 [nbatch, nat, nat]
+ * (D4Model.get_atomic_c6 with the q-dependent weights) and static polarizabilities
+ * [nbatch, nat] (BaseModel.get_polarizabilities, model/base.py:286-302).
+ * ``energy_scratch_dev`` is a [nbatch, nat] scratch the kernel zeroes. */
+int d4b200_properties_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                          const int64_t* numbers_dev, const double* positions_dev,
+                          const double* q_dev, double* cn_dev, double* c6_dev, double* alpha_dev,
+                          double* energy_scratch_dev, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
+int d4b200_properties_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                          const int64_t* numbers_dev, const float* positions_dev, const float* q_dev,
+                          float* cn_dev, float* c6_dev, float* alpha_dev, float* energy_scratch_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Synchronises ``stream`` and returns the device status bits recorded by the
  * last energy/gradient call that used ``workspace_dev``. */
 int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);

@@ -267,7 +267,8 @@ int configure(d4b200_tables* h) {
 template <typename T, bool GRAD>
 int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
               const int64_t* numbers, const T* pos, const T* q, const T* gin, T* energy, T* cn_out,
-              T* grad, T* gradq, void* ws, size_t ws_bytes, cudaStream_t st) {
+              T* grad, T* gradq, void* ws, size_t ws_bytes, cudaStream_t st, T* c6_out = nullptr,
+              T* alpha_out = nullptr) {
   constexpr int dt = sizeof(T) == 8 ? 0 : 1;
   constexpr int gr = GRAD ? 1 : 0;
   g_launches = 0;
@@ -299,6 +300,8 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   A.cn_out = cn_out;
   A.grad = grad;
   A.gradq = gradq;
+  A.c6_out = c6_out;
+  A.alpha_out = alpha_out;
   A.nbatch = nbatch;
   A.phase = nullptr;
   A.nat = nat;
@@ -348,6 +351,19 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
 }
 
 }  // namespace
+
+// (cn, C6, alpha) of tad_dftd4.get_properties (disp.py:149-197); the energy kernel stops
+// after the weighted-polarizability vectors.  ``energy_scratch_dev`` [nbatch, nat] is zeroed.
+template <typename T>
+static int run_props(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                     const int64_t* numbers, const T* pos, const T* q, T* cn, T* c6, T* alpha,
+                     T* energy_scratch, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!c6 || !energy_scratch) return D4B200_EINVAL;
+  cudaError_t e = cudaMemsetAsync(c6, 0, sizeof(T) * (size_t)nbatch * nat * nat, st);
+  if (e != cudaSuccess) return (int)e;
+  return run_small<T, false>(t, par, nbatch, nat, numbers, pos, q, nullptr, energy_scratch, cn, nullptr,
+                             nullptr, ws, ws_bytes, st, c6, alpha);
+}
 
 extern "C" {
 
@@ -475,6 +491,21 @@ int d4b200_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch,
                         float* grad, float* gradq, void* ws, size_t ws_bytes, void* stream) {
   return run_small<float, true>(t, par, nbatch, nat, numbers, pos, q, gin, nullptr, nullptr, grad,
                                 gradq, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int d4b200_properties_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                          const int64_t* numbers, const double* pos, const double* q, double* cn,
+                          double* c6, double* alpha, double* energy_scratch, void* ws,
+                          size_t ws_bytes, void* stream) {
+  return run_props<double>(t, par, nbatch, nat, numbers, pos, q, cn, c6, alpha, energy_scratch, ws,
+                           ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_properties_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                          const int64_t* numbers, const float* pos, const float* q, float* cn,
+                          float* c6, float* alpha, float* energy_scratch, void* ws, size_t ws_bytes,
+                          void* stream) {
+  return run_props<float>(t, par, nbatch, nat, numbers, pos, q, cn, c6, alpha, energy_scratch, ws,
+                          ws_bytes, (cudaStream_t)stream);
 }
 
 int d4b200_status(void* ws, void* stream, int* bits) {

@@ -33,6 +33,8 @@ struct SmallArgs {
   T* cn_out;
   T* grad;
   T* gradq;
+  T* c6_out;     // properties mode: [nbatch, nat, nat] pair C6 (pre-zeroed by the host side)
+  T* alpha_out;  // properties mode: [nbatch, nat] static polarizabilities
   T* scratch;  // [gridDim.x][2 or 3][CAP(CAP-1)/2] per-CTA, L2-resident per-pair results
   int nbatch, nat, cls;
   unsigned long long* phase;  // optional [16] per-phase cycle counters (development profiling)
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         if (!GRAD) {
           A.energy[o] = T(0);
           if (A.cn_out) A.cn_out[o] = T(0);
+          if (A.alpha_out) A.alpha_out[o] = T(0);
         } else {
           if (A.grad) {
             A.grad[3 * o] = T(0);
@@ -490,6 +493,25 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     }
     __syncthreads();
     PHASE(4);
+
+    // ---- properties mode (disp.py:149-197): cn, C6_ij = A_i.A_j, alpha_i, then next structure
+    if constexpr (!GRAD) {
+      if (A.c6_out) {
+        T* c6row = A.c6_out + (size_t)b * A.nat * A.nat;
+        for (int t = tid; t < n * n; t += NT) {
+          const int i = t / n, j = t - i * n;
+          c6row[(size_t)idx[i] * A.nat + idx[j]] = dot23<T, CAP>(Aq, i, j);
+        }
+        for (int i = tid; i < n; i += NT) {
+          T al = T(0);
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) al += WT(WT_Q)[i * NREF + a] * tab.alpha0[zs[i] * NREF + a];
+          if (A.alpha_out) A.alpha_out[(size_t)b * A.nat + idx[i]] = al;
+          A.energy[(size_t)b * A.nat + idx[i]] = T(0);
+        }
+        continue;
+      }
+    }
 
     // ---- phase 4: two-body energy (twobody.py:134-201, rational damping) ---
     if constexpr (!GRAD) {

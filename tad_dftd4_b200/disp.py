@@ -118,6 +118,26 @@ class _Engine:
             self._status(ws, stream)
         return energy, cn
 
+    def properties(self, par: _lib.Params, numbers: Tensor, positions: Tensor, q: Tensor):
+        nbatch, nat = numbers.shape
+        cn = torch.empty_like(q)
+        alpha = torch.empty_like(q)
+        escr = torch.empty_like(q)
+        c6 = torch.empty((nbatch, nat, nat), dtype=q.dtype, device=q.device)
+        ws = self.workspace(nbatch, nat)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = (self.lib.d4b200_properties_f64 if positions.dtype == torch.float64
+              else self.lib.d4b200_properties_f32)  # fmt: skip
+        _lib.check(
+            fn(self.handle, C.byref(par), nbatch, nat, numbers.data_ptr(), positions.data_ptr(),
+               q.data_ptr(), cn.data_ptr(), c6.data_ptr(), alpha.data_ptr(), escr.data_ptr(),
+               ws.data_ptr(), ws.numel(), stream),
+            "d4b200_properties",
+        )  # fmt: skip
+        if _CHECKS:
+            self._status(ws, stream)
+        return cn, c6, alpha
+
     def gradient(self, par: _lib.Params, numbers: Tensor, positions: Tensor, q: Tensor,
                  gout: Tensor | None, want_pos: bool, want_q: bool):  # fmt: skip
         nbatch, nat = numbers.shape
@@ -335,5 +355,37 @@ def get_properties(
     *,
     q: Tensor | None = None,
 ):
-    """(cn, q, c6, alpha) as ``tad_dftd4.get_properties`` (``disp.py:149-197``)."""
-    raise NotImplementedError("get_properties: device kernel not built yet (SURVEY.md 8f-1)")
+    """``(cn, q, c6, alpha)`` as ``tad_dftd4.get_properties`` (``disp.py:149-197``):
+    D4 coordination numbers, atomic charges, pair C6 ``(..., nat, nat)`` and static
+    polarizabilities.  ``q`` (keyword, extension of the reference signature) passes
+    explicit charges; without it EEQ charges come from ``tad-multicharge``."""
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError(
+            f"Shape of positions ({positions.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
+    if positions.device.type != "cuda":
+        raise RuntimeError("tad_dftd4_b200 runs on B200 GPUs only (no CPU fallback).")
+    if q is None:
+        eeq_cut = cutoff if cutoff is not None else Cutoff(device=positions.device, dtype=positions.dtype)
+        chg = torch.tensor(0.0) if charge is None else (charge if isinstance(charge, Tensor) else torch.tensor(charge))
+        q = _eeq_charges(numbers, positions, chg.to(positions.device, positions.dtype), eeq_cut)
+    if numbers.shape != q.shape:
+        raise ValueError(
+            f"Shape of atomic charges ({q.shape}) is not consistent with atomic numbers ({numbers.shape})."
+        )
+    par = _flatten_param({"a1": defaults.A1, "a2": defaults.A2}, cutoff, 0, defaults.WF_DEFAULT)
+    engine = _Engine.get(positions.device, defaults.GA_DEFAULT, defaults.GC_DEFAULT)
+    nat = numbers.shape[-1]
+    batch_shape = numbers.shape[:-1]
+    num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
+    pos2 = positions.detach().reshape(-1, nat, 3).contiguous()
+    q2 = q.detach().to(positions.dtype).reshape(-1, nat).contiguous()
+    with torch.cuda.device(positions.device):
+        cn, c6, alpha = engine.properties(par, num2, pos2, q2)
+    return (
+        cn.reshape(*batch_shape, nat),
+        q,
+        c6.reshape(*batch_shape, nat, nat),
+        alpha.reshape(*batch_shape, nat),
+    )

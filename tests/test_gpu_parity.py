@@ -82,3 +82,17 @@ def test_energy_and_gradient_f32(name):
     assert np.all(np.abs(tot - rtot) <= RTOL32 * np.abs(rtot) + 1e-12)
     assert np.abs(e - ref).max() / np.abs(ref).max() < 5 * RTOL32
     assert np.abs(g - gref).max() < 5 * RTOL32 * max(np.abs(gref).max(), 1e-3)
+
+
+@pytest.mark.parametrize("name", ["sih4_tpssh", "organic_33", "ragged_batch", "holes", "all_elements"])
+def test_properties_f64(name):
+    """get_properties (cn, C6 matrix, static polarizabilities) vs the reference's model classes."""
+    d4 = _d4()
+    case = load_golden(name)
+    dev = torch.device("cuda:0")
+    numbers, positions, q = as_torch(case, dev, torch.float64)
+    cn, qout, c6, alpha = d4.get_properties(numbers, positions, q=q)
+    assert qout is q
+    assert np.allclose(cn.cpu().numpy(), case["cn"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(c6.cpu().numpy(), case["c6"], rtol=1e-11, atol=1e-13)
+    assert np.allclose(alpha.cpu().numpy(), case["alpha"], rtol=1e-11, atol=1e-13)
