@@ -7,36 +7,11 @@
 #include <new>
 
 #include "d4b200_common.cuh"
-#include "d4b200_small.cuh"
+#include "d4b200_flavour.cuh"
+#include "d4b200_handle.cuh"
+#include "d4b200_small_args.cuh"
 
-using namespace d4b200;
 
-struct d4b200_tables {
-  int device;
-  int num_sms;
-  double ga, gc;
-  double* f64;  // device copy of the double blob
-  float* f32;   // same blob converted to float
-  int* i32;
-  size_t n_f64, n_i32;
-  Tables<double> t64;
-  Tables<float> t32;
-  // cached launch configuration: [dtype][grad][class]
-  int caps[2][2][NCLASS];
-  int threads[2][2][NCLASS];
-  int grid_per_sm[2][2][NCLASS];
-  size_t smem[2][2][NCLASS];
-  // classes are independent: they run concurrently on a small stream pool
-  cudaStream_t cstream[NCLASS];
-  cudaEvent_t ev_fork, ev_join[NCLASS];
-  // optional per-launch timing (bench.py roofline): events around each class kernel
-  int profile;
-  cudaEvent_t ev[2 * NCLASS];
-  cudaEvent_t ev_call[3];  // call start, prep done, call end
-  unsigned long long* phase_dev;  // [NCLASS][16] per-phase cycle counters (development)
-  int phase_on;
-  int ev_used[NCLASS];
-};
 
 static thread_local int g_launches = 0;
 
@@ -44,7 +19,7 @@ namespace {
 
 // section offsets inside the double blob (must match tables.py F64_LAYOUT)
 struct BlobOffsets {
-  size_t rcov, r4r2, sqrt_r4r2, gamgc, zeff, refcn, refq, zeta0, alpha0, den, alpha_w, wfpair, total;
+  size_t rcov, r4r2, sqrt_r4r2, gamgc, zeff, refcn, refq, zeta0, alpha0, den, alpha_w, wfpair, rc6, total;
   size_t refc, maxcn_ref, itotal;
 };
 BlobOffsets blob_offsets() {
@@ -62,6 +37,7 @@ BlobOffsets blob_offsets() {
   o.den = p, p += NELEM * NELEM;
   o.alpha_w = p, p += NELEM * NREF * NFREQ;
   o.wfpair = p, p += NELEM * NELEM;
+  o.rc6 = p, p += (size_t)NELEM * NELEM * NREF * NREF;
   o.total = p;
   size_t q = 0;
   o.refc = q, q += NELEM * NREF;
@@ -80,6 +56,7 @@ Tables<T> make_tables(const T* real, const double* f64, const int* i32) {
   t.den = real + o.den;
   t.alpha_w = real + o.alpha_w;
   t.alpha0 = real + o.alpha0;
+  t.rc6 = real + o.rc6;
   t.gamgc = f64 + o.gamgc;
   t.zeff = f64 + o.zeff;
   t.refcn = f64 + o.refcn;
@@ -168,8 +145,6 @@ Work carve_work(void* ws, int nbatch) {
 }
 
 constexpr int MAX_SMS = 160;
-// upper bound of resident CTAs per SM we ever launch for a class
-__host__ inline int class_occ_cap(int c) { return c == 0 ? 10 : c == 1 ? 5 : c == 2 ? 4 : 2; }
 
 size_t scratch_bytes_class(int c, int cap, size_t elem) {
   return align_up((size_t)MAX_SMS * class_occ_cap(c) * 2 * (cap * (cap - 1) / 2) * elem, 256);
@@ -196,72 +171,9 @@ Par<T> make_par(const d4b200_params* p, double ga) {
   return P;
 }
 
-// Size classes per kernel flavour: X(class, CAP, threads, min CTAs/SM for launch bounds).
-// Caps are bounded by the 227 KB shared-memory budget (Lay<>::total).
-#define D4_CLASSES_F64_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 3) X(3, 96, 512, 1) X(4, 128, 512, 1)
-#define D4_CLASSES_F64_G(X) X(0, 32, 128, 4) X(1, 48, 256, 2) X(2, 64, 512, 1) X(3, 80, 512, 1) X(4, 100, 512, 1)
-#define D4_CLASSES_F32_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 4) X(3, 96, 512, 2) X(4, 128, 512, 1)
-#define D4_CLASSES_F32_G(X) X(0, 32, 128, 6) X(1, 48, 256, 3) X(2, 64, 512, 2) X(3, 96, 512, 1) X(4, 128, 512, 1)
-
 template <typename T, bool GRAD>
-struct Flavour;
-#define D4_FLAVOUR(TYPE, GRADV, LIST)                                                              \
-  template <>                                                                                      \
-  struct Flavour<TYPE, GRADV> {                                                                    \
-    static int configure(d4b200_tables* h, int dt, int gr) {                                       \
-      cudaError_t e = cudaSuccess;                                                                 \
-      int occ = 0;                                                                                 \
-      LIST(D4_CFG_ONE)                                                                             \
-      return 0;                                                                                    \
-    }                                                                                              \
-    static void launch(int c, unsigned grid, cudaStream_t st, const SmallArgs<TYPE>& A) {          \
-      switch (c) { LIST(D4_LAUNCH_ONE) }                                                           \
-    }                                                                                              \
-  };
-#define D4_CFG_ONE(C, CAPV, NTV, MINBV)                                                            \
-  {                                                                                                \
-    using LL = Lay<type_t, grad_v, CAPV>;                                                          \
-    static_assert(LL::total <= 227 * 1024, "class does not fit the shared-memory budget");         \
-    auto kern = small_kernel<type_t, grad_v, CAPV, NTV, MINBV>;                                    \
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL::total);   \
-    if (e != cudaSuccess) return (int)e;                                                           \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTV, LL::total);                 \
-    if (e != cudaSuccess) return (int)e;                                                           \
-    if (occ < 1) occ = 1;                                                                          \
-    if (occ > class_occ_cap(C)) occ = class_occ_cap(C);                                            \
-    h->caps[dt][gr][C] = CAPV;                                                                     \
-    h->threads[dt][gr][C] = NTV;                                                                   \
-    h->smem[dt][gr][C] = LL::total;                                                                \
-    h->grid_per_sm[dt][gr][C] = occ;                                                               \
-  }
-#define D4_LAUNCH_ONE(C, CAPV, NTV, MINBV)                                                         \
-  case C:                                                                                          \
-    small_kernel<type_t, grad_v, CAPV, NTV, MINBV>                                                 \
-        <<<grid, NTV, Lay<type_t, grad_v, CAPV>::total, st>>>(A);                                  \
-    break;
-
-#define type_t double
-#define grad_v false
-D4_FLAVOUR(double, false, D4_CLASSES_F64_E)
-#undef grad_v
-#define grad_v true
-D4_FLAVOUR(double, true, D4_CLASSES_F64_G)
-#undef grad_v
-#undef type_t
-#define type_t float
-#define grad_v false
-D4_FLAVOUR(float, false, D4_CLASSES_F32_E)
-#undef grad_v
-#define grad_v true
-D4_FLAVOUR(float, true, D4_CLASSES_F32_G)
-#undef grad_v
-#undef type_t
-
-template <typename T, bool GRAD>
-int configure(d4b200_tables* h) {
-  constexpr int dt = sizeof(T) == 8 ? 0 : 1;
-  constexpr int gr = GRAD ? 1 : 0;
-  return Flavour<T, GRAD>::configure(h, dt, gr);
+int configure(d4b200_tables* h, int model) {
+  return flavour_configure<T>(h, GRAD, model);
 }
 
 template <typename T, bool GRAD>
@@ -272,6 +184,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   constexpr int dt = sizeof(T) == 8 ? 0 : 1;
   constexpr int gr = GRAD ? 1 : 0;
   g_launches = 0;
+  const int md = par && par->model == D4B200_MODEL_D4S ? 1 : 0;
   if (!h || !par || !numbers || !pos || !q || !ws || nbatch < 0 || nat < 0) return D4B200_EINVAL;
   if (!GRAD && !energy) return D4B200_EINVAL;
   if (!(par->a1 == par->a1) || !(par->a2 == par->a2)) return D4B200_EPARAM;
@@ -284,7 +197,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   if (e != cudaSuccess) return (int)e;
   ++g_launches;
   Caps caps;
-  for (int c = 0; c < NCLASS; ++c) caps.v[c] = h->caps[dt][gr][c];
+  for (int c = 0; c < NCLASS; ++c) caps.v[c] = h->caps[md][dt][gr][c];
   k_count<<<(nbatch + 7) / 8, 256, 0, st>>>(numbers, nbatch, nat, wk);
   k_scan<<<1, 32, 0, st>>>(nbatch, wk, caps);
   k_scatter<<<(nbatch + 255) / 256, 256, 0, st>>>(nbatch, wk);
@@ -327,14 +240,14 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
       A.cls = c;
       A.phase = h->phase_on ? h->phase_dev + 16 * c : nullptr;
       A.scratch = reinterpret_cast<T*>(scratch);
-      long grid = (long)h->grid_per_sm[dt][gr][c] * h->num_sms;
+      long grid = (long)h->grid_per_sm[md][dt][gr][c] * h->num_sms;
       if (grid > nbatch) grid = nbatch;
       const long gmax = (long)(h->num_sms < MAX_SMS ? h->num_sms : MAX_SMS) * class_occ_cap(c);
       if (grid > gmax) grid = gmax;
       cudaStream_t cs = h->profile ? st : h->cstream[c];  // profiling: serialise on the caller's stream
       if (!h->profile) cudaStreamWaitEvent(cs, h->ev_fork, 0);
       if (h->profile) cudaEventRecord(h->ev[2 * c], st);
-      Flavour<T, GRAD>::launch(c, (unsigned)grid, cs, A);
+      flavour_launch<T>(GRAD, par->model, c, (unsigned)grid, cs, A);
       if (h->profile) cudaEventRecord(h->ev[2 * c + 1], st);
       h->ev_used[c] = h->profile;
       if (!h->profile) {
@@ -425,10 +338,13 @@ int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
     if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) break;
     h->t64 = make_tables<double>(h->f64, h->f64, h->i32);
     h->t32 = make_tables<float>(h->f32, h->f64, h->i32);
-    if ((rc = configure<double, false>(h)) != 0) break;
-    if ((rc = configure<double, true>(h)) != 0) break;
-    if ((rc = configure<float, false>(h)) != 0) break;
-    if ((rc = configure<float, true>(h)) != 0) break;
+    for (int model = 0; model < 2 && rc == 0; ++model) {
+      if ((rc = configure<double, false>(h, model)) != 0) break;
+      if ((rc = configure<double, true>(h, model)) != 0) break;
+      if ((rc = configure<float, false>(h, model)) != 0) break;
+      if ((rc = configure<float, true>(h, model)) != 0) break;
+    }
+    if (rc != 0) break;
   } while (0);
   cudaSetDevice(prev_dev);
   if (e != cudaSuccess || rc != 0) {
@@ -576,7 +492,7 @@ int d4b200_profile_read(d4b200_tables_t h, float* ms_per_class) {
 
 int d4b200_class_caps(d4b200_tables_t h, int fp32, int grad, int* caps_out) {
   if (!h || !caps_out) return D4B200_EINVAL;
-  for (int c = 0; c < NCLASS; ++c) caps_out[c] = h->caps[fp32 ? 1 : 0][grad ? 1 : 0][c];
+  for (int c = 0; c < NCLASS; ++c) caps_out[c] = h->caps[0][fp32 ? 1 : 0][grad ? 1 : 0][c];
   return 0;
 }
 

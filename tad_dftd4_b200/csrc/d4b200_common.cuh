@@ -26,6 +26,7 @@ struct Tables {
   const T* den;        // [NELEM*NELEM] CN electronegativity factor
   const T* alpha_w;    // [NELEM*NREF*NFREQ] sqrt(3/pi w) * alpha
   const T* alpha0;     // [NELEM*NREF] alpha(i0)
+  const T* rc6;        // [NELEM*NELEM*NREF*NREF] reference C6 (D4S pair contraction)
   const double* gamgc;   // [NELEM]
   const double* zeff;    // [NELEM]
   const double* refcn;   // [NELEM*NREF]

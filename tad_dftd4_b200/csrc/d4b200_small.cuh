@@ -20,28 +20,11 @@
 #include <math.h>
 
 #include "d4b200_common.cuh"
+#include "d4b200_small_args.cuh"
 
 namespace d4b200 {
 
-template <typename T>
-struct SmallArgs {
-  const int64_t* numbers;
-  const T* pos;
-  const T* q;
-  const T* gin;  // upstream dL/dE (nullable = ones)
-  T* energy;
-  T* cn_out;
-  T* grad;
-  T* gradq;
-  T* c6_out;     // properties mode: [nbatch, nat, nat] pair C6 (pre-zeroed by the host side)
-  T* alpha_out;  // properties mode: [nbatch, nat] static polarizabilities
-  T* scratch;  // [gridDim.x][2 or 3][CAP(CAP-1)/2] per-CTA, L2-resident per-pair results
-  int nbatch, nat, cls;
-  unsigned long long* phase;  // optional [16] per-phase cycle counters (development profiling)
-  Tables<T> tab;
-  Par<T> par;
-  Work wk;
-};
+
 
 // ---------------------------------------------------------------- math shims
 __device__ __forceinline__ double d4_erfc(double x) { return erfc(x); }
@@ -95,24 +78,61 @@ enum { AT_X = 0, AT_Y, AT_Z, AT_Q, AT_CN, AT_E, AT_RCOV, AT_SQ, AT_G, AT_DCN, AT
 // per-atom x 7 T arrays
 enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG };
 
-template <typename T, bool GRAD, int CAP>
+template <typename T, bool GRAD, bool D4S, int CAP>
 struct Lay {
   static constexpr int CP = CAP * (CAP - 1) / 2;
   static constexpr size_t plane_bytes = size_t(3) * CP * sizeof(T);
-  // energy kernel: the weights live on top of the (not yet used) planes when they
-  // fit; the gradient kernel needs the weights until the end
-  static constexpr bool wt_alias = !GRAD && size_t(2) * NREF * CAP * sizeof(T) <= plane_bytes;
-  static constexpr int n_abuf = GRAD ? 4 : 1;  // energy: Aq, then A0 in the same buffer
+  // D4 energy kernel: the weights live on top of the (not yet used) planes when they
+  // fit; the gradient kernel needs the weights until the end, and the D4S kernels read
+  // them while the planes are being written
+  static constexpr bool wt_alias = !GRAD && !D4S && size_t(2) * NREF * CAP * sizeof(T) <= plane_bytes;
+  // A/B vector buffers [23][CAP]: D4 energy 1 (Aq, then A0), D4 gradient 4 (Aq, A0, Bq, B0);
+  // D4S has no per-atom vectors (pair-dependent weights) and only needs room for the
+  // per-warp partial sums of the energy triple loop (16 warps)
+  static constexpr size_t abuf_elems = D4S ? (GRAD ? 0 : size_t(16) * CAP) : size_t(GRAD ? 4 : 1) * NFREQ * CAP;
   static constexpr int n_atom = GRAD ? 11 : 8;
-  static constexpr int n_wt = GRAD ? 5 : (wt_alias ? 0 : 2);
+  static constexpr int n_wt = D4S ? (GRAD ? 3 : 2) : (GRAD ? 5 : (wt_alias ? 0 : 2));
   static constexpr size_t planes = 0;
   static constexpr size_t abuf = al16(plane_bytes);
-  static constexpr size_t atoms = abuf + al16(size_t(n_abuf) * NFREQ * CAP * sizeof(T));
+  static constexpr size_t atoms = abuf + al16(abuf_elems * sizeof(T));
   static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
   static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
   static constexpr size_t total = ints + al16((2 * CAP + 8) * sizeof(int));
   static constexpr int scratch_planes = 2;
 };
+
+// Unnormalised Gaussian weights S_a (and dS_a/dcn) of one atom for a given weighting
+// factor, float64, max-shifted exponentials (model/d4s.py:189-213: pair-dependent wf).
+template <bool DERIV>
+__device__ __forceinline__ void d4s_gauss(const double* __restrict__ refcn, const int* __restrict__ refc,
+                                          int z, double cn, double wf, double (&S)[NREF],
+                                          double (&dS)[NREF], double& norm, double& dnorm) {
+  double arg[NREF];
+  double shift = 1e300;
+#pragma unroll
+  for (int a = 0; a < NREF; ++a) {
+    const double d = cn - refcn[z * NREF + a];
+    arg[a] = refc[z * NREF + a] > 0 ? wf * d * d : 1e300;
+    shift = fmin(shift, arg[a]);
+  }
+  norm = 0.0;
+  dnorm = 0.0;
+#pragma unroll
+  for (int a = 0; a < NREF; ++a) {
+    const int rc = refc[z * NREF + a];
+    const double d = cn - refcn[z * NREF + a];
+    double s = 0.0, ds = 0.0;
+    for (int k = 1; k <= rc; ++k) {
+      const double e = exp(-((double)k * arg[a] - shift));
+      s += e;
+      if (DERIV) ds += -2.0 * (double)k * wf * d * e;
+    }
+    S[a] = s;
+    dS[a] = ds;
+    norm += s;
+    dnorm += ds;
+  }
+}
 
 // p -> (hi, lo) with hi > lo and p = hi(hi-1)/2 + lo
 __device__ __forceinline__ void pair_decode(int p, int& hi, int& lo) {
@@ -272,9 +292,9 @@ __device__ __forceinline__ T reduce8x32(const T (&v)[8], bool b4, bool b3, bool 
   return y;
 }
 
-template <typename T, bool GRAD, int CAP, int NT, int MINB>
+template <typename T, bool GRAD, bool D4S, int CAP, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
-  using L = Lay<T, GRAD, CAP>;
+  using L = Lay<T, GRAD, D4S, CAP>;
   constexpr int CP = L::CP;
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -425,12 +445,12 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       const int rc = on ? tab.refc[z * NREF + a] : 0;
       const double cn_i = on ? (double)ATOM(AT_CN)[i] : 0.0;
       const double d = on ? cn_i - tab.refcn[z * NREF + a] : 0.0;
-      const double arg = rc > 0 ? P.wf * d * d : 1e300;
+      const double arg = (rc > 0 && !D4S) ? P.wf * d * d : 1e300;
       double shift = arg;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, o));
       double S = 0.0, dS = 0.0;
-      for (int k = 1; k <= rc; ++k) {
+      for (int k = 1; k <= (D4S ? 0 : rc); ++k) {
         const double e = exp(-((double)k * arg - shift));
         S += e;
         dS += -2.0 * (double)k * P.wf * d * e;
@@ -463,6 +483,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         }
         const double z0 = tab.zeta0[z * NREF + a];
         const int o = i * NREF + a;
+        if (D4S) {  // weights are pair dependent: keep the charge scaling only
+          WT(WT_Q)[o] = (T)zeta;
+          WT(WT_0)[o] = (T)z0;
+          if (GRAD) WT(WT_ZGD)[o] = (T)dzeta;
+        } else {
         WT(WT_Q)[o] = (T)(zeta * gw);
         WT(WT_0)[o] = (T)(z0 * gw);
         if (GRAD) {
@@ -470,11 +495,87 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           WT(WT_Z0GD)[o] = (T)(z0 * dgw);
           WT(WT_DZG)[o] = (T)(dzeta * gw);
         }
+        }
       }
     }
     __syncthreads();
     PHASE(3);
 
+    bool open = false;
+    if constexpr (D4S) {
+      // ---- D4S: pair-dependent Gaussian weights (model/d4s.py:109-290) ------
+      // C6_ij = sum_ab rc6[Zi,Zj,a,b] (zeta_ia gw_ia|Zj) (zeta_jb gw_jb|Zi) with the weights
+      // of each atom evaluated for the partner's element, per pair, in float64.
+      // One fused pass: two-body energy (energy kernel) + ATM stash.
+      for (int p = tid; p < np; p += NT) {
+        int i, j;
+        pair_decode(p, i, j);
+        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        const int zi = zs[i], zj = zs[j];
+        double S[NREF], dS[NREF], norm, dnorm;
+        // partner j as seen by i
+        d4s_gauss<false>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], S, dS, norm, dnorm);
+        double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+        T v[NREF], v0[NREF];
+#pragma unroll
+        for (int bq = 0; bq < NREF; ++bq) {
+          const T g = (T)(S[bq] * inv);
+          v[bq] = WT(WT_Q)[j * NREF + bq] * g;
+          v0[bq] = WT(WT_0)[j * NREF + bq] * g;
+        }
+        d4s_gauss<false>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], S, dS, norm, dnorm);
+        inv = norm > 0.0 ? 1.0 / norm : 0.0;
+        const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
+        T c6q = T(0), c60 = T(0);
+#pragma unroll
+        for (int a = 0; a < NREF; ++a) {
+          T t = T(0), t0 = T(0);
+#pragma unroll
+          for (int bq = 0; bq < NREF; ++bq) {
+            const T rab = R[a * NREF + bq];
+            t += rab * v[bq];
+            t0 += rab * v0[bq];
+          }
+          const T g = (T)(S[a] * inv);
+          c6q += WT(WT_Q)[i * NREF + a] * g * t;
+          c60 += WT(WT_0)[i * NREF + a] * g * t0;
+        }
+        const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+        const T R0 = P.a1 * ss + P.a2;
+        if (!GRAD) {
+          T e = T(0);
+          if (r2 <= P.disp2_sq) {
+            const T qq = ss * ss;
+            const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+            const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+            T F = P.s6 * d4_rcp(r6 + R6) + P.s8 * qq * d4_rcp(r8 + R8);
+            if (P.s10k != T(0)) F += P.s10k * qq * qq * d4_rcp(r8 * r2 + R8 * R2);
+            e = c6q * F;
+          }
+          out0[p] = e;
+        }
+        if (P.has_atm) {
+          const T r = d4_sqrt(r2);
+          const T rinv = d4_rcp(r);
+          const bool inside = r2 <= P.disp3_sq;
+          if (!inside) misc[2] = 1;
+          pa[p] = inside ? r2 : -r2;
+          pP[p] = P.fac9 * d4_sqrt(fabs(c60)) * (rinv * rinv * rinv);
+          pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
+        }
+      }
+      __syncthreads();
+      PHASE(7);
+      open = misc[2] != 0;
+      if (!GRAD) {
+        for (int i = tid; i < n; i += NT) ATOM(AT_E)[i] = T(-0.5) * row_sum2(out0, out0, i, n);
+        __syncthreads();  // the triple loop reuses out0
+      }
+    }
+    if constexpr (!D4S) {
     // ---- phase 3: weighted polarizability vectors A_i[w] -------------------
     // energy kernel: only the charge-scaled flavour now; the q = 0 flavour for
     // the ATM term is built into the same buffer after the two-body pass
@@ -555,7 +656,6 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     }
 
     // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
-    bool open = false;
     if (P.has_atm) {
       // NB: in the aliased layout the stash overwrites the weights, which are
       // dead by now (WT lives at the start of plane `pa`)
@@ -580,7 +680,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       __syncthreads();
       PHASE(7);
       open = misc[2] != 0;
-
+    }
+    }  // !D4S
+    if (P.has_atm) {
       // ---- phase 6: triple loop ---------------------------------------------
       if constexpr (GRAD) {
         // Gradient: one thread per owner pair (j,k), all third atoms i.  Every
@@ -694,6 +796,105 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       PHASE(9);
     } else {
       // =================== gradient back-propagation =========================
+      if constexpr (D4S) {
+        // D4S: weights (and their cn-derivatives) are re-evaluated per pair; the four
+        // chain-rule contributions of a pair go to per-pair planes that are summed
+        // per atom afterwards.
+        //   pa <- d L/d cn (share of the higher-index atom)   pP <- (lower-index atom)
+        //   out0/out1 <- d L/d q shares                       pu <- radial force coefficient
+        for (int p = tid; p < np; p += NT) {
+          int i, j;
+          pair_decode(p, i, j);
+          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+          const T r2 = dx * dx + dy * dy + dz * dz;
+          const int zi = zs[i], zj = zs[j];
+          const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
+          double S[NREF], dS[NREF], norm, dnorm;
+          T gi[NREF], dgi[NREF], gj[NREF], dgj[NREF];
+          d4s_gauss<true>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], S, dS, norm, dnorm);
+          double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) {
+            const double g = S[a] * inv;
+            gi[a] = (T)g;
+            dgi[a] = (T)((dS[a] - g * dnorm) * inv);
+          }
+          d4s_gauss<true>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], S, dS, norm, dnorm);
+          inv = norm > 0.0 ? 1.0 / norm : 0.0;
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) {
+            const double g = S[a] * inv;
+            gj[a] = (T)g;
+            dgj[a] = (T)((dS[a] - g * dnorm) * inv);
+          }
+          // t = R v, s = R^T u for both flavours
+          T c6q = T(0), c60 = T(0), dq_cni = T(0), d0_cni = T(0), dq_qi = T(0);
+          T sq[NREF], s0[NREF];
+#pragma unroll
+          for (int bq = 0; bq < NREF; ++bq) sq[bq] = s0[bq] = T(0);
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) {
+            const T zq = WT(WT_Q)[i * NREF + a], z0 = WT(WT_0)[i * NREF + a];
+            const T u = zq * gi[a], u0 = z0 * gi[a];
+            T t = T(0), t0 = T(0);
+#pragma unroll
+            for (int bq = 0; bq < NREF; ++bq) {
+              const T rab = R[a * NREF + bq];
+              t += rab * (WT(WT_Q)[j * NREF + bq] * gj[bq]);
+              t0 += rab * (WT(WT_0)[j * NREF + bq] * gj[bq]);
+              sq[bq] += rab * u;
+              s0[bq] += rab * u0;
+            }
+            c6q += u * t;
+            c60 += u0 * t0;
+            dq_cni += zq * dgi[a] * t;
+            d0_cni += z0 * dgi[a] * t0;
+            dq_qi += WT(WT_ZGD)[i * NREF + a] * gi[a] * t;
+          }
+          T dq_cnj = T(0), d0_cnj = T(0), dq_qj = T(0);
+#pragma unroll
+          for (int bq = 0; bq < NREF; ++bq) {
+            dq_cnj += WT(WT_Q)[j * NREF + bq] * dgj[bq] * sq[bq];
+            d0_cnj += WT(WT_0)[j * NREF + bq] * dgj[bq] * s0[bq];
+            dq_qj += WT(WT_ZGD)[j * NREF + bq] * gj[bq] * sq[bq];
+          }
+          const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
+          T coefq = T(0), fc = T(2) * pu[p];
+          if (r2 <= P.disp2_sq) {
+            const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+            const T R0 = P.a1 * ss + P.a2;
+            const T qq = ss * ss;
+            const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+            const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+            const T t6 = d4_rcp(r6 + R6), t8 = d4_rcp(r8 + R8);
+            T F = P.s6 * t6 + P.s8 * qq * t8;
+            T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
+            if (P.s10k != T(0)) {
+              const T t10 = d4_rcp(r8 * r2 + R8 * R2);
+              F += P.s10k * qq * qq * t10;
+              dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
+            }
+            coefq = G2 * F;
+            fc += G2 * c6q * dF;
+          }
+          const T gam = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
+          pa[p] = coefq * dq_cni + gam * d0_cni;
+          pP[p] = coefq * dq_cnj + gam * d0_cnj;
+          out0[p] = coefq * dq_qi;
+          out1[p] = coefq * dq_qj;
+          pu[p] = fc;
+        }
+        __syncthreads();
+        PHASE(10);
+        for (int i = tid; i < n; i += NT) {
+          ATOM(AT_DCN)[i] = row_sum2(pa, pP, i, n);
+          ATOM(AT_DQ)[i] = row_sum2(out0, out1, i, n);
+        }
+        __syncthreads();
+        PHASE(12);
+      } else {
       // phase 7: per-pair coefficients
       //   pa <- G2 F          (dL/dC6q)
       //   pP <- Gamma/(2 C60) (dL/dC60)
@@ -780,6 +981,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
       __syncthreads();
       PHASE(12);
+      }  // D4 / D4S
       // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
       for (int p = tid; p < np; p += NT) {
         int i, j;

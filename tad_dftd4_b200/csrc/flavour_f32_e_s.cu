@@ -1,0 +1,8 @@
+// Kernel flavour: float, energy, D4S (see d4b200_flavour.cuh).
+#include "d4b200_handle.cuh"
+#include "d4b200_small.cuh"
+#define D4_TYPE float
+#define D4_GRAD false
+#define D4_S true
+#include "d4b200_flavour.cuh"
+D4_DEFINE_FLAVOUR(f32_e_s, D4_CLASSES_F32_E_S)

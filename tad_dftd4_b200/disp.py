@@ -322,9 +322,6 @@ def dftd4(
             "tad_dftd4_b200 runs on B200 GPUs only (no CPU fallback): move numbers/positions "
             f"to a CUDA device (got {positions.device})."
         )
-    if model_id == 1:
-        raise NotImplementedError("the D4S model is not yet available in the fused kernels")
-
     if q is None:
         chg = charge if isinstance(charge, Tensor) else torch.tensor(charge)
         eeq_cut = cutoff if cutoff is not None else Cutoff(device=positions.device, dtype=positions.dtype)

@@ -85,6 +85,7 @@ class ElementTables:
         ("den", NELEM * NELEM),  # CN electronegativity factor
         ("alpha_w", NELEM * NREF * NFREQ),
         ("wfpair", NELEM * NELEM),
+        ("rc6", NELEM * NELEM * NREF * NREF),  # reference C6 per element pair (D4S)
     )
     I32_LAYOUT = (
         ("refc", NELEM * NREF),
@@ -127,6 +128,9 @@ class ElementTables:
         self.alpha0 = self.alpha[..., 0].copy()
         self.alpha_w = self.alpha * np.sqrt(THOPI * CP_WEIGHTS)[None, None, :]
         self.wfpair = raw["wfpair"][:NELEM, :NELEM].copy()
+        # rc6[Za, Zb, a, b] = (3/pi) sum_w w_w alpha[Za,a,w] alpha[Zb,b,w]  (utils.py:91-94)
+        flat = self.alpha_w.reshape(NELEM * NREF, NFREQ)
+        self.rc6 = (flat @ flat.T).reshape(NELEM, NREF, NELEM, NREF).transpose(0, 2, 1, 3).copy()
 
     def f64_blob(self) -> np.ndarray:
         parts = []

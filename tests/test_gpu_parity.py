@@ -96,3 +96,30 @@ def test_properties_f64(name):
     assert np.allclose(cn.cpu().numpy(), case["cn"], rtol=1e-12, atol=1e-14)
     assert np.allclose(c6.cpu().numpy(), case["c6"], rtol=1e-11, atol=1e-13)
     assert np.allclose(alpha.cpu().numpy(), case["alpha"], rtol=1e-11, atol=1e-13)
+
+
+D4S_LIMIT64 = 120  # largest structure of the FP64 D4S kernels
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_d4s_energy_and_gradient_f64(name):
+    """model="d4s": pair-dependent Gaussian weights (reference model/d4s.py)."""
+    case = load_golden(name)
+    if _small(name) > D4S_LIMIT64:
+        pytest.skip("beyond the FP64 D4S small-family limit")
+    e, g = _run(case, torch.float64, model="d4s")
+    ref, gref = case["energy_d4s"], case["grad_d4s"]
+    assert np.abs(e - ref).max() / np.abs(ref).max() < E_RTOL64
+    tot, rtot = e.sum(-1), ref.sum(-1)
+    assert np.all(np.abs(tot - rtot) <= E_RTOL64 * np.abs(rtot) + 1e-300)
+    assert np.abs(g - gref).max() < G_ATOL64
+
+
+@pytest.mark.parametrize("name", ["single_pbe0", "organic_64", "ragged_batch", "tight_cutoffs"])
+def test_d4s_f32(name):
+    case = load_golden(name)
+    e, g = _run(case, torch.float32, model="d4s")
+    ref, gref = case["energy_d4s"], case["grad_d4s"]
+    tot, rtot = e.sum(-1), ref.sum(-1)
+    assert np.all(np.abs(tot - rtot) <= RTOL32 * np.abs(rtot) + 1e-12)
+    assert np.abs(g - gref).max() < 5 * RTOL32 * max(np.abs(gref).max(), 1e-3)
