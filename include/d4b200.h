@@ -137,6 +137,33 @@ int d4b200_properties_f32(d4b200_tables_t tables, const d4b200_params* par, int 
                           float* cn_dev, float* c6_dev, float* alpha_dev, float* energy_scratch_dev,
                           void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- single large structures (tiled kernels, no N^2 / N^3 storage) ---------
+ * One structure of ``nat`` atoms (no padding rows; 0 entries are skipped), atoms
+ * preferably in a spatially coherent order.  The call ACCUMULATES into
+ * ``energy_dev`` [nat] (zero it first) the contributions of
+ *   - two-body rows  [row_begin, row_end)            (E_i of these atoms, complete)
+ *   - ATM centre groups [group_begin, group_end)     (groups of d4b200_large_group_size()
+ *     consecutive atoms; shares of ALL atoms i,k that have a centre in these groups)
+ * so that ranks owning disjoint ranges obtain the reference's
+ * dftd4(numbers, positions, ...) by one all-reduce(sum) of ``energy_dev``
+ * (SURVEY.md 8e).  ``cn_dev`` (optional) receives the coordination numbers,
+ * ``group_cost_dev`` (optional, [ceil(nat/group)]) the neighbour count of every centre
+ * group (cost of a group ~ count^2) for load-balanced partitioning; with
+ * ``energy_dev == NULL`` only these are computed. */
+int d4b200_large_group_size(void);
+size_t d4b200_large_workspace_bytes(d4b200_tables_t tables, int nat, int fp32);
+int d4b200_large_energy_f64(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                            const int64_t* numbers_dev, const double* positions_dev,
+                            const double* q_dev, int row_begin, int row_end, int group_begin,
+                            int group_end, double* energy_dev, double* cn_dev,
+                            int* group_cost_dev, void* workspace_dev, size_t workspace_bytes,
+                            void* stream);
+int d4b200_large_energy_f32(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                            const int64_t* numbers_dev, const float* positions_dev,
+                            const float* q_dev, int row_begin, int row_end, int group_begin,
+                            int group_end, float* energy_dev, float* cn_dev, int* group_cost_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Synchronises ``stream`` and returns the device status bits recorded by the
  * last energy/gradient call that used ``workspace_dev``. */
 int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);

@@ -306,11 +306,14 @@ def atm_dispersion(
     cutoff: float = DISP3_CUTOFF,
     s9=S9_DEFAULT,
     alp=ALP_DEFAULT,
+    centres: Tensor | None = None,
 ) -> Tensor:
     """dispersion/threebody.py:54-163 with ZeroDamping(order=9, only_damping)
     (damping/functions.py:329-375; rs9 is not forwarded -> 1).
 
-    The cutoff mask tests r_ij and r_jk only (threebody.py:153-157)."""
+    The cutoff mask tests r_ij and r_jk only (threebody.py:153-157), i.e. atom j is the
+    *centre* of the term.  ``centres`` (bool (..., nat), test helper for the row-block
+    multi-GPU partition) restricts the sum to centres j inside the set."""
     dtype = pos.dtype
     eps = torch.finfo(dtype).eps
     zero = torch.zeros((), dtype=dtype)
@@ -336,6 +339,8 @@ def atm_dispersion(
         (r2ij + r2jk - r2ik) * (r2ij - r2jk + r2ik) * (-r2ij + r2jk + r2ik),
         zero,
     )
+    if centres is not None:
+        m3 = m3 & centres.unsqueeze(-1).unsqueeze(-3)
     ang = torch.where(
         m3 & (r2ij <= c2) & (r2jk <= c2),
         0.375 * s / r5 + 1.0 / r3,
@@ -358,6 +363,7 @@ def dftd4(
     disp2: float = DISP2_CUTOFF,
     disp3: float = DISP3_CUTOFF,
     parts: bool = False,
+    centres: Tensor | None = None,
 ):
     """``tad_dftd4.dftd4`` (disp.py:44-146 -> dispersion/base.py:285-431) with
     explicit charges: TwoBodyTerm(Rational, q-dependent) + D4ATMApprox(Zero,
@@ -401,6 +407,7 @@ def dftd4(
         disp3,
         s9=_p(param, "s9", S9_DEFAULT),
         alp=_p(param, "alp", ALP_DEFAULT),
+        centres=centres,
     )
     if parts:
         return e2, e3, cn, c6q, c60

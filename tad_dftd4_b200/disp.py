@@ -83,6 +83,12 @@ class _Engine:
             eng = cls._cache[key] = cls(device, ga, gc)
         return eng
 
+    def large_workspace(self, need: int) -> Tensor:
+        ws = getattr(self, "_ws_large", None)
+        if ws is None or ws.numel() < need:
+            self._ws_large = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
+
     def workspace(self, nbatch: int, nat: int) -> Tensor:
         need = int(self.lib.d4b200_workspace_bytes(nbatch, nat))
         if self._ws is None or self._ws.numel() < need:
@@ -257,6 +263,33 @@ def _resolve_model(model: Any) -> tuple[int, float, float, float]:
     raise NotImplementedError(f"model instance of type {name} is outside the accelerated D4 hot path")
 
 
+def _small_limit(dtype: torch.dtype, grad: bool, model_id: int) -> int:
+    """Largest structure of the one-CTA-per-structure kernels (csrc/d4b200_flavour.cuh)."""
+    if dtype == torch.float32:
+        return 128
+    if model_id == 1:
+        return 120
+    return 100 if grad else 128
+
+
+def _compact_front(numbers: Tensor, positions: Tensor, q: Tensor, width: int):
+    """Move the real atoms of every structure to the front and cut the atom axis to
+    ``width`` (all structures here have at most ``width`` real atoms)."""
+    order = torch.argsort((numbers == 0).to(torch.int8), dim=-1, stable=True)[:, :width]
+    return (
+        torch.gather(numbers, 1, order).contiguous(),
+        torch.gather(positions, 1, order.unsqueeze(-1).expand(-1, -1, 3)).contiguous(),
+        torch.gather(q, 1, order).contiguous(),
+        order,
+    )
+
+
+def _scatter_back(values: Tensor, order: Tensor, nat: int) -> Tensor:
+    out = values.new_zeros((values.shape[0], nat))
+    out.scatter_(1, order, values)
+    return out
+
+
 def _eeq_charges(numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: Cutoff) -> Tensor:
     try:
         from tad_multicharge import get_eeq_charges  # type: ignore
@@ -339,6 +372,35 @@ def dftd4(
     num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
     pos2 = positions.reshape(-1, nat, 3).contiguous()
     q2 = q.to(positions.dtype).reshape(-1, nat).contiguous()
+
+    limit = _small_limit(positions.dtype, positions.requires_grad or q.requires_grad, model_id)
+    if nat > limit:
+        # padded width beyond the one-CTA-per-structure kernels: structures that really
+        # are that large go through the tiled kernels one by one (one host sync)
+        counts = (num2 != 0).sum(-1)
+        big = torch.nonzero(counts > limit).flatten().tolist()
+        if big:
+            if positions.requires_grad or q.requires_grad:
+                raise NotImplementedError(
+                    f"gradients for structures with more than {limit} atoms: the tiled "
+                    "large-system path provides energies only so far"
+                )
+            if model_id != 0:
+                raise NotImplementedError("the tiled large-system path supports model='d4' only")
+            from .large import dftd4_large
+
+            energy = torch.zeros_like(q2)
+            small = [b for b in range(num2.shape[0]) if b not in set(big)]
+            for b in big:
+                energy[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff)
+            if small:
+                # compact the small structures to the front of the atom axis
+                sel = torch.tensor(small, device=num2.device)
+                ns, ps, qs, back = _compact_front(num2[sel], pos2[sel], q2[sel], limit)
+                with torch.cuda.device(positions.device):
+                    es = _D4Function.apply(ps, qs, ns, par, engine)
+                energy[sel] = _scatter_back(es, back, nat)
+            return energy.reshape(*batch_shape, nat)
     with torch.cuda.device(positions.device):
         energy = _D4Function.apply(pos2, q2, num2, par, engine)
     return energy.reshape(*batch_shape, nat)
