@@ -59,7 +59,37 @@ WORKLOADS = {
                name="4096 synthetic 20-60-atom organics, D4 energy (two-body + ATM), padded to 60"),
     "c3": dict(nbatch=1024, lo=100, hi=100, seed=3, grad=True,
                name="1024 synthetic 100-atom molecules, D4 energy + analytic gradient incl. ATM"),
+    "c4": dict(nmol=6667, seed=4, grad=False, large=True,
+               name="single 20001-atom water cluster (6667 H2O), D4 energy, default 60/40/30 Bohr cutoffs, "
+                    "row-block split over the GPUs + all-reduce"),
 }  # fmt: skip
+
+
+def water_cluster(nmol: int, seed: int):
+    """O on a jittered simple-cubic lattice (5.86 Bohr) clipped to a
+    sphere, random orientation per molecule, r_OH = 1.81 Bohr, HOH = 104.5 deg."""
+    rng = np.random.default_rng(seed)
+    m = int(np.ceil((nmol * 6 / np.pi) ** (1 / 3))) + 2
+    grid = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) - (m - 1) / 2
+    grid = grid[np.argsort(np.linalg.norm(grid, axis=1), kind="stable")][:nmol]
+    o = grid * 5.86 + rng.normal(scale=0.3, size=(nmol, 3))
+    a = np.deg2rad(104.5) / 2
+    h1 = np.array([np.sin(a), np.cos(a), 0.0]) * 1.81
+    h2 = np.array([-np.sin(a), np.cos(a), 0.0]) * 1.81
+    # random rotations from normalised quaternions
+    qn = rng.normal(size=(nmol, 4))
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    w, x, y, z = qn.T
+    R = np.stack([
+        np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+        np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+        np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1),
+    ], 1)  # fmt: skip
+    pos = np.stack([o, o + R @ h1, o + R @ h2], 1).reshape(-1, 3)
+    numbers = np.tile(np.array([8, 1, 1]), nmol)
+    q = np.tile(np.array([-0.66, 0.33, 0.33]), nmol) + 0.02 * rng.normal(size=3 * nmol)
+    q -= q.mean()
+    return torch.from_numpy(numbers), torch.from_numpy(pos), torch.from_numpy(q)
 
 
 def oracle():
@@ -374,6 +404,84 @@ def run_b200(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_large(args, wl, rank, world, local_rank):
+    """C4: one large structure, strong scaling over the ranks (row-block + all-reduce)."""
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the dense reference formulation needs "
+                              "157 GB for rc6 and 6.4e13 B per N^3 temporary at 20k atoms (BASELINE.md); "
+                              "see cpu_baseline of the b200 arm for sub-cluster timings"}), flush=True)
+        return
+    import tad_dftd4_b200 as d4
+    from tad_dftd4_b200.large import dftd4_large
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    numbers_h, positions_h, q_h = water_cluster(args.nmol or wl["nmol"], wl["seed"])
+    nat = numbers_h.shape[0]
+    numbers, positions, q = numbers_h.to(dev), positions_h.to(dev, dtype), q_h.to(dev, dtype)
+    d4.set_checks(False)
+
+    def step():
+        return dftd4_large(numbers, positions, PBE0, q)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e = step()
+    torch.cuda.synchronize(dev)
+    with ClockSampler(local_rank) as clocks:
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s in range(args.steps):
+            ev[s][0].record()
+            e = step()
+            ev[s][1].record()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    stat = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+    sec = stat.item() / args.steps * 1e-3
+    # exact work counts (centre-triples: sum_j C(n_j, 2); pairs within the cutoffs)
+    nb40 = torch.zeros(nat, dtype=torch.int64, device=dev)
+    p60 = 0
+    p32 = positions.to(torch.float32)
+    for b0 in range(0, nat, 2048):
+        d = torch.cdist(p32[b0 : b0 + 2048], p32)
+        nb40[b0 : b0 + 2048] = (d <= 40.0).sum(-1) - 1
+        p60 += int((d <= 60.0).sum().item()) - d.shape[0]
+    ctrip = float((nb40 * (nb40 - 1) // 2).sum().item())
+    pairs = p60 / 2
+    if rank == 0:
+        line = {
+            "metric": "D4 dispersion throughput, single large system (atoms/s)",
+            "value": nat / sec, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": wl["name"], "atoms": nat, "parallelism": f"row-block x{world}, NCCL all-reduce of E",
+                       "l2": "working set (neighbour lists, stash) exceeds L2"},
+            "pair_terms_per_s": pairs / sec, "centre_triple_terms_per_s": ctrip / sec,
+            "pair_terms": pairs, "centre_triple_terms": ctrip,
+            "energy_sum": float(e.sum().item()),
+            "algorithmic_tflops": (F_P2 * pairs + F_T * ctrip) / sec / 1e12,
+            "e2e": None, "gpu_launches": None, "cpu_baseline": None,
+            "clocks": clocks.summary(),
+        }  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -383,13 +491,16 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nmol", type=int, default=0, help="c4: number of water molecules (default 6667)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl.get("large"):
+        run_large(args, wl, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:
         run_b200(args, wl, rank, world, local_rank)
