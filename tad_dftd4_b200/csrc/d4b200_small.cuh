@@ -229,20 +229,22 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   accD += W * de;
 }
 
-// One block of 8 consecutive top atoms i0..i0+7 for the lane's bottom pair (j,k);
-// `all` = every lane is active for all eight rows (warp-uniform), otherwise rows
-// are predicated per lane.  One instantiation per mask flavour keeps the hot loop
-// inside the instruction cache.
-template <typename T, int CP, bool OPEN>
+// One block of 8 consecutive top atoms i0..i0+7 for the lane's bottom pair (j,k).
+// PRED = false: every lane is active for all eight rows -> straight-line code in which
+// the compiler interleaves the eight independent evaluations (the chain of one
+// evaluation is ~14 dependent FP64 operations); PRED = true: per-row predicates.
+// Only three instantiations exist (closed straight, closed predicated, open
+// predicated) so that the hot loop stays inside the instruction cache.
+template <typename T, int CP, bool PRED, bool OPEN>
 __device__ __forceinline__ void triple_block8(const T* __restrict__ colj, const T* __restrict__ colk,
-                                              int i0, int j, int n, bool all, T bb, T cjk, T Pjk,
-                                              T ujk, T& accJ, T& accK, T (&v)[8]) {
+                                              int i0, int j, int n, T bb, T cjk, T Pjk, T ujk,
+                                              T& accJ, T& accK, T (&v)[8]) {
   int ti = i0 * (i0 - 1) / 2;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const int i = i0 + u;
     T ei = T(0);
-    if (all || (i < n && i > j)) {
+    if (!PRED || (i < n && i > j)) {
       const T a_s = colj[ti], c_s = colk[ti];
       const T t = colj[ti + 2 * CP] * colk[ti + 2 * CP] * ujk;
       const T pp = colj[ti + CP] * colk[ti + CP] * Pjk;
@@ -756,9 +758,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           for (int i0 = jmin + 1; i0 < n; i0 += 8) {
             const bool all = i0 > jmax && i0 + 8 <= n;  // warp-uniform
             if (open)
-              triple_block8<T, CP, true>(colj, colk, i0, j, n, all, bb, cjk, Pjk, ujk, accJ, accK, v);
+              triple_block8<T, CP, true, true>(colj, colk, i0, j, n, bb, cjk, Pjk, ujk, accJ, accK, v);
+            else if (all)
+              triple_block8<T, CP, false, false>(colj, colk, i0, j, n, bb, cjk, Pjk, ujk, accJ, accK, v);
             else
-              triple_block8<T, CP, false>(colj, colk, i0, j, n, all, bb, cjk, Pjk, ujk, accJ, accK, v);
+              triple_block8<T, CP, true, false>(colj, colk, i0, j, n, bb, cjk, Pjk, ujk, accJ, accK, v);
             const T y = reduce8x32(v, b4, b3, b2);
             const int iw = i0 + (lane >> 2);
             if ((lane & 3) == 0 && iw < n) Tw[iw] += y;
