@@ -164,6 +164,35 @@ int d4b200_large_energy_f32(d4b200_tables_t tables, const d4b200_params* par, in
                             int group_end, float* energy_dev, float* cn_dev, int* group_cost_dev,
                             void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Gradient of a single large structure, L = sum_i g_i E_i, in two stages so that ranks
+ * owning disjoint row / centre-group ranges need only two all-reduces:
+ *   stage 1 (d4b200_large_gradient_*): ACCUMULATES into force_dev [nat,3], dcn_dev [nat],
+ *           dq_dev [nat] (zero them first) the direct two-body and ATM terms of this
+ *           rank's ranges;  -> all-reduce(dcn_dev), all-reduce(dq_dev)
+ *   stage 2 (d4b200_large_cn_chain_*): adds the coordination-number chain rule for the
+ *           rows of this rank, given the TOTAL dL/dcn;  -> all-reduce(force_dev).
+ * dq_dev is dL/dq (returned to torch so that it can be chained through the charges). */
+int d4b200_large_gradient_f64(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                              const int64_t* numbers_dev, const double* positions_dev,
+                              const double* q_dev, const double* grad_energy_dev, int row_begin,
+                              int row_end, int group_begin, int group_end, double* force_dev,
+                              double* dcn_dev, double* dq_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
+int d4b200_large_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                              const int64_t* numbers_dev, const float* positions_dev,
+                              const float* q_dev, const float* grad_energy_dev, int row_begin,
+                              int row_end, int group_begin, int group_end, float* force_dev,
+                              float* dcn_dev, float* dq_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
+int d4b200_large_cn_chain_f64(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                              const int64_t* numbers_dev, const double* positions_dev,
+                              const double* dcn_total_dev, int row_begin, int row_end,
+                              double* force_dev, void* stream);
+int d4b200_large_cn_chain_f32(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                              const int64_t* numbers_dev, const float* positions_dev,
+                              const float* dcn_total_dev, int row_begin, int row_end,
+                              float* force_dev, void* stream);
+
 /* Synchronises ``stream`` and returns the device status bits recorded by the
  * last energy/gradient call that used ``workspace_dev``. */
 int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);

@@ -364,6 +364,7 @@ def dftd4(
     disp3: float = DISP3_CUTOFF,
     parts: bool = False,
     centres: Tensor | None = None,
+    cn: Tensor | None = None,
 ):
     """``tad_dftd4.dftd4`` (disp.py:44-146 -> dispersion/base.py:285-431) with
     explicit charges: TwoBodyTerm(Rational, q-dependent) + D4ATMApprox(Zero,
@@ -376,7 +377,8 @@ def dftd4(
         raise ValueError("Shape of atomic charges is not consistent with atomic numbers.")
     r4r2 = t["r4r2"].to(dtype)[numbers]
     rc6 = reference_c6(numbers, ga, gc, dtype)
-    cn = cn_d4(numbers, positions)
+    if cn is None:  # test helper: coordination numbers as an independent variable
+        cn = cn_d4(numbers, positions)
 
     if model == "d4":
         c6q = atomic_c6_d4(rc6, weight_references_d4(numbers, cn, q, ga, gc, wf))

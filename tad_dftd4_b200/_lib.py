@@ -44,6 +44,10 @@ _SIGS = {
     "d4b200_large_workspace_bytes": (C.c_size_t, [_VP, C.c_int, C.c_int]),
     "d4b200_large_energy_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_large_energy_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_large_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_large_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_large_cn_chain_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "d4b200_large_cn_chain_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "d4b200_status": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
     "d4b200_last_launch_count": (C.c_int, []),
     "d4b200_profile_enable": (C.c_int, [_VP, C.c_int]),

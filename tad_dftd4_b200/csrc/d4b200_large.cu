@@ -46,6 +46,17 @@ struct LargeArgs {
   T* cstash;               // [gridDim.x][GROUP][3][ucap] per-CTA centre stash scratch
   int* queue;              // [1] dynamic group counter
   int* status;
+  // gradient path
+  const T* gin;            // [nat] upstream dL/dE (nullable = ones)
+  T* zgd;                  // [nat,7] zeta * dgw/dcn
+  T* z0gd;                 // [nat,7] zeta0 * dgw/dcn
+  T* dzg;                  // [nat,7] dzeta/dq * gw
+  T* daq_cn;               // [nat,AVEC] dA_q/dcn
+  T* da0_cn;               // [nat,AVEC] dA_0/dcn
+  T* daq_q;                // [nat,AVEC] dA_q/dq
+  T* force;                // [nat,3] accumulated dL/dR
+  T* dcn;                  // [nat] accumulated dL/dcn (stage 2 input: total over ranks)
+  T* dq;                   // [nat] accumulated dL/dq
   int nat, ngroups, ucap;
   int row_begin, row_end;      // two-body rows of this rank
   int group_begin, group_end;  // ATM centre groups of this rank
@@ -96,7 +107,7 @@ __global__ void __launch_bounds__(128) large_cn(LargeArgs<T> A, int ncolchunks) 
 }
 
 // ---------------------------------------------------------------- weights
-template <typename T>
+template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) large_weights(LargeArgs<T> A) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int i = t >> 3, a = t & 7;
@@ -109,33 +120,53 @@ __global__ void __launch_bounds__(256) large_weights(LargeArgs<T> A) {
   double shift = arg;
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, o));
-  double S = 0.0;
-  for (int k = 1; k <= rc; ++k) S += exp(-((double)k * arg - shift));
-  double norm = S;
+  double S = 0.0, dS = 0.0;
+  for (int k = 1; k <= rc; ++k) {
+    const double e = exp(-((double)k * arg - shift));
+    S += e;
+    dS += -2.0 * (double)k * A.par.wf * d * e;
+  }
+  double norm = S, dnorm = dS;
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) norm += __shfl_xor_sync(0xffffffffu, norm, o);
+  for (int o = 4; o > 0; o >>= 1) {
+    norm += __shfl_xor_sync(0xffffffffu, norm, o);
+    dnorm += __shfl_xor_sync(0xffffffffu, dnorm, o);
+  }
   if (i < A.nat && a < NREF) {
-    double gw = norm > 0.0 ? S / norm : 0.0, zeta = 0.0;
+    double gw = 0.0, dgw = 0.0, zeta = 0.0, dzeta = 0.0;
+    if (norm > 0.0) {
+      gw = S / norm;
+      dgw = (dS - gw * dnorm) / norm;
+    }
     if (rc > 0) {
       const double qmod = (double)A.q[i] + A.tab.zeff[z];
       if (qmod > 0.0) {
-        const double scale = exp(A.tab.gamgc[z] * (1.0 - A.tab.refq[z * NREF + a] / (qmod - (double)d4_eps<T>())));
+        const double gam = A.tab.gamgc[z], qref = A.tab.refq[z * NREF + a];
+        const double qe = qmod - (double)d4_eps<T>();
+        const double scale = exp(gam * (1.0 - qref / qe));
         zeta = exp(A.par.ga * (1.0 - scale));
+        dzeta = -A.par.ga * gam * scale * zeta * qref / (qe * qe);
       } else {
         zeta = exp(A.par.ga);
       }
     }
+    const double z0 = on ? A.tab.zeta0[z * NREF + a] : 0.0;
     A.wq[i * NREF + a] = (T)(zeta * gw);
-    A.w0[i * NREF + a] = (T)((on ? A.tab.zeta0[z * NREF + a] : 0.0) * gw);
+    A.w0[i * NREF + a] = (T)(z0 * gw);
+    if (GRAD) {
+      A.zgd[i * NREF + a] = (T)(zeta * dgw);
+      A.z0gd[i * NREF + a] = (T)(z0 * dgw);
+      A.dzg[i * NREF + a] = (T)(dzeta * gw);
+    }
   }
 }
 
-template <typename T>
+template <typename T, bool GRAD>
 __global__ void __launch_bounds__(256) large_avec(LargeArgs<T> A) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int i = t / AVEC, w = t - i * AVEC;
   if (i >= A.nat) return;
-  T sq = T(0), s0 = T(0);
+  T sq = T(0), s0 = T(0), dqc = T(0), d0c = T(0), dqq = T(0);
   const int zraw = (int)A.numbers[i];
   if (w < NFREQ && zraw > 0 && zraw < NELEM) {
     const T* al = A.tab.alpha_w + (size_t)zraw * NREF * NFREQ + w;
@@ -144,10 +175,20 @@ __global__ void __launch_bounds__(256) large_avec(LargeArgs<T> A) {
       const T av = al[a * NFREQ];
       sq += A.wq[i * NREF + a] * av;
       s0 += A.w0[i * NREF + a] * av;
+      if (GRAD) {
+        dqc += A.zgd[i * NREF + a] * av;
+        d0c += A.z0gd[i * NREF + a] * av;
+        dqq += A.dzg[i * NREF + a] * av;
+      }
     }
   }
   A.aq[(size_t)i * AVEC + w] = sq;
   A.a0[(size_t)i * AVEC + w] = s0;
+  if (GRAD) {
+    A.daq_cn[(size_t)i * AVEC + w] = dqc;
+    A.da0_cn[(size_t)i * AVEC + w] = d0c;
+    A.daq_q[(size_t)i * AVEC + w] = dqq;
+  }
 }
 
 // ---------------------------------------------------------------- two-body
@@ -429,6 +470,411 @@ __global__ void __launch_bounds__(256, 2) large_atm(LargeArgs<T> A) {
   }
 }
 
+
+// ============================ gradient kernels ==============================
+// dL/dR, dL/dcn, dL/dq for L = sum_i g_i E_i (tests/kernel_model.py has the algebra).
+// Per-pair derivative scalars are 23-term dots with the derivative vectors
+// dA/dcn, dA/dq; everything is accumulated per ATOM (row owner / lane owner / centre
+// owner), so no per-pair storage is needed.
+
+// Two-body, one thread per row atom i: complete force on i from the pair terms and the
+// row's share of dL/dcn_i, dL/dq_i.
+template <typename T>
+__global__ void __launch_bounds__(128) large_twobody_grad(LargeArgs<T> A, int ncolchunks) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  T* const rv = reinterpret_cast<T*>(dsm);           // [3][NFREQ][128] row vectors, transposed
+  T* const sA = rv + 3 * NFREQ * 128;               // [64][AVEC] column tile
+  T* const sx = sA + 64 * AVEC;
+  T* const sy = sx + 64;
+  T* const sz = sy + 64;
+  T* const ss = sz + 64;
+  T* const sg = ss + 64;
+  int* const sreal = reinterpret_cast<int*>(sg + 64);
+  const int tid = threadIdx.x;
+  const int i = A.row_begin + blockIdx.x * 128 + tid;
+  const bool act = i < A.row_end;
+  const int zi = act ? (int)A.numbers[i] : 0;
+  const bool real_i = act && zi > 0 && zi < NELEM;
+  for (int w = 0; w < NFREQ; ++w) {
+    rv[(0 * NFREQ + w) * 128 + tid] = real_i ? A.aq[(size_t)i * AVEC + w] : T(0);
+    rv[(1 * NFREQ + w) * 128 + tid] = real_i ? A.daq_cn[(size_t)i * AVEC + w] : T(0);
+    rv[(2 * NFREQ + w) * 128 + tid] = real_i ? A.daq_q[(size_t)i * AVEC + w] : T(0);
+  }
+  const T xi = act ? A.pos[3 * i] : T(0), yi = act ? A.pos[3 * i + 1] : T(0), zi_ = act ? A.pos[3 * i + 2] : T(0);
+  const T si = real_i ? A.tab.sqrt_r4r2[zi] : T(0);
+  const T gi = real_i ? (A.gin ? A.gin[i] : T(1)) : T(0);
+  const Par<T>& P = A.par;
+  const int chunk = (A.nat + ncolchunks - 1) / ncolchunks;
+  const int c0 = blockIdx.y * chunk, c1 = min(A.nat, c0 + chunk);
+  T fx = T(0), fy = T(0), fz = T(0), dcn = T(0), dq = T(0);
+  for (int base = c0; base < c1; base += 64) {
+    __syncthreads();
+    for (int t = tid; t < 64 * AVEC; t += 128) {
+      const int j = base + t / AVEC;
+      sA[t] = j < c1 ? A.aq[(size_t)j * AVEC + (t % AVEC)] : T(0);
+    }
+    if (tid < 64) {
+      const int j = base + tid;
+      const int zj = j < c1 ? (int)A.numbers[j] : 0;
+      const bool rj = zj > 0 && zj < NELEM;
+      sx[tid] = j < c1 ? A.pos[3 * j] : T(0);
+      sy[tid] = j < c1 ? A.pos[3 * j + 1] : T(0);
+      sz[tid] = j < c1 ? A.pos[3 * j + 2] : T(0);
+      ss[tid] = rj ? A.tab.sqrt_r4r2[zj] : T(0);
+      sg[tid] = rj ? (A.gin ? A.gin[j] : T(1)) : T(0);
+      sreal[tid] = rj;
+    }
+    __syncthreads();
+    if (!real_i) continue;
+    const int m = min(64, c1 - base);
+    for (int t = 0; t < m; ++t) {
+      const T dx = xi - sx[t], dy = yi - sy[t], dz = zi_ - sz[t];
+      const T r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 <= P.disp2_sq && base + t != i && sreal[t]) {
+        T c6 = T(0), dc = T(0), dqv = T(0);
+        const T* aj = sA + t * AVEC;
+#pragma unroll
+        for (int w = 0; w < NFREQ; ++w) {
+          const T v = aj[w];
+          c6 += rv[(0 * NFREQ + w) * 128 + tid] * v;
+          dc += rv[(1 * NFREQ + w) * 128 + tid] * v;
+          dqv += rv[(2 * NFREQ + w) * 128 + tid] * v;
+        }
+        const T s2 = si * ss[t];
+        const T R0 = P.a1 * s2 + P.a2;
+        const T qq = s2 * s2;
+        const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
+        const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
+        const T t6 = d4_rcp(r6 + R6), t8 = d4_rcp(r8 + R8);
+        T F = P.s6 * t6 + P.s8 * qq * t8;
+        T dF = -(T(6) * P.s6 * r4 * t6 * t6 + T(8) * P.s8 * qq * r6 * t8 * t8);
+        if (P.s10k != T(0)) {
+          const T t10 = d4_rcp(r8 * r2 + R8 * R2);
+          F += P.s10k * qq * qq * t10;
+          dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
+        }
+        const T G2 = T(-0.5) * (gi + sg[t]);
+        const T fc = G2 * c6 * dF;
+        fx += fc * dx;
+        fy += fc * dy;
+        fz += fc * dz;
+        dcn += G2 * F * dc;
+        dq += G2 * F * dqv;
+      }
+    }
+  }
+  if (real_i) {
+    atomicAdd(&A.force[3 * i], fx);
+    atomicAdd(&A.force[3 * i + 1], fy);
+    atomicAdd(&A.force[3 * i + 2], fz);
+    atomicAdd(&A.dcn[i], dcn);
+    atomicAdd(&A.dq[i], dq);
+  }
+}
+
+// CN chain rule (stage 2, after dL/dcn has been summed over the ranks):
+// F_i += sum_j (dL/dcn_i + dL/dcn_j) dcn_ij/dr (R_i - R_j)/r  for the rows of this rank.
+template <typename T>
+__global__ void __launch_bounds__(128) large_cn_chain(LargeArgs<T> A, int ncolchunks) {
+  __shared__ T sx[128], sy[128], sz[128], sr[128], sd[128];
+  __shared__ int szn[128];
+  const int i = A.row_begin + blockIdx.x * 128 + threadIdx.x;
+  const bool act = i < A.row_end;
+  const int zraw = act ? (int)A.numbers[i] : 0;
+  const int zi = zraw > 0 && zraw < NELEM ? zraw : 0;
+  const T xi = act ? A.pos[3 * i] : T(0), yi = act ? A.pos[3 * i + 1] : T(0), zi_ = act ? A.pos[3 * i + 2] : T(0);
+  const T ri = zi ? A.tab.rcov[zi] : T(1);
+  const T di = zi ? A.dcn[i] : T(0);
+  const int chunk = (A.nat + ncolchunks - 1) / ncolchunks;
+  const int c0 = blockIdx.y * chunk, c1 = min(A.nat, c0 + chunk);
+  T fx = T(0), fy = T(0), fz = T(0);
+  for (int base = c0; base < c1; base += 128) {
+    const int j = base + threadIdx.x;
+    __syncthreads();
+    if (j < c1) {
+      const int zj = (int)A.numbers[j];
+      const bool rj = zj > 0 && zj < NELEM;
+      sx[threadIdx.x] = A.pos[3 * j];
+      sy[threadIdx.x] = A.pos[3 * j + 1];
+      sz[threadIdx.x] = A.pos[3 * j + 2];
+      szn[threadIdx.x] = rj ? zj : 0;
+      sr[threadIdx.x] = rj ? A.tab.rcov[zj] : T(1);
+      sd[threadIdx.x] = rj ? A.dcn[j] : T(0);
+    }
+    __syncthreads();
+    const int m = min(128, c1 - base);
+    if (zi) {
+      for (int t = 0; t < m; ++t) {
+        const T dx = xi - sx[t], dy = yi - sy[t], dz = zi_ - sz[t];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 <= A.par.cn_sq && base + t != i && szn[t] != 0) {
+          const T r = d4_sqrt(r2);
+          const T r0inv = d4_rcp(ri + sr[t]);
+          const T xx = T(7.5) * (r * r0inv - T(1));
+          if (fabs(xx) < T(8.7)) {
+            const T dcn = -A.tab.den[zi * NELEM + szn[t]] * T(7.5) * T(0.5641895835477563) * r0inv * d4_exp(-xx * xx);
+            const T c = (di + sd[t]) * dcn * d4_rcp(r);
+            fx += c * dx;
+            fy += c * dy;
+            fz += c * dz;
+          }
+        }
+      }
+    }
+  }
+  if (zi) {
+    atomicAdd(&A.force[3 * i], fx);
+    atomicAdd(&A.force[3 * i + 1], fy);
+    atomicAdd(&A.force[3 * i + 2], fz);
+  }
+}
+
+// ATM gradient, centre groups.  512 threads: warp w owns rows 2w, 2w+1 of the X tile,
+// lanes own the columns of the Y tile; loop order centre -> row so that the centre's
+// accumulators are four registers reduced once per (tile, centre).
+constexpr int GSTASH = 5;  // r^2, P, u, D^(j)_jx, D^(x)_xj
+template <typename T>
+__global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  T* p = reinterpret_cast<T*>(dsm);
+  T* const cA0 = p;                 p += GROUP * AVEC;         // centres: A0
+  T* const cdA = p;                 p += GROUP * AVEC;         // centres: dA0/dcn
+  T* const cpx = p;                 p += GROUP;
+  T* const cpy = p;                 p += GROUP;
+  T* const cpz = p;                 p += GROUP;
+  T* const csq = p;                 p += GROUP;
+  T* const cg = p;                  p += GROUP;
+  T* const tA0 = p;                 p += 2 * TILE * (AVEC + 1);  // tile atoms: A0
+  T* const tdA = p;                 p += 2 * TILE * (AVEC + 1);  // tile atoms: dA0/dcn
+  T* const tpx = p;                 p += 2 * TILE;
+  T* const tpy = p;                 p += 2 * TILE;
+  T* const tpz = p;                 p += 2 * TILE;
+  T* const tsq = p;                 p += 2 * TILE;
+  T* const tg = p;                  p += 2 * TILE;
+  T* const tst = p;                 p += 2 * GROUP * GSTASH * TILE;  // [side][j][comp][l]
+  int* const tidx = reinterpret_cast<int*>(p);
+  unsigned* const tmask = reinterpret_cast<unsigned*>(tidx + 2 * TILE);
+  int* const creal = reinterpret_cast<int*>(tmask + 2 * TILE);
+  int* const gcur = creal + GROUP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Par<T>& P = A.par;
+  T* const cst = A.cstash + (size_t)blockIdx.x * GROUP * GSTASH * A.ucap;
+#define TST(side, j, comp, l) tst[(((side) * GROUP + (j)) * GSTASH + (comp)) * TILE + (l)]
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) *gcur = A.group_begin + atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int g = *gcur;
+    if (g >= A.group_end) break;
+    const int nU = A.ucount[g];
+    const int* list = A.ulist + (size_t)g * A.ucap;
+    const unsigned* masks = A.umask + (size_t)g * A.ucap;
+    for (int t = tid; t < GROUP * AVEC; t += 512) {
+      const int j = g * GROUP + t / AVEC;
+      cA0[t] = j < A.nat ? A.a0[(size_t)j * AVEC + (t % AVEC)] : T(0);
+      cdA[t] = j < A.nat ? A.da0_cn[(size_t)j * AVEC + (t % AVEC)] : T(0);
+    }
+    if (tid < GROUP) {
+      const int j = g * GROUP + tid;
+      const int zj = j < A.nat ? (int)A.numbers[j] : 0;
+      creal[tid] = zj > 0 && zj < NELEM;
+      cpx[tid] = j < A.nat ? A.pos[3 * j] : T(0);
+      cpy[tid] = j < A.nat ? A.pos[3 * j + 1] : T(0);
+      cpz[tid] = j < A.nat ? A.pos[3 * j + 2] : T(0);
+      csq[tid] = creal[tid] ? A.tab.sqrt_r4r2[zj] : T(0);
+      cg[tid] = creal[tid] ? (A.gin ? A.gin[j] : T(1)) : T(0);
+    }
+    __syncthreads();
+    // ---- prologue: centre stash (5 values) for the whole list
+    for (int t = tid; t < GROUP * nU; t += 512) {
+      const int j = t / nU, u = t - j * nU;
+      const int x = list[u];
+      T a = T(1), Pv = T(0), uv = T(0), Dj = T(0), Dx = T(0);
+      if (masks[u] >> j & 1u) {
+        const T dx = A.pos[3 * x] - cpx[j], dy = A.pos[3 * x + 1] - cpy[j], dz = A.pos[3 * x + 2] - cpz[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        const T rinv = d4_rcp(d4_sqrt(r2));
+        T c6 = T(0), dj = T(0), dxv = T(0);
+        const T* ax = A.a0 + (size_t)x * AVEC;
+        const T* dax = A.da0_cn + (size_t)x * AVEC;
+#pragma unroll
+        for (int w = 0; w < NFREQ; ++w) {
+          c6 += cA0[j * AVEC + w] * ax[w];
+          dj += cdA[j * AVEC + w] * ax[w];
+          dxv += dax[w] * cA0[j * AVEC + w];
+        }
+        const T R0 = P.a1 * csq[j] * A.tab.sqrt_r4r2[(int)A.numbers[x]] + P.a2;
+        a = r2;
+        Pv = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+        uv = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
+        const T h = c6 != T(0) ? T(0.5) * d4_rcp(c6) : T(0);
+        Dj = dj * h;
+        Dx = dxv * h;
+      }
+      cst[((size_t)j * GSTASH + 0) * A.ucap + u] = a;
+      cst[((size_t)j * GSTASH + 1) * A.ucap + u] = Pv;
+      cst[((size_t)j * GSTASH + 2) * A.ucap + u] = uv;
+      cst[((size_t)j * GSTASH + 3) * A.ucap + u] = Dj;
+      cst[((size_t)j * GSTASH + 4) * A.ucap + u] = Dx;
+    }
+    __syncthreads();
+
+    const int ntile = (nU + TILE - 1) / TILE;
+    for (int tx = 0; tx < ntile; ++tx) {
+      for (int ty = tx; ty < ntile; ++ty) {
+        __syncthreads();
+        for (int t = tid; t < 2 * TILE; t += 512) {
+          const int side = t / TILE, l = t - side * TILE;
+          const int u = (side == 0 ? tx : ty) * TILE + l;
+          const bool ok = u < nU;
+          const int x = ok ? list[u] : 0;
+          tidx[t] = ok ? x : -1;
+          tmask[t] = ok ? masks[u] : 0u;
+          tpx[t] = ok ? A.pos[3 * x] : T(0);
+          tpy[t] = ok ? A.pos[3 * x + 1] : T(0);
+          tpz[t] = ok ? A.pos[3 * x + 2] : T(0);
+          tsq[t] = ok ? A.tab.sqrt_r4r2[(int)A.numbers[x]] : T(0);
+          tg[t] = ok ? (A.gin ? A.gin[x] : T(1)) : T(0);
+        }
+        for (int t = tid; t < 2 * TILE * AVEC; t += 512) {
+          const int side = t / (TILE * AVEC), r = t - side * TILE * AVEC;
+          const int l = r / AVEC, w = r - l * AVEC;
+          const int u = (side == 0 ? tx : ty) * TILE + l;
+          const size_t src = u < nU ? (size_t)list[u] * AVEC + w : 0;
+          tA0[(side * TILE + l) * (AVEC + 1) + w] = u < nU ? A.a0[src] : T(0);
+          tdA[(side * TILE + l) * (AVEC + 1) + w] = u < nU ? A.da0_cn[src] : T(0);
+        }
+        for (int t = tid; t < 2 * GROUP * GSTASH * TILE; t += 512) {
+          const int side = t / (GROUP * GSTASH * TILE), r = t - side * GROUP * GSTASH * TILE;
+          const int jc = r / TILE, l = r - jc * TILE;
+          const int u = (side == 0 ? tx : ty) * TILE + l;
+          tst[t] = u < nU ? cst[(size_t)jc * A.ucap + u] : T(0);
+        }
+        __syncthreads();
+        // ---- faces of this lane: rows 2w, 2w+1 x column `lane`
+        const int kk = tidx[TILE + lane];
+        const unsigned mk = tmask[TILE + lane];
+        const T gk = tg[TILE + lane];
+        const T kx = tpx[TILE + lane], ky = tpy[TILE + lane], kz = tpz[TILE + lane];
+        T fc_[2], fP[2], fu[2], fDi[2], fDk[2], rx[2], ry[2], rz[2];
+        bool pv[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = warp * 2 + rr;
+          const int ii = tidx[row];
+          pv[rr] = ii >= 0 && kk >= 0 && ii != kk && (tx != ty || row < lane) && (tmask[row] & mk) != 0u;
+          fc_[rr] = T(1), fP[rr] = T(0), fu[rr] = T(0), fDi[rr] = T(0), fDk[rr] = T(0);
+          rx[rr] = tpx[row] - kx, ry[rr] = tpy[row] - ky, rz[rr] = tpz[row] - kz;  // R_i - R_k
+          if (pv[rr]) {
+            const T c = rx[rr] * rx[rr] + ry[rr] * ry[rr] + rz[rr] * rz[rr];
+            const T rinv = d4_rcp(d4_sqrt(c));
+            T c6 = T(0), di = T(0), dk = T(0);
+            const T* ai = &tA0[row * (AVEC + 1)];
+            const T* ak = &tA0[(TILE + lane) * (AVEC + 1)];
+            const T* dai = &tdA[row * (AVEC + 1)];
+            const T* dak = &tdA[(TILE + lane) * (AVEC + 1)];
+#pragma unroll
+            for (int w = 0; w < NFREQ; ++w) {
+              c6 += ai[w] * ak[w];
+              di += dai[w] * ak[w];
+              dk += dak[w] * ai[w];
+            }
+            const T R0 = P.a1 * tsq[row] * tsq[TILE + lane] + P.a2;
+            const T h = c6 != T(0) ? T(0.5) * d4_rcp(c6) : T(0);
+            fc_[rr] = c;
+            fP[rr] = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+            fu[rr] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
+            fDi[rr] = di * h;
+            fDk[rr] = dk * h;
+          }
+        }
+        T kfx = T(0), kfy = T(0), kfz = T(0), kdc = T(0);         // column atom k
+        T ifx[2] = {T(0), T(0)}, ify[2] = {T(0), T(0)}, ifz[2] = {T(0), T(0)}, idc[2] = {T(0), T(0)};
+        for (int j = 0; j < GROUP; ++j) {
+          T jfx = T(0), jfy = T(0), jfz = T(0), jdc = T(0);       // centre j
+          const T b = TST(1, j, 0, lane), Pb = TST(1, j, 1, lane), ub = TST(1, j, 2, lane);
+          const T Djk = TST(1, j, 3, lane), Dkj = TST(1, j, 4, lane);
+          const T kjx = kx - cpx[j], kjy = ky - cpy[j], kjz = kz - cpz[j];  // R_k - R_j
+          const bool kin = mk >> j & 1u;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const int row = warp * 2 + rr;
+            if (pv[rr] && kin && (tmask[row] >> j & 1u)) {
+              const T a = TST(0, j, 0, row), c = fc_[rr];
+              const T X = a + b - c, Y = a - b + c, Z = b + c - a;
+              const T s = X * Y * Z;
+              const T abc = a * b * c;
+              const T t = TST(0, j, 2, row) * ub * fu[rr];
+              const T d = T(1) + T(6) * t;
+              const T inv = d4_rcp(abc * d);
+              const T Q = inv * d, f = inv * abc;
+              const T psf = TST(0, j, 1, row) * Pb * fP[rr] * f;
+              const T e = (T(0.375) * s * Q + T(1)) * psf;
+              const T W = tg[row] + gk;
+              const T common = e * (T(-2.5) + T(3) * P.alp3 * f * t) + psf;
+              const T k3 = T(0.375) * psf * Q;
+              const T yz = Y * Z, xz = X * Z, xy = X * Y;
+              // dL/d(r^2) of the three edges, times 2 for d r^2/dR
+              const T da = T(2) * W * (common * (Q * b * c) + k3 * (yz + xz - xy));   // (j,i)
+              const T db = T(2) * W * (common * (Q * a * c) + k3 * (yz - xz + xy));   // (j,k)
+              const T dc = T(2) * W * (common * (Q * a * b) + k3 * (xz + xy - yz));   // (i,k)
+              const T ijx = tpx[row] - cpx[j], ijy = tpy[row] - cpy[j], ijz = tpz[row] - cpz[j];  // R_i - R_j
+              const T vax = da * ijx, vay = da * ijy, vaz = da * ijz;
+              const T vbx = db * kjx, vby = db * kjy, vbz = db * kjz;
+              const T vcx = dc * rx[rr], vcy = dc * ry[rr], vcz = dc * rz[rr];
+              ifx[rr] += vax + vcx, ify[rr] += vay + vcy, ifz[rr] += vaz + vcz;
+              kfx += vbx - vcx, kfy += vby - vcy, kfz += vbz - vcz;
+              jfx -= vax + vbx, jfy -= vay + vby, jfz -= vaz + vbz;
+              const T We = W * e;
+              idc[rr] += We * (TST(0, j, 4, row) + fDi[rr]);   // D^(i)_ij + D^(i)_ik
+              kdc += We * (Dkj + fDk[rr]);                      // D^(k)_kj + D^(k)_ki
+              jdc += We * (TST(0, j, 3, row) + Djk);           // D^(j)_ji + D^(j)_jk
+            }
+          }
+          jfx = warp_sum(jfx), jfy = warp_sum(jfy), jfz = warp_sum(jfz), jdc = warp_sum(jdc);
+          if (lane == 0 && (jfx != T(0) || jfy != T(0) || jfz != T(0) || jdc != T(0))) {
+            const int jj = g * GROUP + j;
+            atomicAdd(&A.force[3 * jj], jfx);
+            atomicAdd(&A.force[3 * jj + 1], jfy);
+            atomicAdd(&A.force[3 * jj + 2], jfz);
+            atomicAdd(&A.dcn[jj], jdc);
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const T sx_ = warp_sum(ifx[rr]), sy_ = warp_sum(ify[rr]), sz_ = warp_sum(ifz[rr]), sc_ = warp_sum(idc[rr]);
+          const int ii = tidx[warp * 2 + rr];
+          if (lane == 0 && ii >= 0 && (sx_ != T(0) || sy_ != T(0) || sz_ != T(0) || sc_ != T(0))) {
+            atomicAdd(&A.force[3 * ii], sx_);
+            atomicAdd(&A.force[3 * ii + 1], sy_);
+            atomicAdd(&A.force[3 * ii + 2], sz_);
+            atomicAdd(&A.dcn[ii], sc_);
+          }
+        }
+        if (kk >= 0 && (kfx != T(0) || kfy != T(0) || kfz != T(0) || kdc != T(0))) {
+          atomicAdd(&A.force[3 * kk], kfx);
+          atomicAdd(&A.force[3 * kk + 1], kfy);
+          atomicAdd(&A.force[3 * kk + 2], kfz);
+          atomicAdd(&A.dcn[kk], kdc);
+        }
+      }
+    }
+  }
+#undef TST
+}
+
+template <typename T>
+constexpr size_t atm_grad_smem() {
+  return sizeof(T) * (2 * GROUP * AVEC + 5 * GROUP + 2 * 2 * TILE * (AVEC + 1) + 5 * 2 * TILE +
+                      2 * GROUP * GSTASH * TILE) +
+         sizeof(int) * (2 * TILE + 2 * TILE + GROUP + 4);
+}
+template <typename T>
+constexpr size_t twobody_grad_smem() {
+  return sizeof(T) * (3 * NFREQ * 128 + 64 * AVEC + 5 * 64) + sizeof(int) * 64;
+}
+
 }  // namespace d4b200
 
 using namespace d4b200;
@@ -439,9 +885,10 @@ size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct LargeCarve {
   size_t cn, wq, w0, aq, a0, ulist, umask, ucount, cstash, queue, total;
+  size_t zgd, z0gd, dzg, daq_cn, da0_cn, daq_q;
 };
 
-LargeCarve large_carve(int nat, size_t elem, int nctas) {
+LargeCarve large_carve(int nat, size_t elem, int nctas, bool grad = false) {
   LargeCarve c;
   const size_t ng = (nat + GROUP - 1) / GROUP;
   size_t o = 0;
@@ -454,7 +901,16 @@ LargeCarve large_carve(int nat, size_t elem, int nctas) {
   c.ucount = o, o += al256(ng * sizeof(int));
   c.ulist = o, o += al256(ng * nat * sizeof(int));
   c.umask = o, o += al256(ng * nat * sizeof(unsigned));
-  c.cstash = o, o += al256((size_t)nctas * GROUP * 3 * nat * elem);
+  c.cstash = o, o += al256((size_t)nctas * GROUP * (grad ? GSTASH : 3) * nat * elem);
+  c.zgd = c.z0gd = c.dzg = c.daq_cn = c.da0_cn = c.daq_q = 0;
+  if (grad) {
+    c.zgd = o, o += al256((size_t)nat * NREF * elem);
+    c.z0gd = o, o += al256((size_t)nat * NREF * elem);
+    c.dzg = o, o += al256((size_t)nat * NREF * elem);
+    c.daq_cn = o, o += al256((size_t)nat * AVEC * elem);
+    c.da0_cn = o, o += al256((size_t)nat * AVEC * elem);
+    c.daq_q = o, o += al256((size_t)nat * AVEC * elem);
+  }
   c.total = o;
   return c;
 }
@@ -510,6 +966,8 @@ int run_large(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t
   A.ulist = reinterpret_cast<int*>(w + c.ulist);
   A.umask = reinterpret_cast<unsigned*>(w + c.umask);
   A.cstash = reinterpret_cast<T*>(w + c.cstash);
+  A.gin = nullptr;
+  A.zgd = A.z0gd = A.dzg = A.daq_cn = A.da0_cn = A.daq_q = A.force = A.dcn = A.dq = nullptr;
   A.nat = nat;
   A.ngroups = ng;
   A.ucap = nat;
@@ -529,8 +987,8 @@ int run_large(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t
   const int cchunks = nat > 4096 ? 8 : 1;
   large_cn<T><<<dim3((nat + 127) / 128, cchunks), 128, 0, st>>>(A, cchunks);
   if (cn_out) cudaMemcpyAsync(cn_out, A.cn, nat * sizeof(T), cudaMemcpyDeviceToDevice, st);
-  large_weights<T><<<(nat * 8 + 255) / 256, 256, 0, st>>>(A);
-  large_avec<T><<<(nat * AVEC + 255) / 256, 256, 0, st>>>(A);
+  large_weights<T, false><<<(nat * 8 + 255) / 256, 256, 0, st>>>(A);
+  large_avec<T, false><<<(nat * AVEC + 255) / 256, 256, 0, st>>>(A);
   if (energy && A.row_end > A.row_begin) {
     const int rows = A.row_end - A.row_begin;
     large_twobody<T><<<dim3((rows + 127) / 128, cchunks), 128, 0, st>>>(A, cchunks);
@@ -549,6 +1007,121 @@ int run_large(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+
+template <typename T>
+void fill_common(LargeArgs<T>& A, d4b200_tables* h, const d4b200_params* par, const LargeCarve& c,
+                 unsigned char* w, int nat, const int64_t* numbers, const T* pos, const T* q) {
+  const int ng = (nat + GROUP - 1) / GROUP;
+  A.numbers = numbers;
+  A.pos = pos;
+  A.q = q;
+  A.energy = nullptr;
+  A.status = reinterpret_cast<int*>(w);
+  A.queue = reinterpret_cast<int*>(w) + 1;
+  A.cn = reinterpret_cast<T*>(w + c.cn);
+  A.wq = reinterpret_cast<T*>(w + c.wq);
+  A.w0 = reinterpret_cast<T*>(w + c.w0);
+  A.aq = reinterpret_cast<T*>(w + c.aq);
+  A.a0 = reinterpret_cast<T*>(w + c.a0);
+  A.ucount = reinterpret_cast<int*>(w + c.ucount);
+  A.ulist = reinterpret_cast<int*>(w + c.ulist);
+  A.umask = reinterpret_cast<unsigned*>(w + c.umask);
+  A.cstash = reinterpret_cast<T*>(w + c.cstash);
+  A.zgd = reinterpret_cast<T*>(w + c.zgd);
+  A.z0gd = reinterpret_cast<T*>(w + c.z0gd);
+  A.dzg = reinterpret_cast<T*>(w + c.dzg);
+  A.daq_cn = reinterpret_cast<T*>(w + c.daq_cn);
+  A.da0_cn = reinterpret_cast<T*>(w + c.da0_cn);
+  A.daq_q = reinterpret_cast<T*>(w + c.daq_q);
+  A.gin = nullptr;
+  A.force = A.dcn = A.dq = nullptr;
+  A.nat = nat;
+  A.ngroups = ng;
+  A.ucap = nat;
+  if constexpr (sizeof(T) == 8) {
+    A.tab = h->t64;
+  } else {
+    A.tab = h->t32;
+  }
+  A.par = large_par<T>(par, h->ga);
+}
+
+int large_grad_ctas(const d4b200_tables* h) { return h->num_sms; }
+
+// Stage 1 of the gradient: everything except the CN chain rule.  Accumulates into
+// force [nat,3], dcn [nat], dq [nat] (zero them first).
+template <typename T>
+int run_large_grad(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t* numbers,
+                   const T* pos, const T* q, const T* gin, int row_begin, int row_end,
+                   int group_begin, int group_end, T* force, T* dcn, T* dq, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  if (!h || !par || !numbers || !pos || !q || !ws || !force || !dcn || !dq || nat <= 0) return D4B200_EINVAL;
+  if (par->model != D4B200_MODEL_D4) return D4B200_EPARAM;
+  const int nctas = large_grad_ctas(h);
+  const LargeCarve c = large_carve(nat, sizeof(T), nctas, true);
+  if (ws_bytes < c.total) return D4B200_EWORKSPACE;
+  unsigned char* w = reinterpret_cast<unsigned char*>(ws);
+  LargeArgs<T> A;
+  fill_common<T>(A, h, par, c, w, nat, numbers, pos, q);
+  const int ng = A.ngroups;
+  A.gin = gin;
+  A.force = force;
+  A.dcn = dcn;
+  A.dq = dq;
+  A.row_begin = row_begin < 0 ? 0 : row_begin;
+  A.row_end = row_end > nat ? nat : row_end;
+  A.group_begin = group_begin < 0 ? 0 : group_begin;
+  A.group_end = group_end > ng ? ng : group_end;
+
+  static bool configured[2] = {false, false};
+  constexpr int dt = sizeof(T) == 8 ? 0 : 1;
+  if (!configured[dt]) {
+    cudaFuncSetAttribute(large_atm_grad<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atm_grad_smem<T>());
+    cudaFuncSetAttribute(large_twobody_grad<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)twobody_grad_smem<T>());
+    configured[dt] = true;
+  }
+  cudaMemsetAsync(w, 0, 256, st);
+  cudaMemsetAsync(A.cn, 0, nat * sizeof(T), st);
+  const int cchunks = nat > 4096 ? 8 : 1;
+  large_cn<T><<<dim3((nat + 127) / 128, cchunks), 128, 0, st>>>(A, cchunks);
+  large_weights<T, true><<<(nat * 8 + 255) / 256, 256, 0, st>>>(A);
+  large_avec<T, true><<<(nat * AVEC + 255) / 256, 256, 0, st>>>(A);
+  if (A.row_end > A.row_begin) {
+    const int rows = A.row_end - A.row_begin;
+    large_twobody_grad<T><<<dim3((rows + 127) / 128, cchunks), 128, twobody_grad_smem<T>(), st>>>(A, cchunks);
+  }
+  if (A.par.has_atm && A.group_end > A.group_begin) {
+    large_union<T><<<ng, 256, 0, st>>>(A);
+    int grid = nctas;
+    if (grid > A.group_end - A.group_begin) grid = A.group_end - A.group_begin;
+    large_atm_grad<T><<<grid, 512, atm_grad_smem<T>(), st>>>(A);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+// Stage 2: CN chain rule for the rows of this rank with the TOTAL dL/dcn.
+template <typename T>
+int run_large_chain(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t* numbers,
+                    const T* pos, const T* dcn_total, int row_begin, int row_end, T* force,
+                    cudaStream_t st) {
+  if (!h || !par || !numbers || !pos || !dcn_total || !force || nat <= 0) return D4B200_EINVAL;
+  LargeArgs<T> A;
+  LargeCarve c = large_carve(nat, sizeof(T), 1, true);
+  unsigned char dummy = 0;
+  fill_common<T>(A, h, par, c, &dummy, nat, numbers, pos, pos);
+  A.dcn = const_cast<T*>(dcn_total);
+  A.force = force;
+  A.row_begin = row_begin < 0 ? 0 : row_begin;
+  A.row_end = row_end > nat ? nat : row_end;
+  if (A.row_end <= A.row_begin) return 0;
+  const int cchunks = nat > 4096 ? 8 : 1;
+  const int rows = A.row_end - A.row_begin;
+  large_cn_chain<T><<<dim3((rows + 127) / 128, cchunks), 128, 0, st>>>(A, cchunks);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -557,7 +1130,38 @@ int d4b200_large_group_size(void) { return GROUP; }
 
 size_t d4b200_large_workspace_bytes(d4b200_tables_t h, int nat, int fp32) {
   if (!h || nat <= 0) return 0;
-  return large_carve(nat, fp32 ? 4 : 8, large_ctas(h)).total;
+  const size_t e = large_carve(nat, fp32 ? 4 : 8, large_ctas(h)).total;
+  const size_t g = large_carve(nat, fp32 ? 4 : 8, large_grad_ctas(h), true).total;
+  return e > g ? e : g;
+}
+
+int d4b200_large_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nat,
+                              const int64_t* numbers, const double* pos, const double* q,
+                              const double* gin, int row_begin, int row_end, int group_begin,
+                              int group_end, double* force, double* dcn, double* dq, void* ws,
+                              size_t ws_bytes, void* stream) {
+  return run_large_grad<double>(t, par, nat, numbers, pos, q, gin, row_begin, row_end, group_begin,
+                                group_end, force, dcn, dq, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_large_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nat,
+                              const int64_t* numbers, const float* pos, const float* q,
+                              const float* gin, int row_begin, int row_end, int group_begin,
+                              int group_end, float* force, float* dcn, float* dq, void* ws,
+                              size_t ws_bytes, void* stream) {
+  return run_large_grad<float>(t, par, nat, numbers, pos, q, gin, row_begin, row_end, group_begin,
+                               group_end, force, dcn, dq, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_large_cn_chain_f64(d4b200_tables_t t, const d4b200_params* par, int nat,
+                              const int64_t* numbers, const double* pos, const double* dcn_total,
+                              int row_begin, int row_end, double* force, void* stream) {
+  return run_large_chain<double>(t, par, nat, numbers, pos, dcn_total, row_begin, row_end, force,
+                                 (cudaStream_t)stream);
+}
+int d4b200_large_cn_chain_f32(d4b200_tables_t t, const d4b200_params* par, int nat,
+                              const int64_t* numbers, const float* pos, const float* dcn_total,
+                              int row_begin, int row_end, float* force, void* stream) {
+  return run_large_chain<float>(t, par, nat, numbers, pos, dcn_total, row_begin, row_end, force,
+                                (cudaStream_t)stream);
 }
 
 int d4b200_large_energy_f64(d4b200_tables_t t, const d4b200_params* par, int nat,

@@ -285,9 +285,7 @@ def _compact_front(numbers: Tensor, positions: Tensor, q: Tensor, width: int):
 
 
 def _scatter_back(values: Tensor, order: Tensor, nat: int) -> Tensor:
-    out = values.new_zeros((values.shape[0], nat))
-    out.scatter_(1, order, values)
-    return out
+    return values.new_zeros((values.shape[0], nat)).scatter(1, order, values)
 
 
 def _eeq_charges(numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: Cutoff) -> Tensor:
@@ -380,27 +378,23 @@ def dftd4(
         counts = (num2 != 0).sum(-1)
         big = torch.nonzero(counts > limit).flatten().tolist()
         if big:
-            if positions.requires_grad or q.requires_grad:
-                raise NotImplementedError(
-                    f"gradients for structures with more than {limit} atoms: the tiled "
-                    "large-system path provides energies only so far"
-                )
             if model_id != 0:
                 raise NotImplementedError("the tiled large-system path supports model='d4' only")
             from .large import dftd4_large
 
-            energy = torch.zeros_like(q2)
+            rows: list[Tensor | None] = [None] * num2.shape[0]
             small = [b for b in range(num2.shape[0]) if b not in set(big)]
             for b in big:
-                energy[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff)
+                rows[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff)
             if small:
                 # compact the small structures to the front of the atom axis
                 sel = torch.tensor(small, device=num2.device)
                 ns, ps, qs, back = _compact_front(num2[sel], pos2[sel], q2[sel], limit)
                 with torch.cuda.device(positions.device):
-                    es = _D4Function.apply(ps, qs, ns, par, engine)
-                energy[sel] = _scatter_back(es, back, nat)
-            return energy.reshape(*batch_shape, nat)
+                    es = _scatter_back(_D4Function.apply(ps, qs, ns, par, engine), back, nat)
+                for n, b in enumerate(small):
+                    rows[b] = es[n]
+            return torch.stack(rows).reshape(*batch_shape, nat)
     with torch.cuda.device(positions.device):
         energy = _D4Function.apply(pos2, q2, num2, par, engine)
     return energy.reshape(*batch_shape, nat)

@@ -17,7 +17,7 @@ from typing import Callable, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["dftd4_large", "morton_order", "balanced_ranges"]
+__all__ = ["dftd4_large", "dftd4_large_vjp", "large_energy", "morton_order", "balanced_ranges"]
 
 Tensor = torch.Tensor
 
@@ -78,6 +78,149 @@ def _kernel_compute(engine, par, numbers, positions, q, rows, groups, want_cost)
     return energy, cost
 
 
+class _Plan:
+    """Sorted/compacted view of one structure + this rank's share of the work."""
+
+    def __init__(self, numbers, positions, q, group, compute_cost, gs):
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        keep = torch.nonzero(numbers != 0).flatten()
+        self.order = keep[morton_order(positions[keep])]
+        self.numbers = numbers[self.order].to(torch.int64).contiguous()
+        self.positions = positions[self.order].detach().contiguous()
+        self.q = q[self.order].detach().to(positions.dtype).contiguous()
+        self.nat = int(self.order.numel())
+        ng = (self.nat + gs - 1) // gs
+        if self.world > 1 and self.nat > 0:
+            # cost model: a centre group with m neighbours evaluates ~m^2/2 pairs x group size
+            cost = compute_cost(self.numbers, self.positions, self.q)
+            g0, g1 = balanced_ranges(cost.to(torch.float64) ** 2, self.world)[self.rank]
+            r0, r1 = min(self.nat, g0 * gs), min(self.nat, g1 * gs)  # rows follow the same blocks
+            if self.rank == self.world - 1:
+                r1 = self.nat
+        else:
+            g0, g1, r0, r1 = 0, ng, 0, self.nat
+        self.rows, self.groups = (r0, r1), (g0, g1)
+
+    def all_reduce(self, t: Tensor) -> Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def _kernel_backend(positions: Tensor, param, cutoff):
+    from . import _lib, defaults
+    from .disp import _Engine, _flatten_param
+
+    engine = _Engine.get(positions.device, defaults.GA_DEFAULT, defaults.GC_DEFAULT)
+    par = _flatten_param(param, cutoff, 0, defaults.WF_DEFAULT)
+    lib = engine.lib
+    gs = int(lib.d4b200_large_group_size())
+    fp32 = positions.dtype == torch.float32
+
+    def ws_for(nat):
+        return engine.large_workspace(int(lib.d4b200_large_workspace_bytes(engine.handle, nat, int(fp32))))
+
+    def stream():
+        return torch.cuda.current_stream(positions.device).cuda_stream
+
+    def energy(n, p, qq, rows, groups, want_cost):
+        with torch.cuda.device(p.device):
+            return _kernel_compute(engine, par, n, p, qq, rows, groups, want_cost)
+
+    def grad1(n, p, qq, g, rows, groups):
+        nat = n.shape[0]
+        force = torch.zeros((nat, 3), dtype=p.dtype, device=p.device)
+        dcn = torch.zeros(nat, dtype=p.dtype, device=p.device)
+        dq = torch.zeros(nat, dtype=p.dtype, device=p.device)
+        ws = ws_for(nat)
+        fn = lib.d4b200_large_gradient_f32 if fp32 else lib.d4b200_large_gradient_f64
+        with torch.cuda.device(p.device):
+            _lib.check(
+                fn(engine.handle, C.byref(par), nat, n.data_ptr(), p.data_ptr(), qq.data_ptr(),
+                   g.data_ptr() if g is not None else None, rows[0], rows[1], groups[0], groups[1],
+                   force.data_ptr(), dcn.data_ptr(), dq.data_ptr(), ws.data_ptr(), ws.numel(), stream()),
+                "d4b200_large_gradient",
+            )  # fmt: skip
+        return force, dcn, dq
+
+    def grad2(n, p, dcn_total, rows, force):
+        fn = lib.d4b200_large_cn_chain_f32 if fp32 else lib.d4b200_large_cn_chain_f64
+        with torch.cuda.device(p.device):
+            _lib.check(
+                fn(engine.handle, C.byref(par), n.shape[0], n.data_ptr(), p.data_ptr(),
+                   dcn_total.data_ptr(), rows[0], rows[1], force.data_ptr(), stream()),
+                "d4b200_large_cn_chain",
+            )  # fmt: skip
+        return force
+
+    return dict(energy=energy, grad1=grad1, grad2=grad2, group_size=gs)
+
+
+def _check_single(numbers, positions, q):
+    if numbers.dim() != 1 or positions.shape != (numbers.shape[0], 3) or q.shape != numbers.shape:
+        raise ValueError("expected numbers (nat,), positions (nat, 3), q (nat,)")
+
+
+def large_energy(numbers, positions, param, q, *, cutoff=None, group=None, backend=None) -> Tensor:
+    """Atom-resolved D4 energy of ONE structure ``(nat,)`` with the tiled kernels
+    (no autograd; see :func:`dftd4_large`)."""
+    _check_single(numbers, positions, q)
+    be = backend or _kernel_backend(positions, param, cutoff)
+    plan = _Plan(numbers, positions, q, group,
+                 lambda n, p, qq: be["energy"](n, p, qq, (0, 0), (0, 0), True)[1], be["group_size"])  # fmt: skip
+    out = torch.zeros(numbers.shape[0], dtype=positions.dtype, device=positions.device)
+    if plan.nat == 0:
+        return out
+    e_s, _ = be["energy"](plan.numbers, plan.positions, plan.q, plan.rows, plan.groups, False)
+    out[plan.order] = plan.all_reduce(e_s)
+    return out
+
+
+def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=None, backend=None):
+    """``(dL/dpositions, dL/dq)`` for ``L = sum_i gout_i E_i`` of ONE structure.
+
+    Two stages with one all-reduce each (plus the final one for the forces):
+    direct two-body/ATM terms -> all-reduce(dL/dcn, dL/dq) -> CN chain rule on the
+    rank's rows -> all-reduce(dL/dpositions)."""
+    _check_single(numbers, positions, q)
+    be = backend or _kernel_backend(positions, param, cutoff)
+    plan = _Plan(numbers, positions, q, group,
+                 lambda n, p, qq: be["energy"](n, p, qq, (0, 0), (0, 0), True)[1], be["group_size"])  # fmt: skip
+    gpos = torch.zeros_like(positions)
+    gq = torch.zeros(numbers.shape[0], dtype=positions.dtype, device=positions.device)
+    if plan.nat == 0:
+        return gpos, gq
+    g_s = None if gout is None else gout[plan.order].to(positions.dtype).contiguous()
+    force, dcn, dq = be["grad1"](plan.numbers, plan.positions, plan.q, g_s, plan.rows, plan.groups)
+    if plan.world > 1:
+        both = torch.stack([dcn, dq])
+        plan.all_reduce(both)
+        dcn, dq = both[0].contiguous(), both[1].contiguous()
+    force = be["grad2"](plan.numbers, plan.positions, dcn, plan.rows, force)
+    plan.all_reduce(force)
+    gpos[plan.order] = force
+    gq[plan.order] = dq
+    return gpos, gq
+
+
+class _LargeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, positions, q, numbers, param, cutoff, group):
+        ctx.save_for_backward(positions, q, numbers)
+        ctx.param, ctx.cutoff, ctx.group = param, cutoff, group
+        return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        positions, q, numbers = ctx.saved_tensors
+        gpos, gq = dftd4_large_vjp(numbers, positions, ctx.param, q, gout.contiguous(),
+                                   cutoff=ctx.cutoff, group=ctx.group)  # fmt: skip
+        return gpos, gq, None, None, None, None
+
+
 def dftd4_large(
     numbers: Tensor,
     positions: Tensor,
@@ -89,59 +232,17 @@ def dftd4_large(
     compute: Callable | None = None,
     group_size: int | None = None,
 ) -> Tensor:
-    """Atom-resolved D4 energy of ONE structure ``(nat,)`` with the tiled kernels.
+    """Atom-resolved D4 energy of ONE structure ``(nat,)`` with the tiled kernels;
+    differentiable with respect to ``positions`` and ``q``.
 
     With an initialised ``torch.distributed`` process group every rank passes the same
     (replicated) inputs, evaluates its share of two-body rows / ATM centre groups and
     the result is all-reduced, so every rank returns the full energy vector.
 
     ``compute(numbers, positions, q, rows, groups, want_cost)`` is injectable for CPU
-    tests of this host logic.
+    tests of this host logic (energy only).
     """
-    if numbers.dim() != 1 or positions.shape != (numbers.shape[0], 3) or q.shape != numbers.shape:
-        raise ValueError("dftd4_large expects numbers (nat,), positions (nat, 3), q (nat,)")
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-
-    real = numbers != 0
-    keep = torch.nonzero(real).flatten()
-    order = keep[morton_order(positions[keep])]
-    num_s = numbers[order].to(torch.int64).contiguous()
-    pos_s = positions[order].detach().contiguous()
-    q_s = q[order].detach().to(positions.dtype).contiguous()
-    nat = int(order.numel())
-    out = torch.zeros(numbers.shape[0], dtype=positions.dtype, device=positions.device)
-    if nat == 0:
-        return out
-
-    if compute is None:
-        from . import defaults
-        from .disp import _Engine, _flatten_param
-
-        engine = _Engine.get(positions.device, defaults.GA_DEFAULT, defaults.GC_DEFAULT)
-        par = _flatten_param(param, cutoff, 0, defaults.WF_DEFAULT)
-        gs = int(engine.lib.d4b200_large_group_size())
-
-        def compute(n, p, qq, rows, groups, want_cost):
-            with torch.cuda.device(p.device):
-                return _kernel_compute(engine, par, n, p, qq, rows, groups, want_cost)
-    else:
-        gs = group_size or 16
-    ng = (nat + gs - 1) // gs
-
-    if world > 1:
-        # cost model: a centre group with m neighbours evaluates ~m^2/2 pairs x group size
-        _, cost = compute(num_s, pos_s, q_s, (0, 0), (0, 0), True)
-        granges = balanced_ranges(cost.to(torch.float64) ** 2, world)
-        g0, g1 = granges[rank]
-        # two-body rows follow the same blocks (cost ~ rows)
-        r0, r1 = min(nat, g0 * gs), min(nat, g1 * gs)
-        if rank == world - 1:
-            r1 = nat
-    else:
-        g0, g1, r0, r1 = 0, ng, 0, nat
-    e_s, _ = compute(num_s, pos_s, q_s, (r0, r1), (g0, g1), False)
-    if world > 1:
-        dist.all_reduce(e_s, op=dist.ReduceOp.SUM, group=group)
-    out[order] = e_s
-    return out
+    if compute is not None:
+        be = dict(energy=compute, group_size=group_size or 16)
+        return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group, backend=be)
+    return _LargeFunction.apply(positions, q, numbers, param, cutoff, group)
