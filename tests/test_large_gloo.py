@@ -36,6 +36,84 @@ def _oracle_compute(orc):
     return compute
 
 
+def _oracle_backend(orc):
+    """Oracle stand-in for the kernel backend of tad_dftd4_b200.large (energy, the two
+    gradient stages) with the same partial-sum semantics."""
+
+    def partial(n, p, q, g, rows, groups, cn=None):
+        nat = n.shape[0]
+        centres = torch.zeros(nat, dtype=torch.bool)
+        centres[groups[0] * GS : min(nat, groups[1] * GS)] = True
+        e2, e3, *_ = orc.dftd4(n, p, PARAM, q, parts=True, centres=centres, cn=cn)
+        rowmask = torch.zeros(nat, dtype=torch.bool)
+        rowmask[rows[0] : rows[1]] = True
+        e = torch.where(rowmask, e2, torch.zeros_like(e2)) + e3
+        return e if g is None else (e * g)
+
+    def grad1(n, p, q, g, rows, groups):
+        pp = p.clone().requires_grad_(True)
+        qq = q.clone().requires_grad_(True)
+        cn = orc.cn_d4(n, p).requires_grad_(True)  # independent variable: direct terms only
+        gg = torch.ones_like(q) if g is None else g
+        # NB: the two-body rows of the kernels carry -1/2 (g_i + g_j) per ordered pair;
+        # with a row mask on E2 that is reproduced by symmetrising the upstream weights
+        nat = n.shape[0]
+        rowmask = torch.zeros(nat, dtype=q.dtype)
+        rowmask[rows[0] : rows[1]] = 1.0
+        centres = torch.zeros(nat, dtype=torch.bool)
+        centres[groups[0] * GS : min(nat, groups[1] * GS)] = True
+        _, e3, *_ = orc.dftd4(n, pp, PARAM, qq, parts=True, centres=centres, cn=cn)
+        # row-owner form of the pair terms: atom i's row holds 1/2 of every pair (i,j)
+        L = (e3 * gg).sum() + _rowowner_twobody(orc, n, pp, qq, cn, gg, rowmask)
+        f, dcn, dq = torch.autograd.grad(L, (pp, cn, qq), allow_unused=True)
+        return f, dcn, dq
+
+    def grad2(n, p, dcn_total, rows, force):
+        pp = p.clone().requires_grad_(True)
+        (f,) = torch.autograd.grad((orc.cn_d4(n, pp) * dcn_total).sum(), pp)
+        out = force.clone()
+        out[rows[0] : rows[1]] += f[rows[0] : rows[1]]
+        return out
+
+    def energy(n, p, q, rows, groups, want_cost):
+        if want_cost:
+            nat = n.shape[0]
+            ng = (nat + GS - 1) // GS
+            near = (torch.cdist(p, p) <= 40.0).sum(-1).to(torch.float64)
+            return None, torch.stack([near[g * GS : (g + 1) * GS].sum() for g in range(ng)])
+        return partial(n, p, q, None, rows, groups), None
+
+    return dict(energy=energy, grad1=grad1, grad2=grad2, group_size=GS)
+
+
+def _rowowner_twobody(orc, n, pos, q, cn, g, rowmask):
+    """sum over ordered pairs (i in rows, j): -1/4 (g_i + g_j) c6_ij F_ij ... such that the
+    derivative with respect to R_i, cn_i, q_i of the rows equals the full derivative."""
+    # The kernels give, for every row atom i, the COMPLETE derivative of
+    # L2 = sum_{i<j} -1/2 (g_i+g_j) c6 F with respect to R_i, cn_i and q_i.  Emulate it
+    # with a stop-gradient on the partner atom: L_i = sum_j -1/2 (g_i+g_j) c6(i, sg(j)) F(i, sg(j)).
+    t = orc._tables()
+    dtype = pos.dtype
+    r4r2 = t["r4r2"].to(dtype)[n]
+
+    def wfun(cn_, q_):
+        return orc.weight_references_d4(n, cn_, q_)
+
+    rc6 = orc.reference_c6(n, dtype=dtype)
+    w_live, w_stop = wfun(cn, q), wfun(cn.detach(), q.detach())
+    c6 = torch.einsum("ijab,ia,jb->ij", rc6, w_live, w_stop)  # row i live, column j frozen
+    d = (pos.unsqueeze(1) - pos.detach().unsqueeze(0)).norm(dim=-1)
+    nat = n.shape[0]
+    off = ~torch.eye(nat, dtype=torch.bool)
+    d = torch.where(off, d, torch.ones_like(d))
+    qq = 3 * r4r2.unsqueeze(-1) * r4r2.unsqueeze(-2)
+    R0 = PARAM["a1"] * torch.sqrt(qq) + PARAM["a2"]
+    F = 1.0 / (d**6 + R0**6) + PARAM["s8"] * qq / (d**8 + R0**8)
+    F = torch.where(off & (d <= 60.0), F, torch.zeros_like(F))
+    G2 = -0.5 * (g.unsqueeze(-1) + g.unsqueeze(-2))
+    return ((G2 * c6 * F).sum(-1) * rowmask).sum()
+
+
 def _worker(rank, world, port, out_dir):
     for p in (ROOT, ROOT / "oracle"):
         sys.path.insert(0, str(p))
@@ -53,6 +131,17 @@ def _worker(rank, world, port, out_dir):
         e = dftd4_large(numbers, positions, PARAM, qq, compute=_oracle_compute(orc), group_size=GS)
         ref = orc.dftd4(numbers, positions, PARAM, qq)
         assert (e - ref).abs().max() < 1e-15, (e - ref).abs().max()
+
+        # two-stage gradient (direct terms -> all-reduce dL/dcn, dL/dq -> CN chain -> all-reduce)
+        from tad_dftd4_b200.large import dftd4_large_vjp
+
+        g = torch.from_numpy(np.random.default_rng(2).normal(size=numbers.shape[0]))
+        pos = positions.clone().requires_grad_(True)
+        qv = qq.clone().requires_grad_(True)
+        gp_ref, gq_ref = torch.autograd.grad((orc.dftd4(numbers, pos, PARAM, qv) * g).sum(), (pos, qv))
+        gp, gq = dftd4_large_vjp(numbers, positions, PARAM, qq, g, backend=_oracle_backend(orc))
+        assert (gp - gp_ref).abs().max() < 1e-14, (gp - gp_ref).abs().max()
+        assert (gq - gq_ref).abs().max() < 1e-14, (gq - gq_ref).abs().max()
         Path(out_dir, f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
