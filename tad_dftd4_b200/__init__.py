@@ -8,15 +8,17 @@ behind the functional API of ``tad_dftd4``::
 CUDA kernels: ``csrc/`` (C ABI in ``include/d4b200.h``).  No CPU fallback.
 """
 
-from . import batch, cutoff, damping, defaults
+from . import batch, cutoff, damping, defaults, dispersion, large, model, ncoord, parallel
 from .batch import pack
 from .cutoff import Cutoff
 from .damping import Param, RationalDamping, get_params
 from .disp import dftd4, get_properties, last_launch_count, set_checks
+from .model import D4Model, D4SModel
 
 __version__ = "0.1.0"
 
 __all__ = [
     "__version__", "batch", "cutoff", "Cutoff", "damping", "defaults", "dftd4", "get_params",
     "get_properties", "pack", "Param", "RationalDamping", "set_checks", "last_launch_count",
+    "dispersion", "large", "model", "ncoord", "parallel", "D4Model", "D4SModel",
 ]  # fmt: skip

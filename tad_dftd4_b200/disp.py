@@ -342,10 +342,15 @@ def dftd4(
     if rcov is not None or r4r2 is not None or rvdw is not None:
         raise NotImplementedError("custom rcov/r4r2/rvdw are outside the accelerated hot path")
     for name, fn in (("cn_function", cn_function), ("counting_function", counting_function)):
-        if fn is not None and getattr(fn, "__name__", "") not in ("cn_d4", "erf_count", "cn_d4_cuda"):
+        if fn is not None and getattr(fn, "__name__", "") not in ("cn_d4", "erf_count"):
             raise NotImplementedError(f"custom {name} is outside the accelerated hot path")
     if damping_function is not None and type(damping_function).__name__ != "RationalDamping":
         raise NotImplementedError("only RationalDamping is accelerated")
+    if q is not None and numbers.shape != q.shape:
+        raise ValueError(
+            f"Shape of atomic charges ({q.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
     if positions.dtype not in (torch.float64, torch.float32):
         raise NotImplementedError(f"dtype {positions.dtype} is not supported (float64/float32)")
     if positions.device.type != "cuda":

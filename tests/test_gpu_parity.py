@@ -123,3 +123,54 @@ def test_d4s_f32(name):
     tot, rtot = e.sum(-1), ref.sum(-1)
     assert np.all(np.abs(tot - rtot) <= RTOL32 * np.abs(rtot) + 1e-12)
     assert np.abs(g - gref).max() < 5 * RTOL32 * max(np.abs(gref).max(), 1e-3)
+
+
+def test_class_interface_and_term_selection_gpu():
+    """DispD4 == dftd4; single registered terms select two-body / ATM only (reference:
+    test/test_d4/test_class.py, test_twobody.py, test_atm.py)."""
+    d4 = _d4()
+    import d4_oracle as orc
+
+    case = load_golden("organic_33")
+    dev = torch.device("cuda:0")
+    numbers, positions, q = as_torch(case, dev, torch.float64)
+    param = dict(case["param"])
+    e = d4.dftd4(numbers, positions, 0.0, param, q=q)
+    assert torch.equal(d4.dispersion.DispD4().calculate(numbers, positions, 0.0, param, q=q), e)
+    n, p, qq = as_torch(case)
+    e2, e3, *_ = orc.dftd4(n, p, param, qq, parts=True)
+    two = d4.dispersion.Disp()
+    two.register(d4.dispersion.TwoBodyTerm())
+    assert (two.calculate(numbers, positions, 0.0, param, q=q).cpu() - e2).abs().max() < 1e-12 * e2.abs().max()
+    atm = d4.dispersion.Disp()
+    atm.register(d4.dispersion.D4ATMApprox())
+    assert (atm.calculate(numbers, positions, 0.0, param).cpu() - e3).abs().max() < 1e-10 * e3.abs().max()
+    cn = d4.ncoord.cn_d4(numbers, positions)
+    assert np.allclose(cn.cpu().numpy(), case["cn"], rtol=1e-12)
+
+
+def test_device_status_reports_bad_atomic_number():
+    d4 = _d4()
+    dev = torch.device("cuda:0")
+    numbers = torch.tensor([[6, 1, 120]], device=dev)
+    positions = torch.tensor([[[0.0, 0, 0], [0, 0, 2.0], [0, 3.0, 0]]], dtype=torch.float64, device=dev)
+    with pytest.raises(ValueError, match="atomic number"):
+        d4.dftd4(numbers, positions, 0.0, {"a1": 0.4, "a2": 5.0}, q=torch.zeros(1, 3, dtype=torch.float64, device=dev))
+
+
+def test_idempotent_and_permutation_invariant():
+    """Size-independent properties: same result on repeated calls; permuting the structures
+    of a batch permutes the energies; permuting atoms permutes atomic energies (<=1e-13)."""
+    d4 = _d4()
+    case = load_golden("ragged_batch")
+    dev = torch.device("cuda:0")
+    numbers, positions, q = as_torch(case, dev, torch.float64)
+    param = dict(case["param"])
+    e1 = d4.dftd4(numbers, positions, 0.0, param, q=q)
+    e2 = d4.dftd4(numbers, positions, 0.0, param, q=q)
+    assert torch.equal(e1, e2)
+    perm = torch.randperm(numbers.shape[0], device=dev)
+    assert torch.equal(d4.dftd4(numbers[perm], positions[perm], 0.0, param, q=q[perm]), e1[perm])
+    ap = torch.randperm(numbers.shape[1], device=dev)
+    e3 = d4.dftd4(numbers[:, ap], positions[:, ap], 0.0, param, q=q[:, ap])
+    assert (e3 - e1[:, ap]).abs().max() < 1e-13 * e1.abs().max()
