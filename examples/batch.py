@@ -1,7 +1,11 @@
 # Padded batch of molecules (mirrors the reference's examples/batch.py): numbers == 0 is padding.
+import sys
+from pathlib import Path
+
 import torch
 
-import tad_dftd4_b200 as d4
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import tad_dftd4_b200 as d4  # noqa: E402
 
 dev = torch.device("cuda:0")
 numbers = d4.pack(

@@ -1,7 +1,11 @@
 # D4S model: element-pair specific Gaussian weighting (mirrors the reference's examples/d4s.py).
+import sys
+from pathlib import Path
+
 import torch
 
-import tad_dftd4_b200 as d4
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import tad_dftd4_b200 as d4  # noqa: E402
 
 dev = torch.device("cuda:0")
 numbers = torch.tensor([14, 1, 1, 1, 1], device=dev)  # SiH4

@@ -1,8 +1,12 @@
 # Energy of one molecule through the drop-in API (mirrors the reference's examples/single.py,
 # with explicit charges: EEQ charges are outside the accelerated hot path).
+import sys
+from pathlib import Path
+
 import torch
 
-import tad_dftd4_b200 as d4
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import tad_dftd4_b200 as d4  # noqa: E402
 
 dev = torch.device("cuda:0")
 numbers = torch.tensor([6, 6, 6, 6, 7, 6, 16, 1, 1, 1, 1, 1], device=dev)  # C4NCS H5

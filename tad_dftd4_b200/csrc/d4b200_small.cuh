@@ -734,11 +734,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         __syncwarp();
         const int nchunks = (np + 31) >> 5;
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-        while (true) {
-          int chunk = 0;
-          if (lane == 0) chunk = atomicAdd(&misc[4], 1);
-          chunk = __shfl_sync(0xffffffffu, chunk, 0);
-          if (chunk >= nchunks) break;
+        // static round-robin over the chunks (sorted by decreasing sweep length): the
+        // order of every floating-point sum is fixed, so results are bitwise reproducible
+        for (int chunk = warp; chunk < nchunks; chunk += NW) {
           const int p = chunk * 32 + lane;
           const bool valid = p < np;
           int j = 1 << 20, k = 0;

@@ -170,7 +170,7 @@ def test_idempotent_and_permutation_invariant():
     e2 = d4.dftd4(numbers, positions, 0.0, param, q=q)
     assert torch.equal(e1, e2)
     perm = torch.randperm(numbers.shape[0], device=dev)
-    assert torch.equal(d4.dftd4(numbers[perm], positions[perm], 0.0, param, q=q[perm]), e1[perm])
+    assert torch.equal(d4.dftd4(numbers[perm], positions[perm], 0.0, param, q=q[perm]), e1[perm])  # bitwise
     ap = torch.randperm(numbers.shape[1], device=dev)
     e3 = d4.dftd4(numbers[:, ap], positions[:, ap], 0.0, param, q=q[:, ap])
     assert (e3 - e1[:, ap]).abs().max() < 1e-13 * e1.abs().max()
