@@ -299,15 +299,9 @@ def run_b200(args, wl, rank, world, local_rank):
     engine = _Engine.get(dev, 3.0, 2.0)
     lib = _lib.load()
     step_resident()  # builds tables / workspace
-    launches_per_step = d4.last_launch_count()
-    if wl["grad"]:
-        # forward + backward: count both calls
-        d4.dftd4(numbers, positions, 0.0, PBE0, q=q)
-        launches_per_step = d4.last_launch_count()
-        pos = positions.detach().requires_grad_(True)
-        e = d4.dftd4(numbers, pos, 0.0, PBE0, q=q)
-        torch.autograd.grad(e.sum(), pos)
-        launches_per_step += d4.last_launch_count()
+    n0 = int(lib.d4b200_total_launch_count())
+    step_resident()
+    launches_per_step = int(lib.d4b200_total_launch_count()) - n0
 
     with ClockSampler(local_rank) as clocks:
         total_ms, _ = timed(step_resident, args.steps, args.warmup)

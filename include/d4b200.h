@@ -122,6 +122,20 @@ int d4b200_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nb
                         float* grad_positions_dev, float* grad_q_dev, void* workspace_dev,
                         size_t workspace_bytes, void* stream);
 
+/* Fused call: atom-resolved energies AND the vector-Jacobian product for the upstream
+ * weights ``grad_energy_dev`` (NULL = ones, i.e. the forces of sum E) in one launch per
+ * size class -- what `E = dftd4(...); torch.autograd.grad(E.sum(), positions)` needs. */
+int d4b200_energy_gradient_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch,
+                               int nat, const int64_t* numbers_dev, const double* positions_dev,
+                               const double* q_dev, const double* grad_energy_dev,
+                               double* energy_dev, double* grad_positions_dev, double* grad_q_dev,
+                               void* workspace_dev, size_t workspace_bytes, void* stream);
+int d4b200_energy_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch,
+                               int nat, const int64_t* numbers_dev, const float* positions_dev,
+                               const float* q_dev, const float* grad_energy_dev, float* energy_dev,
+                               float* grad_positions_dev, float* grad_q_dev, void* workspace_dev,
+                               size_t workspace_bytes, void* stream);
+
 /* Model properties, == tad_dftd4.get_properties (src/tad_dftd4/disp.py:149-197) with
  * explicit charges: coordination numbers [nbatch, nat], pair C6 [nbatch, nat, nat]
  * (D4Model.get_atomic_c6 with the q-dependent weights) and static polarizabilities
@@ -200,6 +214,8 @@ int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);
 /* Number of kernel launches the last energy/gradient call on this thread
  * issued (for bench.py's gpu_launches claim). */
 int d4b200_last_launch_count(void);
+/* Cumulative number of launches of all batched energy/gradient calls of this process. */
+long long d4b200_total_launch_count(void);
 
 /* --- measurement hooks used by bench.py (no effect on results) ----------- */
 /* Record CUDA events around every hot-kernel launch of the following calls. */

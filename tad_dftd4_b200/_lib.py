@@ -38,6 +38,8 @@ _SIGS = {
     "d4b200_energy_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_energy_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_energy_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_properties_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_properties_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_large_group_size": (C.c_int, []),
@@ -50,6 +52,7 @@ _SIGS = {
     "d4b200_large_cn_chain_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "d4b200_status": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
     "d4b200_last_launch_count": (C.c_int, []),
+    "d4b200_total_launch_count": (C.c_longlong, []),
     "d4b200_profile_enable": (C.c_int, [_VP, C.c_int]),
     "d4b200_profile_read": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "d4b200_class_caps": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int)]),

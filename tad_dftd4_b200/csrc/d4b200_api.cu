@@ -14,6 +14,7 @@
 
 
 static thread_local int g_launches = 0;
+static long long g_total_launches = 0;  // cumulative, all calls of this process
 
 namespace {
 
@@ -147,7 +148,7 @@ Work carve_work(void* ws, int nbatch) {
 constexpr int MAX_SMS = 160;
 
 size_t scratch_bytes_class(int c, int cap, size_t elem) {
-  return align_up((size_t)MAX_SMS * class_occ_cap(c) * 2 * (cap * (cap - 1) / 2) * elem, 256);
+  return align_up((size_t)MAX_SMS * class_occ_cap(c) * 5 * (cap * (cap - 1) / 2) * elem, 256);
 }
 
 template <typename T>
@@ -259,6 +260,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
     scratch += sbytes;
   }
   if (h->profile) cudaEventRecord(h->ev_call[2], st);
+  g_total_launches += g_launches;
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -408,6 +410,22 @@ int d4b200_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch,
   return run_small<float, true>(t, par, nbatch, nat, numbers, pos, q, gin, nullptr, nullptr, grad,
                                 gradq, ws, ws_bytes, (cudaStream_t)stream);
 }
+int d4b200_energy_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                               const int64_t* numbers, const double* pos, const double* q,
+                               const double* gin, double* energy, double* grad, double* gradq,
+                               void* ws, size_t ws_bytes, void* stream) {
+  if (!energy) return D4B200_EINVAL;
+  return run_small<double, true>(t, par, nbatch, nat, numbers, pos, q, gin, energy, nullptr, grad,
+                                 gradq, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_energy_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                               const int64_t* numbers, const float* pos, const float* q,
+                               const float* gin, float* energy, float* grad, float* gradq, void* ws,
+                               size_t ws_bytes, void* stream) {
+  if (!energy) return D4B200_EINVAL;
+  return run_small<float, true>(t, par, nbatch, nat, numbers, pos, q, gin, energy, nullptr, grad,
+                                gradq, ws, ws_bytes, (cudaStream_t)stream);
+}
 
 int d4b200_properties_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                           const int64_t* numbers, const double* pos, const double* q, double* cn,
@@ -434,6 +452,7 @@ int d4b200_status(void* ws, void* stream, int* bits) {
 }
 
 int d4b200_last_launch_count(void) { return g_launches; }
+long long d4b200_total_launch_count(void) { return g_total_launches; }
 
 // development profiling: per-phase cycle counters of the small-family kernels
 int d4b200_phase_profile(d4b200_tables_t h, int enable, unsigned long long* out /*[NCLASS*16] or NULL*/) {

@@ -98,7 +98,7 @@ struct Lay {
   static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
   static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
   static constexpr size_t total = ints + al16((2 * CAP + 8) * sizeof(int));
-  static constexpr int scratch_planes = 2;
+  static constexpr int scratch_planes = GRAD ? 5 : 2;  // gradient: Gamma, D, E3 shares (2), E2
 };
 
 // Unnormalised Gaussian weights S_a (and dS_a/dcn) of one atom for a given weighting
@@ -200,17 +200,20 @@ __device__ __forceinline__ T row_sum2(const T* __restrict__ lo, const T* __restr
 template <typename T, bool OPEN>
 __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T cjk,
                                            T Pjk, T ujk, T inv_b, T alp3, T gi, T gj, T gk,
-                                           T& accG, T& accD) {
+                                           T& accG, T& accD, T& accH, T& accL) {
   T a = a_s, c = c_s;
   T W = gi + gj + gk;
+  T mj = T(2), mk = T(2);  // closed triple: multiplicity 2 for every atom
   if (OPEN) {
     const T cij = a_s > T(0) ? T(1) : T(0);
     const T cik = c_s > T(0) ? T(1) : T(0);
     a = fabs(a_s);
     c = fabs(c_s);
-    W = gi * (cjk * (cij + cik)) + gj * (cik * (cij + cjk)) + gk * (cij * (cik + cjk));
+    mj = cik * (cij + cjk);
+    mk = cij * (cik + cjk);
+    W = gi * (cjk * (cij + cik)) + gj * mj + gk * mk;
   } else {
-    W = W + W;  // closed triple: multiplicity 2 for every atom
+    W = W + W;
   }
   const T X = a + b - c, Y = a - b + c, Z = b + c - a;
   const T s = X * Y * Z;
@@ -227,6 +230,8 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   const T de = common * inv_b + T(0.375) * psf * Q * dsdb;
   accG += W * e;
   accD += W * de;
+  accH += mj * e;  // energy shares of the owner pair's atoms (fused energy + gradient call)
+  accL += mk * e;
 }
 
 // One block of 8 consecutive top atoms i0..i0+7 for the lane's bottom pair (j,k).
@@ -382,6 +387,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           if (A.cn_out) A.cn_out[o] = T(0);
           if (A.alpha_out) A.alpha_out[o] = T(0);
         } else {
+          if (A.energy) A.energy[o] = T(0);
           if (A.grad) {
             A.grad[3 * o] = T(0);
             A.grad[3 * o + 1] = T(0);
@@ -700,7 +706,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const T inv_b = d4_rcp(bb);
           const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
           const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
-          T accG = T(0), accD = T(0);
+          T accG = T(0), accD = T(0), accH = T(0), accL = T(0);
           for (int i = 0; i < n; ++i) {
             if (i == j || i == k) continue;
             const int ti = i * (i - 1) / 2;
@@ -708,13 +714,17 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             const int pik = i > k ? ti + k : tk + i;
             if (open)
               grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
-                                  Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD);
+                                  Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD, accH, accL);
             else
               grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
-                                   Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD);
+                                   Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD, accH, accL);
           }
           out0[p] = accG;
           out1[p] = accD;
+          if (A.energy) {
+            out0[2 * CP + p] = accH;
+            out0[3 * CP + p] = accL;
+          }
         }
         __syncthreads();  // all reads of the stash done -> planes become outputs
         for (int p = tid; p < np; p += NT) {  // same thread wrote out0/out1[p]
@@ -863,7 +873,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             dq_qj += WT(WT_ZGD)[j * NREF + bq] * gj[bq] * sq[bq];
           }
           const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
-          T coefq = T(0), fc = T(2) * pu[p];
+          T coefq = T(0), fc = T(2) * pu[p], e2 = T(0);
           if (r2 <= P.disp2_sq) {
             const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
             const T R0 = P.a1 * ss + P.a2;
@@ -880,7 +890,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             }
             coefq = G2 * F;
             fc += G2 * c6q * dF;
+            e2 = c6q * F;
           }
+          if (A.energy) out0[4 * CP + p] = e2;
           const T gam = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
           pa[p] = coefq * dq_cni + gam * d0_cni;
           pP[p] = coefq * dq_cnj + gam * d0_cnj;
@@ -910,7 +922,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const T r2 = dx * dx + dy * dy + dz * dz;
         const T c6q = dot23<T, CAP>(Aq, i, j), c60 = dot23<T, CAP>(A0, i, j);
         const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
-        T coefq = T(0), fc = T(2) * pu[p];
+        T coefq = T(0), fc = T(2) * pu[p], e2 = T(0);
         if (r2 <= P.disp2_sq) {
           const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
           const T R0 = P.a1 * ss + P.a2;
@@ -928,7 +940,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           }
           coefq = G2 * F;
           fc += G2 * c6q * dF;
+          e2 = c6q * F;
         }
+        if (A.energy) out0[4 * CP + p] = e2;
         pa[p] = coefq;
         pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
         pu[p] = fc;
@@ -1028,6 +1042,13 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             A.grad[3 * o + 2] = fz;
           }
           if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
+        }
+      }
+      if (A.energy) {  // fused energy + gradient call: assemble the atomic energies as well
+        for (int i = tid; i < n; i += NT) {
+          T e = T(-0.5) * row_sum2(out0 + 4 * CP, out0 + 4 * CP, i, n);
+          if (P.has_atm) e += T(0.5) * row_sum2(out0 + 2 * CP, out0 + 3 * CP, i, n);
+          A.energy[(size_t)b * A.nat + idx[i]] = e;
         }
       }
       __syncthreads();

@@ -27,7 +27,7 @@ from .cutoff import Cutoff
 from .damping import Param, RationalDamping
 from .tables import build_tables
 
-__all__ = ["dftd4", "get_properties", "set_checks", "last_launch_count"]
+__all__ = ["dftd4", "get_properties", "set_checks", "set_fused_forward", "last_launch_count"]
 
 Tensor = torch.Tensor
 
@@ -145,23 +145,42 @@ class _Engine:
         return cn, c6, alpha
 
     def gradient(self, par: _lib.Params, numbers: Tensor, positions: Tensor, q: Tensor,
-                 gout: Tensor | None, want_pos: bool, want_q: bool):  # fmt: skip
+                 gout: Tensor | None, want_pos: bool, want_q: bool, with_energy: bool = False):  # fmt: skip
+        """VJP of the energy; ``with_energy`` additionally returns the energies from the
+        same launch (fused energy + gradient call)."""
         nbatch, nat = numbers.shape
         gpos = torch.empty_like(positions) if want_pos else None
         gq = torch.empty_like(q) if want_q else None
+        energy = torch.empty_like(q) if with_energy else None
         ws = self.workspace(nbatch, nat)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        fn = self.lib.d4b200_gradient_f64 if positions.dtype == torch.float64 else self.lib.d4b200_gradient_f32
-        _lib.check(
-            fn(self.handle, C.byref(par), nbatch, nat, numbers.data_ptr(), positions.data_ptr(),
-               q.data_ptr(), gout.data_ptr() if gout is not None else None,
-               gpos.data_ptr() if gpos is not None else None,
-               gq.data_ptr() if gq is not None else None, ws.data_ptr(), ws.numel(), stream),
-            "d4b200_gradient",
-        )  # fmt: skip
+        f64 = positions.dtype == torch.float64
+        common = (self.handle, C.byref(par), nbatch, nat, numbers.data_ptr(), positions.data_ptr(),
+                  q.data_ptr(), gout.data_ptr() if gout is not None else None)  # fmt: skip
+        tail = (gpos.data_ptr() if gpos is not None else None, gq.data_ptr() if gq is not None else None,
+                ws.data_ptr(), ws.numel(), stream)  # fmt: skip
+        if with_energy:
+            fn = self.lib.d4b200_energy_gradient_f64 if f64 else self.lib.d4b200_energy_gradient_f32
+            _lib.check(fn(*common, energy.data_ptr(), *tail), "d4b200_energy_gradient")
+        else:
+            fn = self.lib.d4b200_gradient_f64 if f64 else self.lib.d4b200_gradient_f32
+            _lib.check(fn(*common, *tail), "d4b200_gradient")
         if _CHECKS:
             self._status(ws, stream)
-        return gpos, gq
+        return (gpos, gq, energy) if with_energy else (gpos, gq)
+
+
+_FUSED_FORWARD = True
+
+
+def set_fused_forward(enabled: bool) -> None:
+    """When inputs require grad, evaluate energies AND the gradient of ``sum(E)`` in the
+    forward launch (default).  ``backward`` then only scales the cached gradient if the
+    upstream gradient is a broadcast scalar (``E.sum().backward()``,
+    ``autograd.grad(E.sum(), positions)``); any other upstream gradient runs the general
+    VJP kernel.  Disable to make the forward pass energy-only."""
+    global _FUSED_FORWARD
+    _FUSED_FORWARD = bool(enabled)
 
 
 class _D4Function(torch.autograd.Function):
@@ -169,7 +188,14 @@ class _D4Function(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, positions: Tensor, q: Tensor, numbers: Tensor, par, engine: _Engine):
-        energy, _ = engine.energy(par, numbers, positions, q)
+        need_pos, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ctx.cached = None
+        if _FUSED_FORWARD and (need_pos or need_q):
+            gpos, gq, energy = engine.gradient(par, numbers, positions, q, None, need_pos, need_q,
+                                               with_energy=True)  # fmt: skip
+            ctx.cached = (gpos, gq)
+        else:
+            energy, _ = engine.energy(par, numbers, positions, q)
         ctx.save_for_backward(positions, q, numbers)
         ctx.par = par
         ctx.engine = engine
@@ -180,6 +206,11 @@ class _D4Function(torch.autograd.Function):
     def backward(ctx, gout: Tensor):
         positions, q, numbers = ctx.saved_tensors
         need_pos, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.cached is not None and all(s == 0 for s in gout.stride()):
+            # upstream gradient is one broadcast scalar c: dL/dx = c * d(sum E)/dx (no sync)
+            c = gout.reshape(-1)[0]
+            gpos, gq = ctx.cached
+            return (gpos * c if need_pos else None), (gq * c if need_q else None), None, None, None
         gpos, gq = ctx.engine.gradient(
             ctx.par, numbers, positions, q, gout.contiguous(), need_pos, need_q
         )

@@ -174,3 +174,38 @@ def test_idempotent_and_permutation_invariant():
     ap = torch.randperm(numbers.shape[1], device=dev)
     e3 = d4.dftd4(numbers[:, ap], positions[:, ap], 0.0, param, q=q[:, ap])
     assert (e3 - e1[:, ap]).abs().max() < 1e-13 * e1.abs().max()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("model", ["d4", "d4s"])
+def test_weighted_upstream_and_charge_gradient(fused, model):
+    """General VJP: arbitrary upstream weights g_i and dL/dq vs oracle autograd, with the
+    fused forward (cached sum-gradient unused because g is not a broadcast scalar) and
+    with the energy-only forward."""
+    d4 = _d4()
+    import d4_oracle as orc
+
+    d4.set_fused_forward(fused)
+    try:
+        case = load_golden("ragged_batch")
+        n, p, q = as_torch(case)
+        g = torch.from_numpy(np.random.default_rng(4).normal(size=tuple(n.shape)))
+        pos = p.clone().requires_grad_(True)
+        qq = q.clone().requires_grad_(True)
+        e_ref = orc.dftd4(n, pos, case["param"], qq, model=model)
+        gp_ref, gq_ref = torch.autograd.grad((e_ref * g).sum(), (pos, qq))
+        dev = torch.device("cuda:0")
+        pd, qd = p.to(dev).requires_grad_(True), q.to(dev).requires_grad_(True)
+        e = d4.dftd4(n.to(dev), pd, 0.0, dict(case["param"]), q=qd, model=model)
+        gp, gq = torch.autograd.grad((e * g.to(dev)).sum(), (pd, qd))
+        assert (e.detach().cpu() - e_ref.detach()).abs().max() / e_ref.detach().abs().max() < E_RTOL64
+        assert (gp.cpu() - gp_ref).abs().max() < G_ATOL64
+        assert (gq.cpu() - gq_ref).abs().max() < G_ATOL64
+        # scaled sum: broadcast upstream gradient -> cached gradient times the scalar
+        pd2 = p.to(dev).requires_grad_(True)
+        e2 = d4.dftd4(n.to(dev), pd2, 0.0, dict(case["param"]), q=q.to(dev), model=model)
+        (g2,) = torch.autograd.grad(2.5 * e2.sum(), pd2)
+        (g2_ref,) = torch.autograd.grad(2.5 * orc.dftd4(n, pos, case["param"], q, model=model).sum(), pos)
+        assert (g2.cpu() - g2_ref).abs().max() < G_ATOL64
+    finally:
+        d4.set_fused_forward(True)
