@@ -119,6 +119,16 @@ def work_counts(numbers: torch.Tensor, grad: bool):
     return n, pairs, triples, flop
 
 
+def measured_traffic(workload: str, dtype: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full
+    capture of the same command (profiles/traffic.json), or None."""
+    try:
+        with open(ROOT / "profiles" / "traffic.json", encoding="utf8") as fp:
+            return json.load(fp).get(f"{workload}_{dtype}", {}).get("dram_bytes_per_launch")
+    except OSError:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -306,6 +316,12 @@ def run_b200(args, wl, rank, world, local_rank):
     with ClockSampler(local_rank) as clocks:
         total_ms, _ = timed(step_resident, args.steps, args.warmup)
         e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+        # keep the same load running (untimed) until nvidia-smi has had time to sample it
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step_resident()
+            torch.cuda.synchronize(dev)
     clk = clocks.summary()
 
     # ---- dominant kernel: per-launch duration measured live with CUDA events
@@ -385,7 +401,7 @@ def run_b200(args, wl, rank, world, local_rank):
                 "kernel": f"small_kernel<{'double' if dtype == torch.float64 else 'float'},"
                           f"{'grad' if wl['grad'] else 'energy'}> size class <= {caps[dom]} atoms",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.workload, args.dtype),
                 "peak_source": "measured in this run: DFMA chain microbenchmark (d4b200_measure_fp64_peak); "
                                f"nominal {nominal_tf} TFLOP/s; MEASURED_PEAKS.json has no FP64 entry",
                 "kernel_ms": class_ms[dom], "kernel_algorithmic_flop": class_flop[dom],
