@@ -106,6 +106,17 @@ int d4b200_energy_f32(d4b200_tables_t tables, const d4b200_params* par, int nbat
                       float* energy_dev, float* cn_dev, void* workspace_dev,
                       size_t workspace_bytes, void* stream);
 
+/* Host-buffer variant (the end-to-end call of bench.py): inputs and the result live in
+ * HOST memory (pinned for full overlap).  The batch flows in ``chunks`` pieces (0 = auto)
+ * through two internal pipeline slots, H2D copy -> kernels -> D2H copy, so the copies of
+ * one chunk overlap the kernels of the other.  Synchronous. */
+int d4b200_energy_host_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                           const int64_t* numbers_host, const double* positions_host,
+                           const double* q_host, double* energy_host, int chunks);
+int d4b200_energy_host_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                           const int64_t* numbers_host, const float* positions_host,
+                           const float* q_host, float* energy_host, int chunks);
+
 /* Vector-Jacobian product of the energy: for upstream weights
  * g = dL/dE [nbatch, nat] (NULL = all ones, i.e. L = sum E) returns
  * dL/dpositions [nbatch, nat, 3] and dL/dq [nbatch, nat] (either may be

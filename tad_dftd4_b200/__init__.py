@@ -12,13 +12,13 @@ from . import batch, cutoff, damping, defaults, dispersion, large, model, ncoord
 from .batch import pack
 from .cutoff import Cutoff
 from .damping import Param, RationalDamping, get_params
-from .disp import dftd4, get_properties, last_launch_count, set_checks, set_fused_forward
+from .disp import dftd4, dftd4_host, get_properties, last_launch_count, set_checks, set_fused_forward
 from .model import D4Model, D4SModel
 
 __version__ = "0.1.0"
 
 __all__ = [
-    "__version__", "batch", "cutoff", "Cutoff", "damping", "defaults", "dftd4", "get_params",
+    "__version__", "batch", "cutoff", "Cutoff", "damping", "defaults", "dftd4", "dftd4_host", "get_params",
     "get_properties", "pack", "Param", "RationalDamping", "set_checks", "set_fused_forward", "last_launch_count",
     "dispersion", "large", "model", "ncoord", "parallel", "D4Model", "D4SModel",
 ]  # fmt: skip

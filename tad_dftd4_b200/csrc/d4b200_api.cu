@@ -181,7 +181,7 @@ template <typename T, bool GRAD>
 int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
               const int64_t* numbers, const T* pos, const T* q, const T* gin, T* energy, T* cn_out,
               T* grad, T* gradq, void* ws, size_t ws_bytes, cudaStream_t st, T* c6_out = nullptr,
-              T* alpha_out = nullptr) {
+              T* alpha_out = nullptr, int pool = 0) {
   constexpr int dt = sizeof(T) == 8 ? 0 : 1;
   constexpr int gr = GRAD ? 1 : 0;
   g_launches = 0;
@@ -229,7 +229,7 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   unsigned char* scratch = reinterpret_cast<unsigned char*>(ws) + int_region_bytes(nbatch);
   // fork: every populated class runs on its own stream, ordered after the prep kernels
   if (h->profile) cudaEventRecord(h->ev_call[1], st);
-  cudaEventRecord(h->ev_fork, st);
+  cudaEventRecord(h->ev_fork[pool], st);
   int prev = 0;
   for (int c = 0; c < NCLASS; ++c) {
     const int cap = caps.v[c];
@@ -245,15 +245,15 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
       if (grid > nbatch) grid = nbatch;
       const long gmax = (long)(h->num_sms < MAX_SMS ? h->num_sms : MAX_SMS) * class_occ_cap(c);
       if (grid > gmax) grid = gmax;
-      cudaStream_t cs = h->profile ? st : h->cstream[c];  // profiling: serialise on the caller's stream
-      if (!h->profile) cudaStreamWaitEvent(cs, h->ev_fork, 0);
+      cudaStream_t cs = h->profile ? st : h->cstream[pool][c];  // profiling: serialise on the caller's stream
+      if (!h->profile) cudaStreamWaitEvent(cs, h->ev_fork[pool], 0);
       if (h->profile) cudaEventRecord(h->ev[2 * c], st);
       flavour_launch<T>(GRAD, par->model, c, (unsigned)grid, cs, A);
       if (h->profile) cudaEventRecord(h->ev[2 * c + 1], st);
       h->ev_used[c] = h->profile;
       if (!h->profile) {
-        cudaEventRecord(h->ev_join[c], cs);
-        cudaStreamWaitEvent(st, h->ev_join[c], 0);
+        cudaEventRecord(h->ev_join[pool][c], cs);
+        cudaStreamWaitEvent(st, h->ev_join[pool][c], 0);
       }
       ++g_launches;
     }
@@ -266,6 +266,80 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
 }
 
 }  // namespace
+
+// Host-buffer variant of the energy call: the batch is cut into chunks that flow through
+// D4_HOST_SLOTS pipeline slots (H2D copy -> kernels -> D2H copy), so the copies of one chunk
+// overlap the kernels of the others.  Pinned host memory is needed for the overlap (pageable
+// memory still works, serialised by the driver).  Synchronous: returns when
+// ``energy_host`` is complete.
+template <typename T>
+static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
+                           const int64_t* numbers, const T* pos, const T* q, T* energy, int chunks) {
+  if (!h || !par || !numbers || !pos || !q || !energy || nbatch < 0 || nat < 0) return D4B200_EINVAL;
+  if (nbatch == 0 || nat == 0) return 0;
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  cudaSetDevice(h->device);
+  if (chunks <= 0) chunks = nbatch >= 2048 ? 4 : nbatch >= 512 ? 2 : 1;
+  if (chunks > nbatch) chunks = nbatch;
+  const int cb = (nbatch + chunks - 1) / chunks;  // structures per chunk
+  const size_t rows = (size_t)cb * nat;
+  const size_t off_pos = align_up(rows * sizeof(int64_t), 256);
+  const size_t off_q = off_pos + align_up(rows * 3 * sizeof(T), 256);
+  const size_t off_e = off_q + align_up(rows * sizeof(T), 256);
+  const size_t off_ws = off_e + align_up(rows * sizeof(T), 256);
+  const size_t ws_bytes = d4b200_workspace_bytes(cb, nat);
+  const size_t need = off_ws + ws_bytes;
+  cudaError_t e = cudaSuccess;
+  if (!h->hcopy) e = cudaStreamCreateWithFlags(&h->hcopy, cudaStreamNonBlocking);
+  for (int s = 0; s < D4_HOST_SLOTS && s < chunks && e == cudaSuccess; ++s) {
+    if (!h->hstream[s]) {
+      e = cudaStreamCreateWithFlags(&h->hstream[s], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->hev_in[s], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->hev_done[s], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess && h->hbuf_bytes[s] < need) {
+      if (h->hbuf[s]) cudaFree(h->hbuf[s]);
+      h->hbuf[s] = nullptr;
+      h->hbuf_bytes[s] = 0;
+      e = cudaMalloc(&h->hbuf[s], need);
+      if (e == cudaSuccess) h->hbuf_bytes[s] = need;
+    }
+  }
+  int rc = 0;
+  long long launches = 0;
+  for (int c = 0; c < chunks && e == cudaSuccess && rc == 0; ++c) {
+    const int b0 = c * cb, nb = (b0 + cb <= nbatch ? cb : nbatch - b0);
+    if (nb <= 0) break;
+    const int s = c % D4_HOST_SLOTS;
+    unsigned char* d = reinterpret_cast<unsigned char*>(h->hbuf[s]);
+    cudaStream_t st = h->hstream[s];
+    const size_t r = (size_t)nb * nat, o = (size_t)b0 * nat;
+    // all uploads share one stream so that they reach the device in chunk order at full
+    // link bandwidth; the slot's stream picks up when its chunk has landed
+    if (c >= D4_HOST_SLOTS) cudaStreamWaitEvent(h->hcopy, h->hev_done[s], 0);
+    cudaMemcpyAsync(d, numbers + o, r * sizeof(int64_t), cudaMemcpyHostToDevice, h->hcopy);
+    cudaMemcpyAsync(d + off_pos, pos + 3 * o, r * 3 * sizeof(T), cudaMemcpyHostToDevice, h->hcopy);
+    cudaMemcpyAsync(d + off_q, q + o, r * sizeof(T), cudaMemcpyHostToDevice, h->hcopy);
+    cudaEventRecord(h->hev_in[s], h->hcopy);
+    cudaStreamWaitEvent(st, h->hev_in[s], 0);
+    rc = run_small<T, false>(h, par, nb, nat, reinterpret_cast<const int64_t*>(d),
+                             reinterpret_cast<const T*>(d + off_pos), reinterpret_cast<const T*>(d + off_q),
+                             nullptr, reinterpret_cast<T*>(d + off_e), nullptr, nullptr, nullptr,
+                             d + off_ws, ws_bytes, st, nullptr, nullptr, 1 + s);
+    launches += g_launches;
+    e = cudaMemcpyAsync(energy + o, d + off_e, r * sizeof(T), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(h->hev_done[s], st);
+  }
+  for (int s = 0; s < D4_HOST_SLOTS; ++s)
+    if (h->hstream[s]) {
+      cudaError_t es = cudaStreamSynchronize(h->hstream[s]);
+      if (e == cudaSuccess) e = es;
+    }
+  g_launches = (int)launches;
+  cudaSetDevice(prev_dev);
+  return rc != 0 ? rc : (e == cudaSuccess ? 0 : (int)e);
+}
 
 // (cn, C6, alpha) of tad_dftd4.get_properties (disp.py:149-197); the energy kernel stops
 // after the weighted-polarizability vectors.  ``energy_scratch_dev`` [nbatch, nat] is zeroed.
@@ -332,12 +406,14 @@ int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
     if ((e = cudaMemcpy(h->i32, i32_blob_host, n_i32 * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) break;
     k_to_float<<<(unsigned)((n_f64 + 255) / 256), 256>>>(h->f64, h->f32, n_f64);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
-    for (int c = 0; c < NCLASS && e == cudaSuccess; ++c) {
-      e = cudaStreamCreateWithFlags(&h->cstream[c], cudaStreamNonBlocking);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming);
+    for (int p = 0; p < 1 + D4_HOST_SLOTS && e == cudaSuccess; ++p) {
+      for (int c = 0; c < NCLASS && e == cudaSuccess; ++c) {
+        e = cudaStreamCreateWithFlags(&h->cstream[p][c], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[p][c], cudaEventDisableTiming);
+      }
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork[p], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) break;
-    if ((e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) break;
     h->t64 = make_tables<double>(h->f64, h->f64, h->i32);
     h->t32 = make_tables<float>(h->f32, h->f64, h->i32);
     for (int model = 0; model < 2 && rc == 0; ++model) {
@@ -363,12 +439,23 @@ int d4b200_tables_destroy(d4b200_tables_t h) {
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 3; ++i)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
-  for (int c = 0; c < NCLASS; ++c) {
-    if (h->cstream[c]) cudaStreamDestroy(h->cstream[c]);
-    if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+  for (int p = 0; p < 1 + D4_HOST_SLOTS; ++p) {
+    for (int c = 0; c < NCLASS; ++c) {
+      if (h->cstream[p][c]) cudaStreamDestroy(h->cstream[p][c]);
+      if (h->ev_join[p][c]) cudaEventDestroy(h->ev_join[p][c]);
+    }
+    if (h->ev_fork[p]) cudaEventDestroy(h->ev_fork[p]);
   }
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   cudaFree(h->phase_dev);
+  if (h->hcopy) cudaStreamDestroy(h->hcopy);
+  for (int s = 0; s < D4_HOST_SLOTS; ++s) {
+    if (h->hbuf[s]) cudaFree(h->hbuf[s]);
+    if (h->hstream[s]) {
+      cudaStreamDestroy(h->hstream[s]);
+      cudaEventDestroy(h->hev_in[s]);
+      cudaEventDestroy(h->hev_done[s]);
+    }
+  }
   cudaFree(h->f64);
   cudaFree(h->f32);
   cudaFree(h->i32);
@@ -396,6 +483,16 @@ int d4b200_energy_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, i
                       float* cn, void* ws, size_t ws_bytes, void* stream) {
   return run_small<float, false>(t, par, nbatch, nat, numbers, pos, q, nullptr, energy, cn, nullptr,
                                  nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_energy_host_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                           const int64_t* numbers_host, const double* pos_host,
+                           const double* q_host, double* energy_host, int chunks) {
+  return run_energy_host<double>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
+}
+int d4b200_energy_host_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                           const int64_t* numbers_host, const float* pos_host, const float* q_host,
+                           float* energy_host, int chunks) {
+  return run_energy_host<float>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
 }
 int d4b200_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                         const int64_t* numbers, const double* pos, const double* q,

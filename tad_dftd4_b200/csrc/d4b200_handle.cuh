@@ -8,6 +8,8 @@
 
 using namespace d4b200;
 
+#define D4_HOST_SLOTS 4
+
 struct d4b200_tables {
   int device;
   int num_sms;
@@ -24,8 +26,9 @@ struct d4b200_tables {
   int grid_per_sm[2][2][2][NCLASS];
   size_t smem[2][2][2][NCLASS];
   // classes are independent: they run concurrently on a small stream pool
-  cudaStream_t cstream[NCLASS];
-  cudaEvent_t ev_fork, ev_join[NCLASS];
+  // class stream pools: pool 0 serves calls on the caller's stream, pool 1+s the host slot s
+  cudaStream_t cstream[1 + D4_HOST_SLOTS][NCLASS];
+  cudaEvent_t ev_fork[1 + D4_HOST_SLOTS], ev_join[1 + D4_HOST_SLOTS][NCLASS];
   // optional per-launch timing (bench.py roofline): events around each class kernel
   int profile;
   cudaEvent_t ev[2 * NCLASS];
@@ -33,6 +36,12 @@ struct d4b200_tables {
   unsigned long long* phase_dev;  // [NCLASS][16] per-phase cycle counters (development)
   int phase_on;
   int ev_used[NCLASS];
+  // host-buffer entry points: D4_HOST_SLOTS pipeline slots (stream, staging buffers, workspace)
+  cudaStream_t hstream[D4_HOST_SLOTS];
+  void* hbuf[D4_HOST_SLOTS];
+  size_t hbuf_bytes[D4_HOST_SLOTS];
+  cudaStream_t hcopy;  // all H2D copies, in chunk order
+  cudaEvent_t hev_in[D4_HOST_SLOTS], hev_done[D4_HOST_SLOTS];
 };
 
 // upper bound of resident CTAs per SM we ever launch for a class

@@ -27,7 +27,7 @@ from .cutoff import Cutoff
 from .damping import Param, RationalDamping
 from .tables import build_tables
 
-__all__ = ["dftd4", "get_properties", "set_checks", "set_fused_forward", "last_launch_count"]
+__all__ = ["dftd4", "dftd4_host", "get_properties", "set_checks", "set_fused_forward", "last_launch_count"]
 
 Tensor = torch.Tensor
 
@@ -434,6 +434,58 @@ def dftd4(
     with torch.cuda.device(positions.device):
         energy = _D4Function.apply(pos2, q2, num2, par, engine)
     return energy.reshape(*batch_shape, nat)
+
+
+def dftd4_host(
+    numbers: Tensor,
+    positions: Tensor,
+    charge: Tensor | float | int,
+    param: Param,
+    *,
+    q: Tensor,
+    model: Any = "d4",
+    cutoff: Cutoff | None = None,
+    device: int | torch.device = 0,
+    chunks: int = 0,
+    out: Tensor | None = None,
+) -> Tensor:
+    """Atom-resolved D4 energy for inputs that live in HOST memory, evaluated on the B200.
+
+    Same arguments as :func:`dftd4` but ``numbers`` / ``positions`` / ``q`` are CPU tensors
+    (pin them for full copy/compute overlap) and the result is a (pinned) CPU tensor.  The
+    batch is pipelined in chunks through the C ABI (``d4b200_energy_host_*``): the
+    host-to-device copy of one chunk overlaps the kernels of the previous one.  Energies
+    only (use :func:`dftd4` with CUDA tensors for gradients)."""
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError(
+            f"Shape of positions ({positions.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
+    if numbers.shape != q.shape:
+        raise ValueError(
+            f"Shape of atomic charges ({q.shape}) is not consistent with atomic numbers ({numbers.shape})."
+        )
+    if positions.device.type != "cpu" or positions.dtype not in (torch.float64, torch.float32):
+        raise ValueError("dftd4_host expects float32/float64 CPU tensors")
+    model_id, ga, gc, wf = _resolve_model(model)
+    par = _flatten_param(param, cutoff, model_id, wf)
+    dev = torch.device("cuda", device) if isinstance(device, int) else device
+    engine = _Engine.get(dev, ga, gc)
+    nat = numbers.shape[-1]
+    if nat > _small_limit(positions.dtype, False, model_id):
+        raise NotImplementedError("dftd4_host handles batches of small structures; use dftd4 for large ones")
+    num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
+    pos2 = positions.reshape(-1, nat, 3).contiguous()
+    q2 = q.to(positions.dtype).reshape(-1, nat).contiguous()
+    if out is None:
+        out = torch.empty(num2.shape, dtype=positions.dtype, pin_memory=True)
+    fn = engine.lib.d4b200_energy_host_f64 if positions.dtype == torch.float64 else engine.lib.d4b200_energy_host_f32
+    _lib.check(
+        fn(engine.handle, C.byref(par), num2.shape[0], nat, num2.data_ptr(), pos2.data_ptr(),
+           q2.data_ptr(), out.data_ptr(), int(chunks)),
+        "d4b200_energy_host",
+    )  # fmt: skip
+    return out.reshape(numbers.shape)
 
 
 def get_properties(

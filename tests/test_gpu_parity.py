@@ -209,3 +209,26 @@ def test_weighted_upstream_and_charge_gradient(fused, model):
         assert (g2.cpu() - g2_ref).abs().max() < G_ATOL64
     finally:
         d4.set_fused_forward(True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("chunks", [0, 1, 3, 7])
+def test_host_buffer_entry_matches_device_entry(dtype, chunks):
+    """d4b200_energy_host_* (chunked H2D / kernels / D2H pipeline) == the device-pointer call,
+    bitwise, for every chunking (structures are independent, chunk assignment is static)."""
+    d4 = _d4()
+    case = load_golden("ragged_batch")
+    numbers, positions, q = as_torch(case, torch.device("cpu"), dtype)
+    rep = 9  # make the batch large enough for several chunks per pipeline slot
+    numbers, positions, q = numbers.repeat(rep, 1), positions.repeat(rep, 1, 1), q.repeat(rep, 1)
+    param = dict(case["param"])
+    e_host = d4.dftd4_host(numbers.pin_memory(), positions.pin_memory(), 0.0, param, q=q.pin_memory(), chunks=chunks)
+    assert e_host.device.type == "cpu" and e_host.shape == numbers.shape
+    e_dev = d4.dftd4(numbers.cuda(), positions.cuda(), 0.0, param, q=q.cuda()).cpu()
+    assert torch.equal(e_host, e_dev)
+    if dtype == torch.float64:
+        ref = np.tile(case["energy_d4"], (rep, 1))
+        assert np.abs(e_host.numpy() - ref).max() / np.abs(ref).max() < E_RTOL64
+    # pageable host memory works too (the driver stages it)
+    e_page = d4.dftd4_host(numbers, positions, 0.0, param, q=q, chunks=2)
+    assert torch.equal(e_page, e_dev)
