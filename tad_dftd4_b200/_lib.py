@@ -7,9 +7,11 @@ is not a B200 the import / first call fails loudly.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libd4b200.so"
+# D4B200_LIBRARY points at an alternative build of the same C ABI (A/B timing of kernel variants)
+LIB_PATH = Path(os.environ.get("D4B200_LIBRARY") or Path(__file__).resolve().parent / "libd4b200.so").resolve()
 
 
 class D4B200Error(RuntimeError):

