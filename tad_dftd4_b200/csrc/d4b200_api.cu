@@ -49,7 +49,7 @@ BlobOffsets blob_offsets() {
 }
 
 template <typename T>
-Tables<T> make_tables(const T* real, const double* f64, const int* i32) {
+Tables<T> make_tables(const T* real, const double* f64, const int* i32, const unsigned short* pij) {
   const BlobOffsets o = blob_offsets();
   Tables<T> t;
   t.rcov = real + o.rcov;
@@ -67,7 +67,14 @@ Tables<T> make_tables(const T* real, const double* f64, const int* i32) {
   t.wfpair = f64 + o.wfpair;
   t.refc = i32 + o.refc;
   t.maxcn_ref = i32 + o.maxcn_ref;
+  t.pij = pij;
   return t;
+}
+
+// p = hi (hi - 1) / 2 + lo  ->  (hi << 8) | lo, for every pair of a SMALL_MAX-atom structure
+__global__ void k_pair_table(unsigned short* __restrict__ pij) {
+  const int hi = blockIdx.x + 1;
+  for (int lo = threadIdx.x; lo < hi; lo += blockDim.x) pij[hi * (hi - 1) / 2 + lo] = (unsigned short)((hi << 8) | lo);
 }
 
 __global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -413,6 +420,8 @@ int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
     if ((e = cudaMalloc(&h->i32, n_i32 * sizeof(int))) != cudaSuccess) break;
     if ((e = cudaMemcpy(h->f64, f64_blob_host, n_f64 * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) break;
     if ((e = cudaMemcpy(h->i32, i32_blob_host, n_i32 * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = cudaMalloc(&h->pij, sizeof(unsigned short) * SMALL_MAX * (SMALL_MAX - 1) / 2)) != cudaSuccess) break;
+    k_pair_table<<<SMALL_MAX - 1, 128>>>(h->pij);
     k_to_float<<<(unsigned)((n_f64 + 255) / 256), 256>>>(h->f64, h->f32, n_f64);
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
     for (int p = 0; p < 1 + D4_HOST_SLOTS && e == cudaSuccess; ++p) {
@@ -423,8 +432,8 @@ int d4b200_tables_create(int device, const double* f64_blob_host, size_t n_f64,
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork[p], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) break;
-    h->t64 = make_tables<double>(h->f64, h->f64, h->i32);
-    h->t32 = make_tables<float>(h->f32, h->f64, h->i32);
+    h->t64 = make_tables<double>(h->f64, h->f64, h->i32, h->pij);
+    h->t32 = make_tables<float>(h->f32, h->f64, h->i32, h->pij);
     for (int model = 0; model < 2 && rc == 0; ++model) {
       if ((rc = configure<double, false>(h, model)) != 0) break;
       if ((rc = configure<double, true>(h, model)) != 0) break;
@@ -456,6 +465,7 @@ int d4b200_tables_destroy(d4b200_tables_t h) {
     if (h->ev_fork[p]) cudaEventDestroy(h->ev_fork[p]);
   }
   cudaFree(h->phase_dev);
+  cudaFree(h->pij);
   if (h->hcopy) cudaStreamDestroy(h->hcopy);
   for (int s = 0; s < D4_HOST_SLOTS; ++s) {
     if (h->hbuf[s]) cudaFree(h->hbuf[s]);

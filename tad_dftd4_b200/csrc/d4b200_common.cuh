@@ -35,6 +35,7 @@ struct Tables {
   const double* wfpair;  // [NELEM*NELEM]
   const int* refc;       // [NELEM*NREF]
   const int* maxcn_ref;  // [NELEM]
+  const unsigned short* pij;  // [SMALL_MAX*(SMALL_MAX-1)/2] pair index p -> (hi << 8) | lo
 };
 
 // Kernel-side view of d4b200_params in the compute type.

@@ -17,6 +17,7 @@ struct d4b200_tables {
   double* f64;  // device copy of the double blob
   float* f32;   // same blob converted to float
   int* i32;
+  unsigned short* pij;  // pair index table of the small family
   size_t n_f64, n_i32;
   Tables<double> t64;
   Tables<float> t32;

@@ -82,10 +82,10 @@ template <typename T, bool GRAD, bool D4S, int CAP>
 struct Lay {
   static constexpr int CP = CAP * (CAP - 1) / 2;
   static constexpr size_t plane_bytes = size_t(3) * CP * sizeof(T);
-  // D4 energy kernel: the weights live on top of the (not yet used) planes when they
-  // fit; the gradient kernel needs the weights until the end, and the D4S kernels read
+  // D4 energy kernel: the weights live on top of the (not yet used) second plane when
+  // they fit; the gradient kernel needs the weights until the end, and the D4S kernels read
   // them while the planes are being written
-  static constexpr bool wt_alias = !GRAD && !D4S && size_t(2) * NREF * CAP * sizeof(T) <= plane_bytes;
+  static constexpr bool wt_alias = !GRAD && !D4S && size_t(2) * NREF * CAP <= size_t(CP);
   // A/B vector buffers [23][CAP]: D4 energy 1 (Aq, then A0), D4 gradient 4 (Aq, A0, Bq, B0);
   // D4S has no per-atom vectors (pair-dependent weights) and only needs room for the
   // per-warp partial sums of the energy triple loop (16 warps)
@@ -134,13 +134,12 @@ __device__ __forceinline__ void d4s_gauss(const double* __restrict__ refcn, cons
   }
 }
 
-// p -> (hi, lo) with hi > lo and p = hi(hi-1)/2 + lo
-__device__ __forceinline__ void pair_decode(int p, int& hi, int& lo) {
-  int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-  if (i * (i - 1) / 2 > p) --i;
-  if ((i + 1) * i / 2 <= p) ++i;
-  hi = i;
-  lo = p - i * (i - 1) / 2;
+// p -> (hi, lo) with hi > lo and p = hi(hi-1)/2 + lo: one L1-resident table lookup
+// (Tables::pij) instead of a float square root plus corrections in every pair pass
+__device__ __forceinline__ void pair_lookup(const unsigned short* __restrict__ pij, int p, int& hi, int& lo) {
+  const unsigned v = __ldg(pij + p);
+  hi = (int)(v >> 8);
+  lo = (int)(v & 255u);
 }
 
 // A_i . A_j over the 23 frequencies with four independent accumulators (a single
@@ -168,30 +167,24 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
-// sum_j lo[pair(i,j)] over j < i  +  sum_j hi[pair(j,i)] over j > i, one thread per
-// row with four independent accumulators (the row phases are latency bound)
+// sum_j lo[pair(i,j)] over j < i  +  sum_j hi[pair(j,i)] over j > i (the row phases are
+// latency bound: eight lanes share a row)
+// Lane `sub` of the row takes every eighth column; must be called by all 32 lanes of a warp, rows >= n contribute nothing.
 template <typename T>
-__device__ __forceinline__ T row_sum2(const T* __restrict__ lo, const T* __restrict__ hi, int i, int n) {
-  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
-  const T* r = lo + i * (i - 1) / 2;
-  int j = 0;
-  for (; j + 4 <= i; j += 4) {
-    s0 += r[j];
-    s1 += r[j + 1];
-    s2 += r[j + 2];
-    s3 += r[j + 3];
+__device__ __forceinline__ T row_sum2_8(const T* __restrict__ lo, const T* __restrict__ hi, int i, int sub, int n) {
+  T s = T(0);
+  if (i < n) {
+    const T* r = lo + i * (i - 1) / 2;
+    for (int j = sub; j < i; j += 8) s += r[j];
+    for (int j = i + 1 + sub; j < n; j += 8) s += hi[j * (j - 1) / 2 + i];
   }
-  for (; j < i; ++j) s0 += r[j];
-  j = i + 1;
-  int tj = j * (j - 1) / 2 + i;
-  for (; j + 2 <= n; j += 2) {
-    s1 += hi[tj];
-    s2 += hi[tj + j];
-    tj += 2 * j + 1;
-  }
-  if (j < n) s3 += hi[tj];
-  return (s0 + s1) + (s2 + s3);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return s;
 }
+#define D4_ROWS8(i, sub) \
+  for (int t0_ = warp * 32, i = (t0_ + lane) >> 3, sub = lane & 7; t0_ < 8 * n; t0_ += NT, i = (t0_ + lane) >> 3)
 
 // Gradient triple visit: owner pair (j,k) with r^2 = b, third atom i with the
 // stash entries of (i,j) and (i,k).
@@ -312,7 +305,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   T* const Bq = Aq + 2 * NFREQ * CAP;  // GRAD only
   T* const B0 = Aq + 3 * NFREQ * CAP;  // GRAD only
   T* const at = reinterpret_cast<T*>(smem + L::atoms);
-  T* const wt = L::wt_alias ? reinterpret_cast<T*>(smem + L::planes)
+  T* const wt = L::wt_alias ? reinterpret_cast<T*>(smem + L::planes) + CP
                             : reinterpret_cast<T*>(smem + L::wts);
   int* const zs = reinterpret_cast<int*>(smem + L::ints);
   int* const idx = zs + CAP;
@@ -417,11 +410,12 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
 #pragma unroll 2
     for (int p = tid; p < np; p += NT) {
       int i, j;
-      pair_decode(p, i, j);
+      pair_lookup(tab.pij, p, i, j);
       const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
       const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
       const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
       const T r2 = dx * dx + dy * dy + dz * dz;
+      pa[p] = r2;  // later pair passes read the squared distance from here
       T cf = T(0);
       if (r2 <= P.cn_sq) {
         const T r = d4_sqrt(r2);
@@ -433,10 +427,12 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     }
     __syncthreads();
     PHASE(1);
-    for (int i = tid; i < n; i += NT) {
-      const T c = row_sum2(pu, pu, i, n);
-      ATOM(AT_CN)[i] = c;
-      if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = c;
+    D4_ROWS8(i, sub) {
+      const T c = row_sum2_8(pu, pu, i, sub, n);
+      if (sub == 0 && i < n) {
+        ATOM(AT_CN)[i] = c;
+        if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = c;
+      }
     }
     __syncthreads();
     PHASE(2);
@@ -516,11 +512,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       // One fused pass: two-body energy (energy kernel) + ATM stash.
       for (int p = tid; p < np; p += NT) {
         int i, j;
-        pair_decode(p, i, j);
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
+        pair_lookup(tab.pij, p, i, j);
+        const T r2 = pa[p];
         const int zi = zs[i], zj = zs[j];
         double S[NREF], dS[NREF], norm, dnorm;
         // partner j as seen by i
@@ -581,7 +574,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       PHASE(7);
       open = misc[2] != 0;
       if (!GRAD) {
-        for (int i = tid; i < n; i += NT) ATOM(AT_E)[i] = T(-0.5) * row_sum2(out0, out0, i, n);
+        D4_ROWS8(i, sub) {
+          const T e2 = row_sum2_8(out0, out0, i, sub, n);
+          if (sub == 0 && i < n) ATOM(AT_E)[i] = T(-0.5) * e2;
+        }
         __syncthreads();  // the triple loop reuses out0
       }
     }
@@ -629,11 +625,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
 #pragma unroll 2
       for (int p = tid; p < np; p += NT) {
         int i, j;
-        pair_decode(p, i, j);
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
+        pair_lookup(tab.pij, p, i, j);
+        const T r2 = pa[p];
         T e = T(0);
         if (r2 <= P.disp2_sq) {
           const T c6 = dot23<T, CAP>(Aq, i, j);
@@ -646,11 +639,14 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           if (P.s10k != T(0)) F += P.s10k * qq * qq * d4_rcp(r8 * r2 + R8 * R2);
           e = c6 * F;
         }
-        pu[p] = e;  // the weights (aliased layout) sit at the start of plane `pa`
+        pu[p] = e;  // the weights (aliased layout) sit in plane `pP`
       }
       __syncthreads();  // all reads of Aq done: the buffer becomes A0
       PHASE(5);
-      for (int i = tid; i < n; i += NT) ATOM(AT_E)[i] = T(-0.5) * row_sum2(pu, pu, i, n);
+      D4_ROWS8(i, sub) {
+        const T e2 = row_sum2_8(pu, pu, i, sub, n);
+        if (sub == 0 && i < n) ATOM(AT_E)[i] = T(-0.5) * e2;
+      }
       if (P.has_atm) {
         for (int t = tid; t < NFREQ * n; t += NT) {
           const int i = t / NFREQ, w = t - i * NFREQ;
@@ -668,15 +664,12 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
     if (P.has_atm) {
       // NB: in the aliased layout the stash overwrites the weights, which are
-      // dead by now (WT lives at the start of plane `pa`)
+      // dead by now (WT lives in plane `pP`)
 #pragma unroll 2
       for (int p = tid; p < np; p += NT) {
         int i, j;
-        pair_decode(p, i, j);
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
+        pair_lookup(tab.pij, p, i, j);
+        const T r2 = pa[p];
         const T r = d4_sqrt(r2);
         const T rinv = d4_rcp(r);
         const T c6 = dot23<T, CAP>(A0, i, j);
@@ -703,7 +696,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         // Gamma (dL/dC60 numerator) and D (dL/d r^2) need no communication.
         for (int p = tid; p < np; p += NT) {
           int j, k;
-          pair_decode(p, j, k);
+          pair_lookup(tab.pij, p, j, k);
           const T bs = pa[p];
           const T bb = fabs(bs);
           const T cjk = bs > T(0) ? T(1) : T(0);
@@ -749,13 +742,17 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         __syncwarp();
         const int nchunks = (np + 31) >> 5;
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-        // static round-robin over the chunks (sorted by decreasing sweep length): the
+        // static assignment of the chunks (sorted by decreasing sweep length): the
         // order of every floating-point sum is fixed, so results are bitwise reproducible
-        for (int chunk = warp; chunk < nchunks; chunk += NW) {
+        for (int round = 0; round * NW < nchunks; ++round) {
+          // boustrophedon: the sweep length decreases with the chunk index, so alternate
+          // the direction in which the chunks of a round are dealt to the warps
+          const int chunk = round * NW + ((round & 1) ? NW - 1 - warp : warp);
+          if (chunk >= nchunks) continue;
           const int p = chunk * 32 + lane;
           const bool valid = p < np;
           int j = 1 << 20, k = 0;
-          if (valid) pair_decode(p, j, k);
+          if (valid) pair_lookup(tab.pij, p, j, k);
           const int jmin = __shfl_sync(0xffffffffu, j, 0);
           // last row that is only partially active; an invalid lane keeps the
           // whole sweep on the predicated path
@@ -799,15 +796,18 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     if constexpr (!GRAD) {
       // ---- final assembly: E_i = E2_i + scale * (ATM shares) ------------------
       const T scale = open ? T(1) : T(2);  // closed triples: every atom has multiplicity 2
-      for (int i = tid; i < n; i += NT) {
-        T e = ATOM(AT_E)[i];
-        if (P.has_atm) {
-          T s3 = row_sum2(out0, out1, i, n);
+      D4_ROWS8(i, sub) {
+        T s3 = T(0);
+        if (P.has_atm) s3 = row_sum2_8(out0, out1, i, sub, n);
+        if (sub == 0 && i < n) {
+          T e = ATOM(AT_E)[i];
+          if (P.has_atm) {
 #pragma unroll
-          for (int w = 0; w < NW; ++w) s3 += Aq[w * CAP + i];
-          e += scale * s3;
+            for (int w = 0; w < NW; ++w) s3 += Aq[w * CAP + i];
+            e += scale * s3;
+          }
+          A.energy[(size_t)b * A.nat + idx[i]] = e;
         }
-        A.energy[(size_t)b * A.nat + idx[i]] = e;
       }
       __syncthreads();
       PHASE(9);
@@ -821,11 +821,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         //   out0/out1 <- d L/d q shares                       pu <- radial force coefficient
         for (int p = tid; p < np; p += NT) {
           int i, j;
-          pair_decode(p, i, j);
-          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-          const T r2 = dx * dx + dy * dy + dz * dz;
+          pair_lookup(tab.pij, p, i, j);
+          const T r2 = fabs(pa[p]);  // stash: signed squared distance
           const int zi = zs[i], zj = zs[j];
           const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
           double S[NREF], dS[NREF], norm, dnorm;
@@ -907,9 +904,13 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         }
         __syncthreads();
         PHASE(10);
-        for (int i = tid; i < n; i += NT) {
-          ATOM(AT_DCN)[i] = row_sum2(pa, pP, i, n);
-          ATOM(AT_DQ)[i] = row_sum2(out0, out1, i, n);
+        D4_ROWS8(i, sub) {
+          const T dc = row_sum2_8(pa, pP, i, sub, n);
+          const T dq = row_sum2_8(out0, out1, i, sub, n);
+          if (sub == 0 && i < n) {
+            ATOM(AT_DCN)[i] = dc;
+            ATOM(AT_DQ)[i] = dq;
+          }
         }
         __syncthreads();
         PHASE(12);
@@ -920,11 +921,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       //   pu <- 2 D + G2 C6q F'/r   (radial force coefficient, CN chain added later)
       for (int p = tid; p < np; p += NT) {
         int i, j;
-        pair_decode(p, i, j);
-        const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-        const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-        const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-        const T r2 = dx * dx + dy * dy + dz * dz;
+        pair_lookup(tab.pij, p, i, j);
+        const T r2 = fabs(pa[p]);  // stash: signed squared distance
         const T c6q = dot23<T, CAP>(Aq, i, j), c60 = dot23<T, CAP>(A0, i, j);
         const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
         T coefq = T(0), fc = T(2) * pu[p], e2 = T(0);
@@ -1006,7 +1004,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
       for (int p = tid; p < np; p += NT) {
         int i, j;
-        pair_decode(p, i, j);
+        pair_lookup(tab.pij, p, i, j);
         const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
         const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
         const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
@@ -1050,10 +1048,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         }
       }
       if (A.energy) {  // fused energy + gradient call: assemble the atomic energies as well
-        for (int i = tid; i < n; i += NT) {
-          T e = T(-0.5) * row_sum2(out0 + 4 * CP, out0 + 4 * CP, i, n);
-          if (P.has_atm) e += T(0.5) * row_sum2(out0 + 2 * CP, out0 + 3 * CP, i, n);
-          A.energy[(size_t)b * A.nat + idx[i]] = e;
+        D4_ROWS8(i, sub) {
+          T e = T(-0.5) * row_sum2_8(out0 + 4 * CP, out0 + 4 * CP, i, sub, n);
+          if (P.has_atm) e += T(0.5) * row_sum2_8(out0 + 2 * CP, out0 + 3 * CP, i, sub, n);
+          if (sub == 0 && i < n) A.energy[(size_t)b * A.nat + idx[i]] = e;
         }
       }
       __syncthreads();
