@@ -131,9 +131,66 @@ __global__ void k_scatter(int nbatch, Work wk) {
   wk.order[pos] = b;
 }
 
+// The three steps above in ONE launch for batches of moderate size: every block counts
+// the atoms of its structures; the block that finishes last (ticket counter) turns the
+// histogram into class ranges and scatters the structures into `order`.
+constexpr int PLAN_THREADS = 1024;
+constexpr int PLAN_MAX_BATCH = 32768;
+
+__global__ void __launch_bounds__(PLAN_THREADS) k_plan(const int64_t* __restrict__ numbers, int nbatch, int nat,
+                                                        Work wk, Caps caps) {
+  __shared__ int s_cursor[HIST_BINS];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = (blockIdx.x * PLAN_THREADS + tid) >> 5;
+  if (b < nbatch) {
+    const int64_t* row = numbers + (size_t)b * nat;
+    int c = 0;
+    for (int t = lane; t < nat; t += 32) c += row[t] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) {
+      wk.nreal[b] = c;
+      atomicAdd(&wk.hist[c <= SMALL_MAX ? c : SMALL_MAX + 1], 1);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(wk.done, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < HIST_BINS) s_cursor[tid] = __ldcg(&wk.hist[tid]);
+  __syncthreads();
+  if (tid == 0) {
+    int pos = 0;  // start[n] = number of structures with more than n atoms
+    for (int n = SMALL_MAX + 1; n >= 0; --n) {
+      const int h = s_cursor[n];
+      s_cursor[n] = pos;
+      pos += h;
+    }
+    int end = nbatch;
+    for (int c = 0; c < NCLASS; ++c) {
+      const int begin = s_cursor[caps.v[c]];
+      wk.class_range[2 * c] = begin;
+      wk.class_range[2 * c + 1] = end;
+      end = begin;
+    }
+    wk.class_range[2 * NCLASS] = 0;  // too large for the small family
+    wk.class_range[2 * NCLASS + 1] = end;
+    if (end > 0) atomicOr(wk.status, D4B200_STATUS_TOO_LARGE);
+  }
+  __syncthreads();
+  for (int s = tid; s < nbatch; s += PLAN_THREADS) {
+    const int n = __ldcg(&wk.nreal[s]);
+    const int pos = atomicAdd(&s_cursor[n <= SMALL_MAX ? n : SMALL_MAX + 1], 1);
+    wk.order[pos] = s;
+  }
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr int HEADER_INTS = 1 + (NCLASS + 1) + 2 * (NCLASS + 1) + 2 * HIST_BINS;
+constexpr int HEADER_INTS = 2 + (NCLASS + 1) + 2 * (NCLASS + 1) + 2 * HIST_BINS;
 
 size_t int_region_bytes(int nbatch) {
   return align_up(sizeof(int) * (HEADER_INTS + 2 * (size_t)nbatch), 256);
@@ -144,6 +201,7 @@ Work carve_work(void* ws, int nbatch) {
   Work wk;
   int* p = reinterpret_cast<int*>(ws);
   wk.status = p, p += 1;
+  wk.done = p, p += 1;
   wk.queue = p, p += NCLASS + 1;
   wk.class_range = p, p += 2 * (NCLASS + 1);
   wk.hist = p, p += HIST_BINS;
@@ -207,10 +265,15 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
   ++g_launches;
   Caps caps;
   for (int c = 0; c < NCLASS; ++c) caps.v[c] = h->caps[md][dt][gr][c];
-  k_count<<<(nbatch + 7) / 8, 256, 0, st>>>(numbers, nbatch, nat, wk);
-  k_scan<<<1, 32, 0, st>>>(nbatch, wk, caps);
-  k_scatter<<<(nbatch + 255) / 256, 256, 0, st>>>(nbatch, wk);
-  g_launches += 3;
+  if (nbatch <= PLAN_MAX_BATCH) {
+    k_plan<<<(nbatch * 32 + PLAN_THREADS - 1) / PLAN_THREADS, PLAN_THREADS, 0, st>>>(numbers, nbatch, nat, wk, caps);
+    g_launches += 1;
+  } else {
+    k_count<<<(nbatch + 7) / 8, 256, 0, st>>>(numbers, nbatch, nat, wk);
+    k_scan<<<1, 32, 0, st>>>(nbatch, wk, caps);
+    k_scatter<<<(nbatch + 255) / 256, 256, 0, st>>>(nbatch, wk);
+    g_launches += 3;
+  }
 
   for (int c = 0; c < NCLASS; ++c) h->ev_used[c] = 0;
   SmallArgs<T> A;

@@ -59,6 +59,7 @@ struct Work {
   int* class_range;  // [2*(NCLASS+1)]  begin/end in `order`; slot NCLASS = too large
   int* queue;        // [NCLASS+1] dynamic work counters
   int* status;       // [1]
+  int* done;         // [1] blocks of the planning kernel that have finished counting
 };
 
 __host__ __device__ inline int tri(int hi, int lo) { return hi * (hi - 1) / 2 + lo; }

@@ -192,12 +192,12 @@ __device__ __forceinline__ T row_sum2_8(const T* __restrict__ lo, const T* __res
 // (threebody.py:113-160 factorised per pair; e' = e_ijk/6 with s9 folded in; the stash
 // holds P' so that 1/(abc) never has to be formed).
 template <typename T, bool OPEN>
-__device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T cjk,
-                                           T Pjk, T ujk, T inv_b, T alp3, T gi, T gj, T gk,
-                                           T& accG, T& accD, T& accH, T& accL) {
+__device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T b2, T twob,
+                                           T cjk, T Pjk, T ujk, T inv_b, T alp3x3, T gi2, T gjk2,
+                                           T gj, T gk, T& accG, T& accD, T& accH, T& accL) {
   T a = a_s, c = c_s;
-  T W = gi + gj + gk;
-  T mj = T(2), mk = T(2);  // closed triple: multiplicity 2 for every atom
+  T W = gi2 + gjk2;  // closed triple: multiplicity 2 for every atom (g*2 = 2 g*)
+  T mj = T(2), mk = T(2);
   if (OPEN) {
     const T cij = a_s > T(0) ? T(1) : T(0);
     const T cik = c_s > T(0) ? T(1) : T(0);
@@ -205,25 +205,29 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
     c = fabs(c_s);
     mj = cik * (cij + cjk);
     mk = cij * (cik + cjk);
-    W = gi * (cjk * (cij + cik)) + gj * mj + gk * mk;
-  } else {
-    W = W + W;
+    W = T(0.5) * gi2 * (cjk * (cij + cik)) + gj * mj + gk * mk;
   }
-  const T X = a + b - c, Y = a - b + c, Z = b + c - a;
-  const T s = X * Y * Z;
-  const T abc = a * b * c;
+  // X = a+b-c, Y = a-b+c, Z = b+c-a:  X Z = b^2 - (a-c)^2,  X + Z = 2b
+  const T t1 = a - c, Y = (a + c) - b;
+  const T XZ = fma(-t1, t1, b2);
+  const T s = XZ * Y;
+  const T dsdb = fma(twob, Y, -XZ);  // d s / d b = Y Z - X Z + X Y
+  const T abc = (a * c) * b;
   const T t = uij * uik * ujk;
-  const T f = d4_rcp(T(1) + T(6) * t);
+  const T f = d4_rcp(fma(T(6), t, T(1)));
   const T pf = Pij * Pik * Pjk * f;  // P' = P / r^2: P_ij P_ik P_jk / (abc d)
   const T psf = pf * abc;
-  const T e = pf * (T(0.375) * s + abc);
-  const T dsdb = Y * Z - X * Z + X * Y;
-  const T common = e * (T(-2.5) + T(3) * alp3 * f * t) + psf;
-  const T de = common * inv_b + T(0.375) * pf * dsdb;
-  accG += W * e;
-  accD += W * de;
-  accH += mj * e;  // energy shares of the owner pair's atoms (fused energy + gradient call)
-  accL += mk * e;
+  const T e = pf * fma(T(0.375), s, abc);
+  const T common = fma(e, fma(alp3x3 * f, t, T(-2.5)), psf);
+  const T de = fma(common, inv_b, T(0.375) * pf * dsdb);
+  accG = fma(W, e, accG);
+  accD = fma(W, de, accD);
+  if (OPEN) {
+    accH = fma(mj, e, accH);  // energy shares of the owner pair's atoms (fused energy + gradient call)
+    accL = fma(mk, e, accL);
+  } else {
+    accH += e;  // both atoms of the owner pair have multiplicity 2 (applied by the caller)
+  }
 }
 
 // One block of 8 consecutive top atoms i0..i0+7 for the lane's bottom pair (j,k).
@@ -266,13 +270,15 @@ __device__ __forceinline__ void triple_block8(const T* __restrict__ colj, const 
         accK += mk * e;
         ei = mi * e;
       } else {
-        accJ += e;
         ei = e;
       }
     }
     v[u] = ei;
     ti += i;
   }
+  // closed triples: the share of the bottom pair is the plain sum of the block (tree sum
+  // instead of a chain of eight dependent additions)
+  if (!OPEN) accJ += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
 }
 
 // transposed reduction: 8 values x 32 lanes -> lane group (lane>>2) holds the sum of v[lane>>2]
@@ -701,8 +707,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const T bb = fabs(bs);
           const T cjk = bs > T(0) ? T(1) : T(0);
           const T Pjk = pP[p], ujk = pu[p];
-          const T inv_b = d4_rcp(bb);
+          const T inv_b = d4_rcp(bb), b2 = bb * bb, twob = bb + bb;
           const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
+          const T gjk2 = T(2) * (gj + gk), alp3x3 = T(3) * P.alp3;
           const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
           T accG = T(0), accD = T(0), accH = T(0), accL = T(0);
           for (int i = 0; i < n; ++i) {
@@ -710,12 +717,17 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             const int ti = i * (i - 1) / 2;
             const int pij = i > j ? ti + j : tj + i;
             const int pik = i > k ? ti + k : tk + i;
+            const T gi2 = T(2) * ATOM(AT_G)[i];
             if (open)
-              grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
-                                  Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD, accH, accL);
+              grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, b2, twob, cjk,
+                                  Pjk, ujk, inv_b, alp3x3, gi2, gjk2, gj, gk, accG, accD, accH, accL);
             else
-              grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, cjk,
-                                   Pjk, ujk, inv_b, P.alp3, ATOM(AT_G)[i], gj, gk, accG, accD, accH, accL);
+              grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, b2, twob, cjk,
+                                   Pjk, ujk, inv_b, alp3x3, gi2, gjk2, gj, gk, accG, accD, accH, accL);
+          }
+          if (!open) {
+            accH += accH;
+            accL = accH;
           }
           out0[p] = accG;
           out1[p] = accD;
