@@ -78,9 +78,15 @@ enum { AT_X = 0, AT_Y, AT_Z, AT_Q, AT_CN, AT_E, AT_RCOV, AT_SQ, AT_G, AT_DCN, AT
 // per-atom x 7 T arrays
 enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG };
 
+// Row stride of the A/B vector buffers [23][AS]: the smallest value >= CAP that is
+// 4 (mod 16), which makes the 8-atom x 4-frequency operand fragments of the FP64
+// tensor-core contraction (mma.m8n8k4) bank-conflict free.
+constexpr int a_stride(int cap) { return cap + (4 - cap % 16 + 16) % 16; }
+
 template <typename T, bool GRAD, bool D4S, int CAP>
 struct Lay {
   static constexpr int CP = CAP * (CAP - 1) / 2;
+  static constexpr int AS = a_stride(CAP);
   static constexpr size_t plane_bytes = size_t(3) * CP * sizeof(T);
   // D4 energy kernel: the weights live on top of the (not yet used) second plane when
   // they fit; the gradient kernel needs the weights until the end, and the D4S kernels read
@@ -89,7 +95,7 @@ struct Lay {
   // A/B vector buffers [23][CAP]: D4 energy 1 (Aq, then A0), D4 gradient 4 (Aq, A0, Bq, B0);
   // D4S has no per-atom vectors (pair-dependent weights) and only needs room for the
   // per-warp partial sums of the energy triple loop (16 warps)
-  static constexpr size_t abuf_elems = D4S ? (GRAD ? 0 : size_t(16) * CAP) : size_t(GRAD ? 4 : 1) * NFREQ * CAP;
+  static constexpr size_t abuf_elems = D4S ? (GRAD ? 0 : size_t(16) * CAP) : size_t(GRAD ? 4 : 1) * NFREQ * AS;
   static constexpr int n_atom = GRAD ? 11 : 8;
   static constexpr int n_wt = D4S ? (GRAD ? 3 : 2) : (GRAD ? 5 : (wt_alias ? 0 : 2));
   static constexpr size_t planes = 0;
@@ -144,19 +150,19 @@ __device__ __forceinline__ void pair_lookup(const unsigned short* __restrict__ p
 
 // A_i . A_j over the 23 frequencies with four independent accumulators (a single
 // chain of 23 dependent FMAs is latency bound)
-template <typename T, int CAP>
+template <typename T, int AS>
 __device__ __forceinline__ T dot23(const T* __restrict__ A, int i, int j) {
   T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
 #pragma unroll
   for (int w = 0; w + 4 <= NFREQ; w += 4) {
-    s0 += A[w * CAP + i] * A[w * CAP + j];
-    s1 += A[(w + 1) * CAP + i] * A[(w + 1) * CAP + j];
-    s2 += A[(w + 2) * CAP + i] * A[(w + 2) * CAP + j];
-    s3 += A[(w + 3) * CAP + i] * A[(w + 3) * CAP + j];
+    s0 += A[w * AS + i] * A[w * AS + j];
+    s1 += A[(w + 1) * AS + i] * A[(w + 1) * AS + j];
+    s2 += A[(w + 2) * AS + i] * A[(w + 2) * AS + j];
+    s3 += A[(w + 3) * AS + i] * A[(w + 3) * AS + j];
   }
-  s0 += A[20 * CAP + i] * A[20 * CAP + j];
-  s1 += A[21 * CAP + i] * A[21 * CAP + j];
-  s2 += A[22 * CAP + i] * A[22 * CAP + j];
+  s0 += A[20 * AS + i] * A[20 * AS + j];
+  s1 += A[21 * AS + i] * A[21 * AS + j];
+  s2 += A[22 * AS + i] * A[22 * AS + j];
   return (s0 + s1) + (s2 + s3);
 }
 
@@ -301,15 +307,16 @@ template <typename T, bool GRAD, bool D4S, int CAP, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   using L = Lay<T, GRAD, D4S, CAP>;
   constexpr int CP = L::CP;
+  constexpr int AS = L::AS;
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem[];
   T* const pa = reinterpret_cast<T*>(smem + L::planes);
   T* const pP = pa + CP;
   T* const pu = pP + CP;
   T* const Aq = reinterpret_cast<T*>(smem + L::abuf);
-  T* const A0 = GRAD ? Aq + NFREQ * CAP : Aq;
-  T* const Bq = Aq + 2 * NFREQ * CAP;  // GRAD only
-  T* const B0 = Aq + 3 * NFREQ * CAP;  // GRAD only
+  T* const A0 = GRAD ? Aq + NFREQ * AS : Aq;
+  T* const Bq = Aq + 2 * NFREQ * AS;  // GRAD only
+  T* const B0 = Aq + 3 * NFREQ * AS;  // GRAD only
   T* const at = reinterpret_cast<T*>(smem + L::atoms);
   T* const wt = L::wt_alias ? reinterpret_cast<T*>(smem + L::planes) + CP
                             : reinterpret_cast<T*>(smem + L::wts);
@@ -601,8 +608,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         sq += WT(WT_Q)[i * NREF + a] * av;
         if (GRAD) s0 += WT(WT_0)[i * NREF + a] * av;
       }
-      Aq[w * CAP + i] = sq;
-      if (GRAD) A0[w * CAP + i] = s0;
+      Aq[w * AS + i] = sq;
+      if (GRAD) A0[w * AS + i] = s0;
     }
     __syncthreads();
     PHASE(4);
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         T* c6row = A.c6_out + (size_t)b * A.nat * A.nat;
         for (int t = tid; t < n * n; t += NT) {
           const int i = t / n, j = t - i * n;
-          c6row[(size_t)idx[i] * A.nat + idx[j]] = dot23<T, CAP>(Aq, i, j);
+          c6row[(size_t)idx[i] * A.nat + idx[j]] = dot23<T, AS>(Aq, i, j);
         }
         for (int i = tid; i < n; i += NT) {
           T al = T(0);
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const T r2 = pa[p];
         T e = T(0);
         if (r2 <= P.disp2_sq) {
-          const T c6 = dot23<T, CAP>(Aq, i, j);
+          const T c6 = dot23<T, AS>(Aq, i, j);
           const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
           const T R0 = P.a1 * ss + P.a2;
           const T qq = ss * ss;  // = 3 r4r2_i r4r2_j
@@ -660,7 +667,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           T s0 = T(0);
 #pragma unroll
           for (int a = 0; a < NREF; ++a) s0 += WT(WT_0)[i * NREF + a] * al[a * NFREQ];
-          A0[w * CAP + i] = s0;
+          A0[w * AS + i] = s0;
         }
       }
       __syncthreads();
@@ -678,7 +685,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const T r2 = pa[p];
         const T r = d4_sqrt(r2);
         const T rinv = d4_rcp(r);
-        const T c6 = dot23<T, CAP>(A0, i, j);
+        const T c6 = dot23<T, AS>(A0, i, j);
         const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
         const bool inside = r2 <= P.disp3_sq;
         if (!inside) misc[2] = 1;
@@ -712,19 +719,25 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const T gjk2 = T(2) * (gj + gk), alp3x3 = T(3) * P.alp3;
           const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
           T accG = T(0), accD = T(0), accH = T(0), accL = T(0);
-          for (int i = 0; i < n; ++i) {
-            if (i == j || i == k) continue;
-            const int ti = i * (i - 1) / 2;
-            const int pij = i > j ? ti + j : tj + i;
-            const int pik = i > k ? ti + k : tk + i;
-            const T gi2 = T(2) * ATOM(AT_G)[i];
-            if (open)
-              grad_visit<T, true>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, b2, twob, cjk,
-                                  Pjk, ujk, inv_b, alp3x3, gi2, gjk2, gj, gk, accG, accD, accH, accL);
-            else
-              grad_visit<T, false>(pa[pij], pP[pij], pu[pij], pa[pik], pP[pik], pu[pik], bb, b2, twob, cjk,
-                                   Pjk, ujk, inv_b, alp3x3, gi2, gjk2, gj, gk, accG, accD, accH, accL);
+          // branch-free sweep over the third atom: for i == j or i == k the visit runs on
+          // the owner's own entry with a zero pair factor (contributes exactly 0), so the
+          // body is straight-line code and two visits can be in flight per thread
+#define D4_SWEEP(OPENV)                                                                         \
+  _Pragma("unroll 4") for (int i = 0; i < n; ++i) {                                             \
+    const int ti = i * (i - 1) / 2;                                                             \
+    const bool ok = (i != j) & (i != k);                                                        \
+    const int pij = ok ? (i > j ? ti + j : tj + i) : p;                                         \
+    const int pik = ok ? (i > k ? ti + k : tk + i) : p;                                         \
+    grad_visit<T, OPENV>(pa[pij], ok ? pP[pij] : T(0), pu[pij], pa[pik], pP[pik], pu[pik], bb,  \
+                         b2, twob, cjk, Pjk, ujk, inv_b, alp3x3, T(2) * ATOM(AT_G)[i], gjk2,    \
+                         gj, gk, accG, accD, accH, accL);                                       \
+  }
+          if (open) {
+            D4_SWEEP(true)
+          } else {
+            D4_SWEEP(false)
           }
+#undef D4_SWEEP
           if (!open) {
             accH += accH;
             accL = accH;
@@ -935,7 +948,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         int i, j;
         pair_lookup(tab.pij, p, i, j);
         const T r2 = fabs(pa[p]);  // stash: signed squared distance
-        const T c6q = dot23<T, CAP>(Aq, i, j), c60 = dot23<T, CAP>(A0, i, j);
+        const T c6q = dot23<T, AS>(Aq, i, j), c60 = dot23<T, AS>(A0, i, j);
         const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
         T coefq = T(0), fc = T(2) * pu[p], e2 = T(0);
         if (r2 <= P.disp2_sq) {
@@ -964,22 +977,57 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
       __syncthreads();
       PHASE(10);
-      // phase 8: B_i[w] = sum_j coef_ij A_j[w]
-      for (int t = tid; t < NFREQ * n; t += NT) {
-        const int w = t / n, i = t - w * n;
-        const int ti = i * (i - 1) / 2;
-        T sq = T(0), s0 = T(0);
-        for (int j = 0; j < i; ++j) {
-          sq += pa[ti + j] * Aq[w * CAP + j];
-          s0 += pP[ti + j] * A0[w * CAP + j];
+      // phase 8: B_i[w] = sum_j coef_ij A_j[w]: an (n x n).(n x 23) matrix product per flavour
+      if constexpr (sizeof(T) == 8) {
+        // FP64 tensor path (mma.m8n8k4): a warp owns an 8-atom x 8-frequency output tile
+        // and walks the contraction index j in steps of four.  Operand fragments:
+        //   A[r][c] = coef(i0 + r, j0 + c), B[c][r] = A_{j0 + c}[w0 + r], r = lane / 4, c = lane % 4
+        const int nrb = (n + 7) >> 3;
+        const int r = lane >> 2, c = lane & 3;
+        for (int tile = warp; tile < nrb * 6; tile += NW) {
+          const int fl = tile & 1, rest = tile >> 1;
+          const int wb = rest % 3, rb = rest / 3;
+          const T* const coef = fl ? pP : pa;
+          const T* const Av = fl ? A0 : Aq;
+          const int i = rb * 8 + r, ti = i * (i - 1) / 2;
+          const int w = wb * 8 + r;
+          const bool iok = i < n, wok = w < NFREQ;
+          double d0 = 0.0, d1 = 0.0;
+          for (int j0 = 0; j0 < n; j0 += 4) {
+            const int j = j0 + c;
+            const bool jok = j < n;
+            double av = 0.0, bv = 0.0;
+            if (iok && jok && j != i) av = coef[j < i ? ti + j : j * (j - 1) / 2 + i];
+            if (wok && jok) bv = Av[w * AS + j];
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(d0), "+d"(d1)
+                         : "d"(av), "d"(bv));
+          }
+          // accumulator fragment: row r (atom), columns 2c, 2c+1 (frequency)
+          T* const Bv = fl ? B0 : Bq;
+          const int wo = wb * 8 + 2 * c;
+          if (iok) {
+            if (wo < NFREQ) Bv[wo * AS + i] = d0;
+            if (wo + 1 < NFREQ) Bv[(wo + 1) * AS + i] = d1;
+          }
         }
-        for (int j = i + 1; j < n; ++j) {
-          const int pj = j * (j - 1) / 2 + i;
-          sq += pa[pj] * Aq[w * CAP + j];
-          s0 += pP[pj] * A0[w * CAP + j];
+      } else {
+        for (int t = tid; t < NFREQ * n; t += NT) {
+          const int w = t / n, i = t - w * n;
+          const int ti = i * (i - 1) / 2;
+          T sq = T(0), s0 = T(0);
+          for (int j = 0; j < i; ++j) {
+            sq += pa[ti + j] * Aq[w * AS + j];
+            s0 += pP[ti + j] * A0[w * AS + j];
+          }
+          for (int j = i + 1; j < n; ++j) {
+            const int pj = j * (j - 1) / 2 + i;
+            sq += pa[pj] * Aq[w * AS + j];
+            s0 += pP[pj] * A0[w * AS + j];
+          }
+          Bq[w * AS + i] = sq;
+          B0[w * AS + i] = s0;
         }
-        Bq[w * CAP + i] = sq;
-        B0[w * CAP + i] = s0;
       }
       __syncthreads();
       PHASE(11);
@@ -993,8 +1041,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
 #pragma unroll
         for (int w = 0; w < NFREQ; ++w) {
           const T av = al[w];
-          pq += av * Bq[w * CAP + i];
-          p0 += av * B0[w * CAP + i];
+          pq += av * Bq[w * AS + i];
+          p0 += av * B0[w * AS + i];
         }
         tcn[t] = WT(WT_ZGD)[t] * pq + WT(WT_Z0GD)[t] * p0;
         tq[t] = WT(WT_DZG)[t] * pq;
