@@ -166,6 +166,41 @@ __device__ __forceinline__ T dot23(const T* __restrict__ A, int i, int j) {
   return (s0 + s1) + (s2 + s3);
 }
 
+// C6_ij = A_i . A_j for all pairs of a structure on the FP64 tensor path: a warp owns
+// an 8 x 8 tile of the (lower triangle of the) pair matrix and contracts the 23 (padded
+// to 24) frequencies in six mma.m8n8k4 steps; results go to the packed pair plane
+// `out[i (i-1)/2 + j]`, j < i.  Called by whole warps.
+template <int AS>
+__device__ __forceinline__ void c6_tiles(const double* __restrict__ Av, double* __restrict__ out,
+                                         const unsigned short* __restrict__ pij, int n, int warp,
+                                         int lane, int nwarps) {
+  const int nb = (n + 7) >> 3;
+  const int r = lane >> 2, c = lane & 3;
+  for (int tile = warp; tile < nb * (nb + 1) / 2; tile += nwarps) {
+    int I, J;  // tile = I (I + 1) / 2 + J, J <= I
+    pair_lookup(pij, tile, I, J);
+    I -= 1;
+    const int i = I * 8 + r, j = J * 8 + r;
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < 24; k0 += 4) {
+      const int w = k0 + c;
+      const bool wok = w < NFREQ;
+      const double av = wok ? Av[w * AS + i] : 0.0;
+      const double bv = wok ? Av[w * AS + j] : 0.0;
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(d0), "+d"(d1)
+                   : "d"(av), "d"(bv));
+    }
+    // accumulator fragment: row r (atom i), columns 2c, 2c+1 (atoms J*8 + ...)
+    if (i < n) {
+      const int jj = J * 8 + 2 * c, ti = i * (i - 1) / 2;
+      if (jj < i) out[ti + jj] = d0;
+      if (jj + 1 < i) out[ti + jj + 1] = d1;
+    }
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -635,6 +670,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
 
     // ---- phase 4: two-body energy (twobody.py:134-201, rational damping) ---
     if constexpr (!GRAD) {
+      if constexpr (sizeof(T) == 8) {  // C6 of all pairs on the tensor path -> plane `pu`
+        c6_tiles<AS>(Aq, pu, tab.pij, n, warp, lane, NW);
+        __syncthreads();
+      }
 #pragma unroll 2
       for (int p = tid; p < np; p += NT) {
         int i, j;
@@ -642,7 +681,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const T r2 = pa[p];
         T e = T(0);
         if (r2 <= P.disp2_sq) {
-          const T c6 = dot23<T, AS>(Aq, i, j);
+          T c6;
+          if constexpr (sizeof(T) == 8) c6 = pu[p];
+          else c6 = dot23<T, AS>(Aq, i, j);
           const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
           const T R0 = P.a1 * ss + P.a2;
           const T qq = ss * ss;  // = 3 r4r2_i r4r2_j
@@ -675,6 +716,12 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     }
 
     // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
+    if constexpr (sizeof(T) == 8) {  // C6(q = 0) of all pairs on the tensor path -> plane `pP`
+      if (P.has_atm) {
+        c6_tiles<AS>(A0, pP, tab.pij, n, warp, lane, NW);
+        __syncthreads();
+      }
+    }
     if (P.has_atm) {
       // NB: in the aliased layout the stash overwrites the weights, which are
       // dead by now (WT lives in plane `pP`)
@@ -685,7 +732,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const T r2 = pa[p];
         const T r = d4_sqrt(r2);
         const T rinv = d4_rcp(r);
-        const T c6 = dot23<T, AS>(A0, i, j);
+        T c6;
+        if constexpr (sizeof(T) == 8) c6 = pP[p];
+        else c6 = dot23<T, AS>(A0, i, j);
         const T R0 = P.a1 * ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j] + P.a2;
         const bool inside = r2 <= P.disp3_sq;
         if (!inside) misc[2] = 1;
