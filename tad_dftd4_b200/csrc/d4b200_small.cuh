@@ -128,10 +128,16 @@ __device__ __forceinline__ void d4s_gauss(const double* __restrict__ refcn, cons
     const int rc = refc[z * NREF + a];
     const double d = cn - refcn[z * NREF + a];
     double s = 0.0, ds = 0.0;
-    for (int k = 1; k <= rc; ++k) {
-      const double e = exp(-((double)k * arg[a] - shift));
-      s += e;
-      if (DERIV) ds += -2.0 * (double)k * wf * d * e;
+    if (rc > 0) {  // geometric series in x = exp(-arg), see the weights phase of the kernel
+      const double t1 = exp(shift - arg[a]), x = exp(-arg[a]);
+      double pw = 1.0, acc = 0.0, dacc = 0.0;
+      for (int k = 1; k <= rc; ++k) {
+        acc += pw;
+        dacc += (double)k * pw;
+        pw *= x;
+      }
+      s = t1 * acc;
+      if (DERIV) ds = -2.0 * wf * d * t1 * dacc;
     }
     S[a] = s;
     dS[a] = ds;
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
                             : reinterpret_cast<T*>(smem + L::wts);
   int* const zs = reinterpret_cast<int*>(smem + L::ints);
   int* const idx = zs + CAP;
-  int* const misc = idx + CAP;  // [0]=work item, [1]=n, [2]=any_open, [3]=skip, [4]=chunk counter
+  int* const misc = idx + CAP;  // [0]=work item, [1]=n, [2]=any_open, [3]=skip, [4]=chunk counter, [5]=near pairs
 #define ATOM(k) (at + (k) * CAP)
 #define WT(k) (wt + (k) * NREF * CAP)
 
@@ -413,6 +419,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         misc[2] = 0;
         misc[3] = count > CAP;
         misc[4] = 0;
+        misc[5] = 0;
         if (bad) atomicOr(A.wk.status, D4B200_STATUS_BAD_NUMBER);
         if (count > CAP) atomicOr(A.wk.status, D4B200_STATUS_TOO_LARGE);
       }
@@ -455,23 +462,46 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     PHASE(0);
 
     // ---- phase 1: coordination number (tad_mctc cn_d4 / erf_count) ----------
-#pragma unroll 2
-    for (int p = tid; p < np; p += NT) {
-      int i, j;
-      pair_lookup(tab.pij, p, i, j);
-      const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
-      const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
-      const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
-      const T r2 = dx * dx + dy * dy + dz * dz;
-      pa[p] = r2;  // later pair passes read the squared distance from here
-      T cf = T(0);
-      if (r2 <= P.cn_sq) {
-        const T r = d4_sqrt(r2);
+    // Sweep 1 (all pairs): squared distance, and a compacted list of the pairs whose
+    // counting function is above one ulp (r < (1 + cut/kcn) r0, about five per atom).
+    // Sweep 2 (listed pairs only): the erfc evaluation, on full warps.
+    {
+      int* const near = reinterpret_cast<int*>(pP);  // plane `pP` is unused until the weights
+      const T reach = T(1) + d4_erfc_cut(T(0)) / T(7.5);
+      for (int p0 = warp * 32; p0 < np; p0 += NT) {
+        const int p = p0 + lane;
+        bool hit = false;
+        if (p < np) {
+          int i, j;
+          pair_lookup(tab.pij, p, i, j);
+          const T dx = ATOM(AT_X)[i] - ATOM(AT_X)[j];
+          const T dy = ATOM(AT_Y)[i] - ATOM(AT_Y)[j];
+          const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
+          const T r2 = dx * dx + dy * dy + dz * dz;
+          pa[p] = r2;  // later pair passes read the squared distance from here
+          pu[p] = T(0);
+          const T rr = reach * (ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j]);
+          hit = r2 <= P.cn_sq && r2 < rr * rr;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&misc[5], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (hit) near[base + __popc(m & ((1u << lane) - 1u))] = p;
+        }
+      }
+      __syncthreads();
+      const int nnear = misc[5];
+      for (int t = tid; t < nnear; t += NT) {
+        const int p = near[t];
+        int i, j;
+        pair_lookup(tab.pij, p, i, j);
+        const T r = d4_sqrt(pa[p]);
         const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
         const T xx = T(7.5) * (r * d4_rcp(r0) - T(1));
-        if (xx < d4_erfc_cut(T(0))) cf = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(xx);
+        if (xx < d4_erfc_cut(T(0))) pu[p] = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(xx);
       }
-      pu[p] = cf;
     }
     __syncthreads();
     PHASE(1);
@@ -500,11 +530,19 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       double shift = arg;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, o));
+      // sum_k exp(-(k arg - shift)) = exp(shift - arg) (1 + x + x^2 + ...), x = exp(-arg): two
+      // independent exponentials per lane instead of one per Gaussian copy
       double S = 0.0, dS = 0.0;
-      for (int k = 1; k <= (D4S ? 0 : rc); ++k) {
-        const double e = exp(-((double)k * arg - shift));
-        S += e;
-        dS += -2.0 * (double)k * P.wf * d * e;
+      if (!D4S && rc > 0) {
+        const double t1 = exp(shift - arg), x = exp(-arg);
+        double pw = 1.0, acc = 0.0, dacc = 0.0;
+        for (int k = 1; k <= rc; ++k) {
+          acc += pw;
+          dacc += (double)k * pw;
+          pw *= x;
+        }
+        S = t1 * acc;
+        dS = -2.0 * P.wf * d * t1 * dacc;
       }
       double norm = S, dnorm = dS;
 #pragma unroll
@@ -514,9 +552,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
       if (on) {
         double gw = 0.0, dgw = 0.0;
-        if (norm > 0.0) {
-          gw = S / norm;
-          dgw = (dS - gw * dnorm) / norm;
+        if (norm > 0.0) {  // norm >= 1: the closest reference contributes exp(0)
+          const double inv = d4_rcp(norm);
+          gw = S * inv;
+          dgw = (dS - gw * dnorm) * inv;
         }
         double zeta = 0.0, dzeta = 0.0;
         if (rc > 0) {
@@ -527,7 +566,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             const double qe = qmod - (double)d4_eps<T>();
             const double scale = exp(gam * (1.0 - qref / qe));
             zeta = exp(P.ga * (1.0 - scale));
-            dzeta = -P.ga * gam * scale * zeta * qref / (qe * qe);
+            if (GRAD) dzeta = -P.ga * gam * scale * zeta * qref / (qe * qe);
           } else {
             zeta = exp(P.ga);
           }
