@@ -505,26 +505,21 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     }
     __syncthreads();
     PHASE(1);
-    D4_ROWS8(i, sub) {
-      const T c = row_sum2_8(pu, pu, i, sub, n);
-      if (sub == 0 && i < n) {
-        ATOM(AT_CN)[i] = c;
-        if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = c;
-      }
-    }
-    __syncthreads();
-    PHASE(2);
-
-    // ---- phase 2: Gaussian weights (float64 always) x zeta -----------------
+    // ---- phase 2: CN row sums -> Gaussian weights (float64 always) x zeta -> A_i[w] ----
     // model/d4.py:137-228; max-shifted exponentials instead of pow(exp(-d^2), k wf).
-    // Eight lanes per atom (one per reference, one idle): the shift (min exponent)
-    // and the normalisation are 8-lane shuffle reductions, no shared temporaries.
-    for (int t = tid; t < 8 * CAP; t += NT) {
-      const int i = t >> 3, a = t & 7;
+    // Eight lanes per atom (one per reference, one idle): the row sum, the shift (min
+    // exponent) and the normalisation are 8-lane shuffle reductions; the weights stay in
+    // registers for the weighted polarizability vectors (three frequencies per lane).
+    D4_ROWS8(i, a) {
+      const T cn_row = row_sum2_8(pu, pu, i, a, n);  // every lane of the row holds the sum
+      if (a == 0 && i < n) {
+        ATOM(AT_CN)[i] = cn_row;
+        if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = cn_row;
+      }
       const bool on = i < n && a < NREF;
-      const int z = on ? zs[i] : 0;
+      const int z = i < n ? zs[i] : 0;
       const int rc = on ? tab.refc[z * NREF + a] : 0;
-      const double cn_i = on ? (double)ATOM(AT_CN)[i] : 0.0;
+      const double cn_i = on ? (double)cn_row : 0.0;
       const double d = on ? cn_i - tab.refcn[z * NREF + a] : 0.0;
       const double arg = (rc > 0 && !D4S) ? P.wf * d * d : 1e300;
       double shift = arg;
@@ -550,6 +545,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         norm += __shfl_xor_sync(0xffffffffu, norm, o);
         dnorm += __shfl_xor_sync(0xffffffffu, dnorm, o);
       }
+      T wq_reg = T(0), w0_reg = T(0);  // zeta gw and zeta(q=0) gw of this lane's reference
       if (on) {
         double gw = 0.0, dgw = 0.0;
         if (norm > 0.0) {  // norm >= 1: the closest reference contributes exp(0)
@@ -573,18 +569,52 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         }
         const double z0 = tab.zeta0[z * NREF + a];
         const int o = i * NREF + a;
+        wq_reg = (T)(zeta * gw);
+        w0_reg = (T)(z0 * gw);
         if (D4S) {  // weights are pair dependent: keep the charge scaling only
           WT(WT_Q)[o] = (T)zeta;
           WT(WT_0)[o] = (T)z0;
           if (GRAD) WT(WT_ZGD)[o] = (T)dzeta;
         } else {
-        WT(WT_Q)[o] = (T)(zeta * gw);
-        WT(WT_0)[o] = (T)(z0 * gw);
+        WT(WT_Q)[o] = wq_reg;
+        WT(WT_0)[o] = w0_reg;
         if (GRAD) {
           WT(WT_ZGD)[o] = (T)(zeta * dgw);
           WT(WT_Z0GD)[o] = (T)(z0 * dgw);
           WT(WT_DZG)[o] = (T)(dzeta * gw);
         }
+        }
+      }
+      if constexpr (!D4S) {
+        // weighted polarizability vectors: lane a takes the frequencies a, a + 8, a + 16 and
+        // collects the seven weights of its atom from the neighbouring lanes.  The energy
+        // kernel builds only the charge-scaled flavour now; the q = 0 flavour for the ATM
+        // term goes into the same buffer after the two-body pass.
+        const T* const al = tab.alpha_w + (size_t)z * NREF * NFREQ;
+        T sq[3] = {T(0), T(0), T(0)}, s0[3] = {T(0), T(0), T(0)};
+#pragma unroll
+        for (int ar = 0; ar < NREF; ++ar) {
+          const T vq = __shfl_sync(0xffffffffu, wq_reg, (lane & 24) + ar);
+          const T v0 = GRAD ? __shfl_sync(0xffffffffu, w0_reg, (lane & 24) + ar) : T(0);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int w = a + 8 * k;
+            if (w < NFREQ) {
+              const T av = al[ar * NFREQ + w];
+              sq[k] += vq * av;
+              if (GRAD) s0[k] += v0 * av;
+            }
+          }
+        }
+        if (i < n) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int w = a + 8 * k;
+            if (w < NFREQ) {
+              Aq[w * AS + i] = sq[k];
+              if (GRAD) A0[w * AS + i] = s0[k];
+            }
+          }
         }
       }
     }
@@ -669,25 +699,6 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
     }
     if constexpr (!D4S) {
-    // ---- phase 3: weighted polarizability vectors A_i[w] -------------------
-    // energy kernel: only the charge-scaled flavour now; the q = 0 flavour for
-    // the ATM term is built into the same buffer after the two-body pass
-    for (int t = tid; t < NFREQ * n; t += NT) {
-      const int i = t / NFREQ, w = t - i * NFREQ;
-      const T* al = tab.alpha_w + (size_t)zs[i] * NREF * NFREQ + w;
-      T sq = T(0), s0 = T(0);
-#pragma unroll
-      for (int a = 0; a < NREF; ++a) {
-        const T av = al[a * NFREQ];
-        sq += WT(WT_Q)[i * NREF + a] * av;
-        if (GRAD) s0 += WT(WT_0)[i * NREF + a] * av;
-      }
-      Aq[w * AS + i] = sq;
-      if (GRAD) A0[w * AS + i] = s0;
-    }
-    __syncthreads();
-    PHASE(4);
-
     // ---- properties mode (disp.py:149-197): cn, C6_ij = A_i.A_j, alpha_i, then next structure
     if constexpr (!GRAD) {
       if (A.c6_out) {
