@@ -518,26 +518,37 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
       const bool on = i < n && a < NREF;
       const int z = i < n ? zs[i] : 0;
-      const int rc = on ? tab.refc[z * NREF + a] : 0;
-      const double cn_i = on ? (double)cn_row : 0.0;
-      const double d = on ? cn_i - tab.refcn[z * NREF + a] : 0.0;
+      // branch-free body (one basic block): the four exponentials below are independent
+      // chains that the scheduler interleaves; table entries are fetched up front
+      const int za = z * NREF + (a < NREF ? a : 0);
+      const int rc = on ? tab.refc[za] : 0;
+      const double rcn = tab.refcn[za], qref = tab.refq[za], z0 = tab.zeta0[za];
+      const double gam = tab.gamgc[z], zeff = tab.zeff[z];
+      const double qat = i < n ? (double)ATOM(AT_Q)[i] : 0.0;
+      const double d = (double)cn_row - rcn;
       const double arg = (rc > 0 && !D4S) ? P.wf * d * d : 1e300;
       double shift = arg;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, o));
       // sum_k exp(-(k arg - shift)) = exp(shift - arg) (1 + x + x^2 + ...), x = exp(-arg): two
-      // independent exponentials per lane instead of one per Gaussian copy
+      // exponentials per lane instead of one per Gaussian copy (refc is 1 or 3 in the D4 data)
       double S = 0.0, dS = 0.0;
-      if (!D4S && rc > 0) {
+      if constexpr (!D4S) {
         const double t1 = exp(shift - arg), x = exp(-arg);
         double pw = 1.0, acc = 0.0, dacc = 0.0;
-        for (int k = 1; k <= rc; ++k) {
+#pragma unroll
+        for (int k = 1; k <= 3; ++k) {
+          acc += k <= rc ? pw : 0.0;
+          dacc += k <= rc ? (double)k * pw : 0.0;
+          pw *= x;
+        }
+        for (int k = 4; k <= rc; ++k) {
           acc += pw;
           dacc += (double)k * pw;
           pw *= x;
         }
-        S = t1 * acc;
-        dS = -2.0 * P.wf * d * t1 * dacc;
+        S = rc > 0 ? t1 * acc : 0.0;
+        dS = rc > 0 ? -2.0 * P.wf * d * t1 * dacc : 0.0;
       }
       double norm = S, dnorm = dS;
 #pragma unroll
@@ -545,29 +556,21 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         norm += __shfl_xor_sync(0xffffffffu, norm, o);
         dnorm += __shfl_xor_sync(0xffffffffu, dnorm, o);
       }
+      // charge scaling zeta (model/base.py:326-335); qmod <= 0 is the scale = 0 limit
+      const double qmod = qat + zeff;
+      const bool qpos = qmod > 0.0;
+      const double qe = qpos ? qmod - (double)d4_eps<T>() : 1.0;
+      const double qinv = 1.0 / qe;
+      const double scale = qpos ? exp(gam * (1.0 - qref * qinv)) : 0.0;
+      const double zeta = rc > 0 ? exp(P.ga * (1.0 - scale)) : 0.0;
+      const double dzeta = GRAD ? -P.ga * gam * scale * zeta * qref * qinv * qinv : 0.0;
+      // normalised Gaussian weight; norm >= 1 where defined (the closest reference contributes exp(0))
+      const bool nz = norm > 0.0;
+      const double inv = d4_rcp(nz ? norm : 1.0);
+      const double gw = nz ? S * inv : 0.0;
+      const double dgw = nz ? (dS - gw * dnorm) * inv : 0.0;
       T wq_reg = T(0), w0_reg = T(0);  // zeta gw and zeta(q=0) gw of this lane's reference
       if (on) {
-        double gw = 0.0, dgw = 0.0;
-        if (norm > 0.0) {  // norm >= 1: the closest reference contributes exp(0)
-          const double inv = d4_rcp(norm);
-          gw = S * inv;
-          dgw = (dS - gw * dnorm) * inv;
-        }
-        double zeta = 0.0, dzeta = 0.0;
-        if (rc > 0) {
-          const double gam = tab.gamgc[z];
-          const double qref = tab.refq[z * NREF + a];
-          const double qmod = (double)ATOM(AT_Q)[i] + tab.zeff[z];
-          if (qmod > 0.0) {
-            const double qe = qmod - (double)d4_eps<T>();
-            const double scale = exp(gam * (1.0 - qref / qe));
-            zeta = exp(P.ga * (1.0 - scale));
-            if (GRAD) dzeta = -P.ga * gam * scale * zeta * qref / (qe * qe);
-          } else {
-            zeta = exp(P.ga);
-          }
-        }
-        const double z0 = tab.zeta0[z * NREF + a];
         const int o = i * NREF + a;
         wq_reg = (T)(zeta * gw);
         w0_reg = (T)(z0 * gw);
