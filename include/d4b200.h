@@ -236,6 +236,9 @@ int d4b200_profile_enable(d4b200_tables_t tables, int enable);
 int d4b200_profile_read(d4b200_tables_t tables, float* ms_out /*[D4B200_NCLASS + 2]*/);
 /* Inclusive atom-count bounds of the size classes for a kernel flavour. */
 int d4b200_class_caps(d4b200_tables_t tables, int fp32, int grad, int* caps_out /*[D4B200_NCLASS]*/);
+/* Largest structure (atoms) the one-CTA-per-structure kernels of a flavour accept; larger
+ * structures go through the d4b200_large_* entry points.  model: D4B200_MODEL_D4 / _D4S. */
+int d4b200_small_limit(d4b200_tables_t tables, int fp32, int grad, int model);
 /* Measured FP64 FMA throughput (TFLOP/s) of the device: roofline denominator. */
 int d4b200_measure_fp64_peak(d4b200_tables_t tables, void* scratch_dev, size_t scratch_bytes,
                              void* stream, double* tflops_out);

@@ -60,6 +60,7 @@ _SIGS = {
     "d4b200_profile_enable": (C.c_int, [_VP, C.c_int]),
     "d4b200_profile_read": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "d4b200_class_caps": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "d4b200_small_limit": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int]),
     "d4b200_phase_profile": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_ulonglong)]),
     "d4b200_measure_fp64_peak": (C.c_int, [_VP, _VP, C.c_size_t, _VP, C.POINTER(C.c_double)]),
 }  # fmt: skip

@@ -694,6 +694,11 @@ int d4b200_class_caps(d4b200_tables_t h, int fp32, int grad, int* caps_out) {
   return 0;
 }
 
+int d4b200_small_limit(d4b200_tables_t h, int fp32, int grad, int model) {
+  if (!h || model < 0 || model > 1) return D4B200_EINVAL;
+  return h->caps[model][fp32 ? 1 : 0][grad ? 1 : 0][NCLASS - 1];
+}
+
 // FP64 vector (DFMA) throughput of the device, measured: the roofline
 // denominator for the FP64-bound kernels (MEASURED_PEAKS.json has no FP64 entry).
 __global__ void k_dfma_peak(double* out, int iters) {

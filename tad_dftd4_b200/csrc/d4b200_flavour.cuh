@@ -11,7 +11,7 @@ struct d4b200_tables;
 
 // Size classes per flavour: X(class, CAP, threads, min CTAs/SM for launch bounds).
 // Caps are bounded by the 227 KB shared-memory budget (Lay<>::total, static_assert).
-#define D4_CLASSES_F64_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 3) X(3, 96, 512, 1) X(4, 128, 512, 1)
+#define D4_CLASSES_F64_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 3) X(3, 96, 512, 1) X(4, 120, 512, 1)
 #define D4_CLASSES_F64_G(X) X(0, 32, 128, 4) X(1, 48, 256, 2) X(2, 64, 512, 1) X(3, 80, 512, 1) X(4, 100, 512, 1)
 #define D4_CLASSES_F32_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 4) X(3, 96, 512, 2) X(4, 128, 512, 1)
 #define D4_CLASSES_F32_G(X) X(0, 32, 128, 6) X(1, 48, 256, 3) X(2, 64, 512, 2) X(3, 96, 512, 1) X(4, 128, 512, 1)

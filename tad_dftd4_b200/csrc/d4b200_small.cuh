@@ -74,7 +74,8 @@ __device__ __forceinline__ T d4_zero_damp_arg(T x, T alp3, bool alp16) {
 constexpr size_t al16(size_t b) { return (b + 15) & ~size_t(15); }
 
 // per-atom T arrays
-enum { AT_X = 0, AT_Y, AT_Z, AT_Q, AT_CN, AT_E, AT_RCOV, AT_SQ, AT_G, AT_DCN, AT_DQ };
+// (the D4 energy kernel only keeps the first five)
+enum { AT_X = 0, AT_Y, AT_Z, AT_RCOV, AT_SQ, AT_Q, AT_CN, AT_E, AT_G, AT_DCN, AT_DQ };
 // per-atom x 7 T arrays
 enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG };
 
@@ -88,23 +89,21 @@ struct Lay {
   static constexpr int CP = CAP * (CAP - 1) / 2;
   static constexpr int AS = a_stride(CAP);
   static constexpr size_t plane_bytes = size_t(3) * CP * sizeof(T);
-  // D4 energy kernel: the weights live on top of the (not yet used) second plane when
-  // they fit; the gradient kernel needs the weights until the end, and the D4S kernels read
-  // them while the planes are being written
-  static constexpr bool wt_alias = !GRAD && !D4S && size_t(2) * NREF * CAP <= size_t(CP);
-  // A/B vector buffers [23][CAP]: D4 energy 1 (Aq, then A0), D4 gradient 4 (Aq, A0, Bq, B0);
+  // D4 energy kernel: the weights never leave the registers of the fused weights phase
+  static constexpr bool wt_alias = false;
+  // A/B vector buffers [23][AS]: D4 energy 2 (Aq, A0), D4 gradient 4 (Aq, A0, Bq, B0);
   // D4S has no per-atom vectors (pair-dependent weights) and only needs room for the
   // per-warp partial sums of the energy triple loop (16 warps)
-  static constexpr size_t abuf_elems = D4S ? (GRAD ? 0 : size_t(16) * CAP) : size_t(GRAD ? 4 : 1) * NFREQ * AS;
-  static constexpr int n_atom = GRAD ? 11 : 8;
-  static constexpr int n_wt = D4S ? (GRAD ? 3 : 2) : (GRAD ? 5 : (wt_alias ? 0 : 2));
+  static constexpr size_t abuf_elems = D4S ? (GRAD ? 0 : size_t(16) * CAP) : size_t(GRAD ? 4 : 2) * NFREQ * AS;
+  static constexpr int n_atom = GRAD ? 11 : (D4S ? 8 : 5);
+  static constexpr int n_wt = D4S ? (GRAD ? 3 : 2) : (GRAD ? 5 : 0);
   static constexpr size_t planes = 0;
   static constexpr size_t abuf = al16(plane_bytes);
   static constexpr size_t atoms = abuf + al16(abuf_elems * sizeof(T));
   static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
   static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
   static constexpr size_t total = ints + al16((2 * CAP + 8) * sizeof(int));
-  static constexpr int scratch_planes = GRAD ? 5 : 2;  // gradient: Gamma, D, E3 shares (2), E2
+  static constexpr int scratch_planes = GRAD ? 5 : 3;  // gradient: Gamma, D, E3 shares (2), E2; energy: E3 shares (2), E2
 };
 
 // Unnormalised Gaussian weights S_a (and dS_a/dcn) of one atom for a given weighting
@@ -350,12 +349,17 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   constexpr int CP = L::CP;
   constexpr int AS = L::AS;
   constexpr int NW = NT / 32;
+  // D4 energy kernel (FP64): once the tensor-path tiles have consumed the A vectors, the
+  // buffer holds the two-body pair energies [CP] followed by the per-warp energy partials
+  // [NW][CAP]; otherwise (too small a buffer, FP32) the pair energies go to the L2 scratch
+  constexpr bool E2S = !GRAD && !D4S && sizeof(T) == 8 &&
+                       size_t(CP) + size_t(NW) * CAP <= size_t(2) * NFREQ * AS;
   extern __shared__ __align__(16) unsigned char smem[];
   T* const pa = reinterpret_cast<T*>(smem + L::planes);
   T* const pP = pa + CP;
   T* const pu = pP + CP;
   T* const Aq = reinterpret_cast<T*>(smem + L::abuf);
-  T* const A0 = GRAD ? Aq + NFREQ * AS : Aq;
+  T* const A0 = Aq + NFREQ * AS;
   T* const Bq = Aq + 2 * NFREQ * AS;  // GRAD only
   T* const B0 = Aq + 3 * NFREQ * AS;  // GRAD only
   T* const at = reinterpret_cast<T*>(smem + L::atoms);
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       ATOM(AT_X)[i] = A.pos[3 * o];
       ATOM(AT_Y)[i] = A.pos[3 * o + 1];
       ATOM(AT_Z)[i] = A.pos[3 * o + 2];
-      ATOM(AT_Q)[i] = A.q[o];
+      if constexpr (GRAD || D4S) ATOM(AT_Q)[i] = A.q[o];
       ATOM(AT_RCOV)[i] = tab.rcov[z];
       ATOM(AT_SQ)[i] = tab.sqrt_r4r2[z];
       if (GRAD) ATOM(AT_G)[i] = A.gin ? A.gin[o] : T(1);
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     D4_ROWS8(i, a) {
       const T cn_row = row_sum2_8(pu, pu, i, a, n);  // every lane of the row holds the sum
       if (a == 0 && i < n) {
-        ATOM(AT_CN)[i] = cn_row;
+        if constexpr (GRAD || D4S) ATOM(AT_CN)[i] = cn_row;
         if (!GRAD && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = cn_row;
       }
       const bool on = i < n && a < NREF;
@@ -524,7 +528,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       const int rc = on ? tab.refc[za] : 0;
       const double rcn = tab.refcn[za], qref = tab.refq[za], z0 = tab.zeta0[za];
       const double gam = tab.gamgc[z], zeff = tab.zeff[z];
-      const double qat = i < n ? (double)ATOM(AT_Q)[i] : 0.0;
+      double qat = 0.0;
+      if (i < n) {
+        if constexpr (GRAD || D4S) qat = (double)ATOM(AT_Q)[i];
+        else qat = (double)A.q[(size_t)b * A.nat + idx[i]];
+      }
       const double d = (double)cn_row - rcn;
       const double arg = (rc > 0 && !D4S) ? P.wf * d * d : 1e300;
       double shift = arg;
@@ -578,34 +586,40 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           WT(WT_Q)[o] = (T)zeta;
           WT(WT_0)[o] = (T)z0;
           if (GRAD) WT(WT_ZGD)[o] = (T)dzeta;
-        } else {
-        WT(WT_Q)[o] = wq_reg;
-        WT(WT_0)[o] = w0_reg;
-        if (GRAD) {
+        } else if (GRAD) {
+          WT(WT_Q)[o] = wq_reg;
+          WT(WT_0)[o] = w0_reg;
           WT(WT_ZGD)[o] = (T)(zeta * dgw);
           WT(WT_Z0GD)[o] = (T)(z0 * dgw);
           WT(WT_DZG)[o] = (T)(dzeta * gw);
         }
+      }
+      if constexpr (!GRAD && !D4S) {
+        if (A.alpha_out) {  // properties mode: alpha_i = sum_a zeta gw alpha_a(0)
+          T al = on ? wq_reg * tab.alpha0[za] : T(0);
+          al += __shfl_xor_sync(0xffffffffu, al, 4);
+          al += __shfl_xor_sync(0xffffffffu, al, 2);
+          al += __shfl_xor_sync(0xffffffffu, al, 1);
+          if (a == 0 && i < n) A.alpha_out[(size_t)b * A.nat + idx[i]] = al;
         }
       }
       if constexpr (!D4S) {
         // weighted polarizability vectors: lane a takes the frequencies a, a + 8, a + 16 and
-        // collects the seven weights of its atom from the neighbouring lanes.  The energy
-        // kernel builds only the charge-scaled flavour now; the q = 0 flavour for the ATM
-        // term goes into the same buffer after the two-body pass.
+        // collects the seven weights of its atom from the neighbouring lanes: the charge-scaled
+        // flavour (two-body term) and the q = 0 flavour (ATM term) together.
         const T* const al = tab.alpha_w + (size_t)z * NREF * NFREQ;
         T sq[3] = {T(0), T(0), T(0)}, s0[3] = {T(0), T(0), T(0)};
 #pragma unroll
         for (int ar = 0; ar < NREF; ++ar) {
           const T vq = __shfl_sync(0xffffffffu, wq_reg, (lane & 24) + ar);
-          const T v0 = GRAD ? __shfl_sync(0xffffffffu, w0_reg, (lane & 24) + ar) : T(0);
+          const T v0 = __shfl_sync(0xffffffffu, w0_reg, (lane & 24) + ar);
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int w = a + 8 * k;
             if (w < NFREQ) {
               const T av = al[ar * NFREQ + w];
               sq[k] += vq * av;
-              if (GRAD) s0[k] += v0 * av;
+              s0[k] += v0 * av;
             }
           }
         }
@@ -615,7 +629,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             const int w = a + 8 * k;
             if (w < NFREQ) {
               Aq[w * AS + i] = sq[k];
-              if (GRAD) A0[w * AS + i] = s0[k];
+              A0[w * AS + i] = s0[k];
             }
           }
         }
@@ -710,21 +724,19 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const int i = t / n, j = t - i * n;
           c6row[(size_t)idx[i] * A.nat + idx[j]] = dot23<T, AS>(Aq, i, j);
         }
-        for (int i = tid; i < n; i += NT) {
-          T al = T(0);
-#pragma unroll
-          for (int a = 0; a < NREF; ++a) al += WT(WT_Q)[i * NREF + a] * tab.alpha0[zs[i] * NREF + a];
-          if (A.alpha_out) A.alpha_out[(size_t)b * A.nat + idx[i]] = al;
-          A.energy[(size_t)b * A.nat + idx[i]] = T(0);
-        }
+        for (int i = tid; i < n; i += NT) A.energy[(size_t)b * A.nat + idx[i]] = T(0);
         continue;
       }
     }
 
-    // ---- phase 4: two-body energy (twobody.py:134-201, rational damping) ---
+    // ---- phase 4 (energy kernel): one pass over the pairs for the two-body energy
+    // (twobody.py:134-201, rational damping) and the ATM pair stash (threebody.py:244-256,
+    // 311-321).  FP64: both pair C6 flavours come from the tensor path (planes `pu`, `pP`).
     if constexpr (!GRAD) {
-      if constexpr (sizeof(T) == 8) {  // C6 of all pairs on the tensor path -> plane `pu`
+      T* const out2 = E2S ? Aq : out0 + 2 * CP;  // two-body pair energies (row sums in the final assembly)
+      if constexpr (sizeof(T) == 8) {
         c6_tiles<AS>(Aq, pu, tab.pij, n, warp, lane, NW);
+        if (P.has_atm) c6_tiles<AS>(A0, pP, tab.pij, n, warp, lane, NW);
         __syncthreads();
       }
 #pragma unroll 2
@@ -732,13 +744,13 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         int i, j;
         pair_lookup(tab.pij, p, i, j);
         const T r2 = pa[p];
+        const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
+        const T R0 = P.a1 * ss + P.a2;
         T e = T(0);
         if (r2 <= P.disp2_sq) {
           T c6;
           if constexpr (sizeof(T) == 8) c6 = pu[p];
           else c6 = dot23<T, AS>(Aq, i, j);
-          const T ss = ATOM(AT_SQ)[i] * ATOM(AT_SQ)[j];
-          const T R0 = P.a1 * ss + P.a2;
           const T qq = ss * ss;  // = 3 r4r2_i r4r2_j
           const T r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4;
           const T R2 = R0 * R0, R4 = R2 * R2, R6 = R4 * R2, R8 = R4 * R4;
@@ -746,29 +758,26 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           if (P.s10k != T(0)) F += P.s10k * qq * qq * d4_rcp(r8 * r2 + R8 * R2);
           e = c6 * F;
         }
-        pu[p] = e;  // the weights (aliased layout) sit in plane `pP`
-      }
-      __syncthreads();  // all reads of Aq done: the buffer becomes A0
-      PHASE(5);
-      D4_ROWS8(i, sub) {
-        const T e2 = row_sum2_8(pu, pu, i, sub, n);
-        if (sub == 0 && i < n) ATOM(AT_E)[i] = T(-0.5) * e2;
-      }
-      if (P.has_atm) {
-        for (int t = tid; t < NFREQ * n; t += NT) {
-          const int i = t / NFREQ, w = t - i * NFREQ;
-          const T* al = tab.alpha_w + (size_t)zs[i] * NREF * NFREQ + w;
-          T s0 = T(0);
-#pragma unroll
-          for (int a = 0; a < NREF; ++a) s0 += WT(WT_0)[i * NREF + a] * al[a * NFREQ];
-          A0[w * AS + i] = s0;
+        out2[p] = e;
+        if (P.has_atm) {
+          T c60;
+          if constexpr (sizeof(T) == 8) c60 = pP[p];
+          else c60 = dot23<T, AS>(A0, i, j);
+          const T r = d4_sqrt(r2);
+          const T rinv = d4_rcp(r);
+          const T ri2 = rinv * rinv;
+          const bool inside = r2 <= P.disp3_sq;
+          if (!inside) misc[2] = 1;
+          pa[p] = inside ? r2 : -r2;
+          pP[p] = P.fac9 * d4_sqrt(fabs(c60)) * (ri2 * ri2 * rinv);  // P' = P / r^2
+          pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
         }
       }
       __syncthreads();
-      PHASE(6);
-    }
-
-    // ---- phase 5: ATM pair stash (threebody.py:244-256, 311-321) -----------
+      PHASE(5);
+      open = misc[2] != 0;
+    } else {
+    // ---- phase 5 (gradient kernel): ATM pair stash --------------------------
     if constexpr (sizeof(T) == 8) {  // C6(q = 0) of all pairs on the tensor path -> plane `pP`
       if (P.has_atm) {
         c6_tiles<AS>(A0, pP, tab.pij, n, warp, lane, NW);
@@ -776,8 +785,6 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
     }
     if (P.has_atm) {
-      // NB: in the aliased layout the stash overwrites the weights, which are
-      // dead by now (WT lives in plane `pP`)
 #pragma unroll 2
       for (int p = tid; p < np; p += NT) {
         int i, j;
@@ -802,6 +809,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       PHASE(7);
       open = misc[2] != 0;
     }
+    }  // gradient kernel
     }  // !D4S
     if (P.has_atm) {
       // ---- phase 6: triple loop ---------------------------------------------
@@ -864,7 +872,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         // entry in registers) and sweeps the top atom i in blocks of eight; the
         // shares of atoms j and k accumulate in lane registers, the share of
         // atom i is reduced over the lanes with a transposed shuffle reduction.
-        T* const Tw = Aq + warp * CAP;  // A vectors are dead: per-warp E_i partials
+        T* const Tw = Aq + (E2S ? CP : 0) + warp * CAP;  // A vectors are dead: per-warp E_i partials
         for (int i = lane; i < n; i += 32) Tw[i] = T(0);
         __syncwarp();
         const int nchunks = (np + 31) >> 5;
@@ -904,9 +912,18 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             const int iw = i0 + (lane >> 2);
             if ((lane & 3) == 0 && iw < n) Tw[iw] += y;
           }
-          if (valid) {
-            out0[p] = accJ;
-            out1[p] = open ? accK : accJ;
+          // shares of the bottom pairs -> per-warp partials: row by row of the chunk (the
+          // lanes of one row j have distinct k), the j share as a warp sum
+          {
+            const T shareK = open ? accK : accJ;
+            const int jtop = __reduce_max_sync(0xffffffffu, valid ? j : 0);
+            for (int jj = jmin; jj <= jtop; ++jj) {
+              const bool mine = valid && j == jj;
+              const T sj = warp_sum(mine ? accJ : T(0));
+              if (mine) Tw[k] += shareK;
+              if (lane == 0) Tw[jj] += sj;
+              __syncwarp();
+            }
           }
         }
         __syncthreads();
@@ -923,14 +940,17 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     if constexpr (!GRAD) {
       // ---- final assembly: E_i = E2_i + scale * (ATM shares) ------------------
       const T scale = open ? T(1) : T(2);  // closed triples: every atom has multiplicity 2
+      const T* const e2p = E2S ? Aq : out0 + 2 * CP;
+      const T* const Tall = Aq + (E2S ? CP : 0);
       D4_ROWS8(i, sub) {
-        T s3 = T(0);
-        if (P.has_atm) s3 = row_sum2_8(out0, out1, i, sub, n);
+        T e = T(0);
+        if constexpr (!D4S) e = T(-0.5) * row_sum2_8(e2p, e2p, i, sub, n);
         if (sub == 0 && i < n) {
-          T e = ATOM(AT_E)[i];
+          if constexpr (D4S) e = ATOM(AT_E)[i];
           if (P.has_atm) {
+            T s3 = T(0);
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s3 += Aq[w * CAP + i];
+            for (int w = 0; w < NW; ++w) s3 += Tall[w * CAP + i];
             e += scale * s3;
           }
           A.energy[(size_t)b * A.nat + idx[i]] = e;

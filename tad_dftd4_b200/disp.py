@@ -71,6 +71,7 @@ class _Engine:
         )
         self.lib = lib
         self.handle = handle
+        self.limits: dict[tuple[bool, bool, int], int] = {}
         self.device = torch.device("cuda", index)
         self._ws: Tensor | None = None
 
@@ -294,13 +295,16 @@ def _resolve_model(model: Any) -> tuple[int, float, float, float]:
     raise NotImplementedError(f"model instance of type {name} is outside the accelerated D4 hot path")
 
 
-def _small_limit(dtype: torch.dtype, grad: bool, model_id: int) -> int:
+def _small_limit(engine: "_Engine", dtype: torch.dtype, grad: bool, model_id: int) -> int:
     """Largest structure of the one-CTA-per-structure kernels (csrc/d4b200_flavour.cuh)."""
-    if dtype == torch.float32:
-        return 128
-    if model_id == 1:
-        return 120
-    return 100 if grad else 128
+    key = (dtype == torch.float32, bool(grad), int(model_id))
+    lim = engine.limits.get(key)
+    if lim is None:
+        lim = int(engine.lib.d4b200_small_limit(engine.handle, int(key[0]), int(key[1]), key[2]))
+        if lim <= 0:
+            raise _lib.D4B200Error(f"d4b200_small_limit failed with code {lim}")
+        engine.limits[key] = lim
+    return lim
 
 
 def _compact_front(numbers: Tensor, positions: Tensor, q: Tensor, width: int):
@@ -407,7 +411,7 @@ def dftd4(
     pos2 = positions.reshape(-1, nat, 3).contiguous()
     q2 = q.to(positions.dtype).reshape(-1, nat).contiguous()
 
-    limit = _small_limit(positions.dtype, positions.requires_grad or q.requires_grad, model_id)
+    limit = _small_limit(engine, positions.dtype, positions.requires_grad or q.requires_grad, model_id)
     if nat > limit:
         # padded width beyond the one-CTA-per-structure kernels: structures that really
         # are that large go through the tiled kernels one by one (one host sync)
@@ -472,7 +476,7 @@ def dftd4_host(
     dev = torch.device("cuda", device) if isinstance(device, int) else device
     engine = _Engine.get(dev, ga, gc)
     nat = numbers.shape[-1]
-    if nat > _small_limit(positions.dtype, False, model_id):
+    if nat > _small_limit(engine, positions.dtype, False, model_id):
         raise NotImplementedError("dftd4_host handles batches of small structures; use dftd4 for large ones")
     num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
     pos2 = positions.reshape(-1, nat, 3).contiguous()
