@@ -41,15 +41,14 @@ __device__ __forceinline__ float d4_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double d4_erfc_cut(double) { return 6.2; }
 __device__ __forceinline__ float d4_erfc_cut(float) { return 4.6f; }
 
-// Reciprocal without the slow-path branch of IEEE division: all operands here
-// are normal, positive numbers.  MUFU.RCP64H seed + two Newton steps (<= 1 ulp).
+// Reciprocal without the slow-path branch of IEEE division: all operands here are normal,
+// positive numbers.  MUFU.RCP64H seed (~20 bits) + one cubically convergent step
+// y (1 + e + e^2), e = 1 - x y: three FMAs, relative error ~ e^3 < 1e-17.
 __device__ __forceinline__ double d4_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-x, y, 1.0);
+  return fma(y, fma(e, e, e), y);
 }
 __device__ __forceinline__ float d4_rcp(float x) { return __frcp_rn(x); }
 
