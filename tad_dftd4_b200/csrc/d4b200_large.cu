@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(256, 2) large_atm(LargeArgs<T> A) {
         for (int w = 0; w < NFREQ; ++w) c6 += cA0[j * AVEC + w] * ax[w];
         const T R0 = P.a1 * csq[j] * A.tab.sqrt_r4r2[(int)A.numbers[x]] + P.a2;
         a = r2;
-        Pv = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+        const T ri2 = rinv * rinv;
+        Pv = P.fac9 * d4_sqrt(fabs(c6)) * (ri2 * ri2 * rinv);  // P' = P / r^2 (see d4b200_small.cuh)
         uv = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
       }
       cst[((size_t)j * 3 + 0) * A.ucap + u] = a;
@@ -441,22 +442,21 @@ __global__ void __launch_bounds__(256, 2) large_atm(LargeArgs<T> A) {
 #pragma unroll
             for (int w = 0; w < NFREQ; ++w) c6 += ai[w] * ak[w];
             const T R0 = P.a1 * tsq[0][row] * tsq[1][lane] + P.a2;
-            const T Pik = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+            const T ri2 = rinv * rinv, c2 = c * c;
+            const T Pik = P.fac9 * d4_sqrt(fabs(c6)) * (ri2 * ri2 * rinv);
             const T uik = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
-            unsigned both = mi & mk;
+            // all centres of the group, branch-free: where i or k is not a neighbour of centre j
+            // the stash holds (r^2, P', u) = (1, 0, 0) and the term is exactly zero
             T esum = T(0);
-#pragma unroll 4
+#pragma unroll 8
             for (int j = 0; j < GROUP; ++j) {
-              if (both >> j & 1u) {
-                const T a = tst[0][j][0][row], b = tst[1][j][0][lane];  // r_ji^2, r_jk^2
-                const T X = a + b - c, Y = a - b + c, Z = b + c - a;
-                const T abc = a * b * c;
-                const T t = tst[0][j][2][row] * tst[1][j][2][lane] * uik;
-                const T d = T(1) + T(6) * t;
-                const T inv = d4_rcp(abc * d);
-                esum += (T(0.375) * (X * Y * Z) * (inv * d) + T(1)) *
-                        (tst[0][j][1][row] * tst[1][j][1][lane] * Pik * (inv * abc));
-              }
+              const T a = tst[0][j][0][row], b = tst[1][j][0][lane];  // r_ji^2, r_jk^2
+              const T t1 = a - b, t2 = a + b;
+              const T s = fma(-t1, t1, c2) * (t2 - c);
+              const T abc = (a * b) * c;
+              const T t = tst[0][j][2][row] * tst[1][j][2][lane] * uik;
+              const T pp = tst[0][j][1][row] * tst[1][j][1][lane] * Pik;
+              esum += (pp * fma(T(0.375), s, abc)) * d4_rcp(fma(T(6), t, T(1)));
             }
             rowacc = esum;
             colacc += esum;
