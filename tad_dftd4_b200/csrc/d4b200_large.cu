@@ -392,34 +392,36 @@ __global__ void __launch_bounds__(256, 2) large_atm(LargeArgs<T> A) {
     __syncthreads();
 
     const int ntile = (nU + TILE - 1) / TILE;
+    // stage one tile of the union list: atoms, A0 vectors, centre stash
+    auto stage = [&](int side, int tileno) {
+      for (int l = tid; l < TILE; l += 256) {
+        const int u = tileno * TILE + l;
+        const bool ok = u < nU;
+        const int x = ok ? list[u] : 0;
+        tidx[side][l] = ok ? x : -1;
+        tmask[side][l] = ok ? masks[u] : 0u;
+        tpx[side][l] = ok ? A.pos[3 * x] : T(0);
+        tpy[side][l] = ok ? A.pos[3 * x + 1] : T(0);
+        tpz[side][l] = ok ? A.pos[3 * x + 2] : T(0);
+        tsq[side][l] = ok ? A.tab.sqrt_r4r2[(int)A.numbers[x]] : T(0);
+      }
+      for (int r = tid; r < TILE * AVEC; r += 256) {
+        const int l = r / AVEC, w = r - l * AVEC;
+        const int u = tileno * TILE + l;
+        tA0[side][l * (AVEC + 1) + w] = u < nU ? A.a0[(size_t)list[u] * AVEC + w] : T(0);
+      }
+      for (int r = tid; r < GROUP * 3 * TILE; r += 256) {
+        const int jc = r / TILE, l = r - jc * TILE;  // jc = j*3 + component
+        const int u = tileno * TILE + l;
+        (&tst[side][0][0][0])[jc * TILE + l] = u < nU ? cst[(size_t)jc * A.ucap + u] : T(0);
+      }
+    };
     for (int tx = 0; tx < ntile; ++tx) {
+      __syncthreads();
+      stage(0, tx);  // X rows: once per row tile
       for (int ty = tx; ty < ntile; ++ty) {
-        __syncthreads();
-        // ---- stage the two tiles (side 0 = X rows, side 1 = Y columns)
-        for (int t = tid; t < 2 * TILE; t += 256) {
-          const int side = t / TILE, l = t - side * TILE;
-          const int u = (side == 0 ? tx : ty) * TILE + l;
-          const bool ok = u < nU;
-          const int x = ok ? list[u] : 0;
-          tidx[side][l] = ok ? x : -1;
-          tmask[side][l] = ok ? masks[u] : 0u;
-          tpx[side][l] = ok ? A.pos[3 * x] : T(0);
-          tpy[side][l] = ok ? A.pos[3 * x + 1] : T(0);
-          tpz[side][l] = ok ? A.pos[3 * x + 2] : T(0);
-          tsq[side][l] = ok ? A.tab.sqrt_r4r2[(int)A.numbers[x]] : T(0);
-        }
-        for (int t = tid; t < 2 * TILE * AVEC; t += 256) {
-          const int side = t / (TILE * AVEC), r = t - side * TILE * AVEC;
-          const int l = r / AVEC, w = r - l * AVEC;
-          const int u = (side == 0 ? tx : ty) * TILE + l;
-          tA0[side][l * (AVEC + 1) + w] = u < nU ? A.a0[(size_t)list[u] * AVEC + w] : T(0);
-        }
-        for (int t = tid; t < 2 * GROUP * 3 * TILE; t += 256) {
-          const int side = t / (GROUP * 3 * TILE), r = t - side * GROUP * 3 * TILE;
-          const int jc = r / TILE, l = r - jc * TILE;  // jc = j*3 + component
-          const int u = (side == 0 ? tx : ty) * TILE + l;
-          (&tst[side][0][0][0])[jc * TILE + l] = u < nU ? cst[(size_t)jc * A.ucap + u] : T(0);
-        }
+        if (ty != tx) __syncthreads();
+        stage(1, ty);  // Y columns
         __syncthreads();
         // ---- evaluate: lane = column k of Y, warp rows 4w..4w+3 of X
         const unsigned mk = tmask[1][lane];
