@@ -60,6 +60,7 @@ struct LargeArgs {
   int nat, ngroups, ucap;
   int row_begin, row_end;      // two-body rows of this rank
   int group_begin, group_end;  // ATM centre groups of this rank
+  int nslice;                  // work item = (group, slice of its row tiles): nslice items per group
   Tables<T> tab;
   Par<T> par;
 };
@@ -344,9 +345,10 @@ __global__ void __launch_bounds__(256, 2) large_atm(LargeArgs<T> A) {
 
   while (true) {
     __syncthreads();
-    if (tid == 0) gcur = A.group_begin + atomicAdd(A.queue, 1);
+    if (tid == 0) gcur = atomicAdd(A.queue, 1);
     __syncthreads();
-    const int g = gcur;
+    // work item = (centre group, slice): the row tiles tx = slice, slice + nslice, ... of the group
+    const int g = A.group_begin + gcur / A.nslice, slice = gcur % A.nslice;
     if (g >= A.group_end) break;
     const int nU = A.ucount[g];
     const int* list = A.ulist + (size_t)g * A.ucap;
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(256, 2) large_atm(LargeArgs<T> A) {
         (&tst[side][0][0][0])[jc * TILE + l] = u < nU ? cst[(size_t)jc * A.ucap + u] : T(0);
       }
     };
-    for (int tx = 0; tx < ntile; ++tx) {
+    for (int tx = slice; tx < ntile; tx += A.nslice) {
       __syncthreads();
       stage(0, tx);  // X rows: once per row tile
       for (int ty = tx; ty < ntile; ++ty) {
@@ -665,9 +667,9 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
 
   while (true) {
     __syncthreads();
-    if (tid == 0) *gcur = A.group_begin + atomicAdd(A.queue, 1);
+    if (tid == 0) *gcur = atomicAdd(A.queue, 1);
     __syncthreads();
-    const int g = *gcur;
+    const int g = A.group_begin + *gcur / A.nslice, slice = *gcur % A.nslice;
     if (g >= A.group_end) break;
     const int nU = A.ucount[g];
     const int* list = A.ulist + (size_t)g * A.ucap;
@@ -723,7 +725,7 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
     __syncthreads();
 
     const int ntile = (nU + TILE - 1) / TILE;
-    for (int tx = 0; tx < ntile; ++tx) {
+    for (int tx = slice; tx < ntile; tx += A.nslice) {
       for (int ty = tx; ty < ntile; ++ty) {
         __syncthreads();
         for (int t = tid; t < 2 * TILE; t += 512) {
@@ -1000,8 +1002,13 @@ int run_large(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t
     if (group_cost_out)
       cudaMemcpyAsync(group_cost_out, A.ucount, ng * sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (energy && A.group_end > A.group_begin) {
+      // about six work items per resident CTA: groups are cut into row-tile slices when a
+      // rank owns too few of them (multi-GPU runs, mid-size systems)
+      const int ngl = A.group_end - A.group_begin;
+      A.nslice = (6 * nctas + ngl - 1) / ngl;
+      if (A.nslice > 16) A.nslice = 16;
       int grid = nctas;
-      if (grid > A.group_end - A.group_begin) grid = A.group_end - A.group_begin;
+      if (grid > ngl * A.nslice) grid = ngl * A.nslice;
       large_atm<T><<<grid, 256, 0, st>>>(A);
     }
   }
@@ -1094,8 +1101,11 @@ int run_large_grad(d4b200_tables* h, const d4b200_params* par, int nat, const in
   }
   if (A.par.has_atm && A.group_end > A.group_begin) {
     large_union<T><<<ng, 256, 0, st>>>(A);
+    const int ngl = A.group_end - A.group_begin;
+    A.nslice = (6 * nctas + ngl - 1) / ngl;
+    if (A.nslice > 16) A.nslice = 16;
     int grid = nctas;
-    if (grid > A.group_end - A.group_begin) grid = A.group_end - A.group_begin;
+    if (grid > ngl * A.nslice) grid = ngl * A.nslice;
     large_atm_grad<T><<<grid, 512, atm_grad_smem<T>(), st>>>(A);
   }
   cudaError_t e = cudaGetLastError();
