@@ -33,10 +33,26 @@ __device__ __forceinline__ double d4_exp(double x) { return exp(x); }
 __device__ __forceinline__ float d4_exp(float x) { return expf(x); }
 __device__ __forceinline__ double d4_log(double x) { return log(x); }
 __device__ __forceinline__ float d4_log(float x) { return logf(x); }
-__device__ __forceinline__ double d4_cbrt(double x) { return cbrt(x); }
-__device__ __forceinline__ float d4_cbrt(float x) { return cbrtf(x); }
 __device__ __forceinline__ double d4_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float d4_sqrt(float x) { return sqrtf(x); }
+// 1/sqrt(x) for normal positive x without the special-case branches of sqrt()/division:
+// MUFU.RSQ64H seed (~20 bits) + one cubically convergent step y (1 + h/2 + 3 h^2/8),
+// h = 1 - x y^2 (relative error ~ h^3 < 1e-17).  sqrt(x) = x rsqrt(x).
+__device__ __forceinline__ double d4_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = fma(-(x * y), y, 1.0);
+  return fma(y * h, fma(0.375, h, 0.5), y);
+}
+__device__ __forceinline__ float d4_rsqrt(float x) { return rsqrtf(x); }
+// x^(-1/3) for normal positive x: float seed 2^(-log2(x)/3) from the MUFU units, one cubically
+// convergent step z (1 + r/3 + 2 r^2/9), r = 1 - x z^3 (seed error ~1e-6 -> ~1e-17)
+__device__ __forceinline__ double d4_rcbrt(double x) {
+  const double z = (double)exp2f(-0.33333334f * __log2f((float)x));
+  const double r = fma(-x, z * z * z, 1.0);
+  return fma(z * r, fma(0.2222222222222222, r, 0.3333333333333333), z);
+}
+__device__ __forceinline__ float d4_rcbrt(float x) { return rcbrtf(x); }
 // erfc(x) is below one ulp of the coordination number beyond this argument
 __device__ __forceinline__ double d4_erfc_cut(double) { return 6.2; }
 __device__ __forceinline__ float d4_erfc_cut(float) { return 4.6f; }
@@ -59,14 +75,24 @@ __device__ __forceinline__ double d4_eps<double>() { return 2.220446049250313e-1
 template <>
 __device__ __forceinline__ float d4_eps<float>() { return 1.1920929e-07f; }
 
-// (R0/r)^(alp/3): x^5 cbrt(x) for the default alp = 16, exp(y log x) otherwise
+// (R0/r)^(alp/3): x^6 (x^(-1/3))^2 for the default alp = 16, exp(y log x) otherwise
 template <typename T>
 __device__ __forceinline__ T d4_zero_damp_arg(T x, T alp3, bool alp16) {
   if (alp16) {
-    const T x2 = x * x;
-    return x2 * x2 * x * d4_cbrt(x);
+    const T z = d4_rcbrt(x);
+    const T x3 = x * x * x;
+    return (x3 * x3) * (z * z);
   }
   return d4_exp(alp3 * d4_log(x));
+}
+
+// stash entries of one pair from r^2, |C6(q=0)| and R0: 1/r, P' = fac9 sqrt|C6| / r^5
+template <typename T>
+__device__ __forceinline__ T d4_stash_p(T fac9, T c60, T rinv) {
+  const T ac = fabs(c60);
+  const T ri2 = rinv * rinv;
+  const T sq = ac > T(1e-30) ? ac * d4_rsqrt(ac) : T(0);
+  return fac9 * sq * (ri2 * ri2 * rinv);
 }
 
 // ---------------------------------------------------------------- smem layout
@@ -147,7 +173,9 @@ __device__ __forceinline__ void d4s_gauss(const double* __restrict__ refcn, cons
 // p -> (hi, lo) with hi > lo and p = hi(hi-1)/2 + lo: one L1-resident table lookup
 // (Tables::pij) instead of a float square root plus corrections in every pair pass
 __device__ __forceinline__ void pair_lookup(const unsigned short* __restrict__ pij, int p, int& hi, int& lo) {
-  const unsigned v = __ldg(pij + p);
+  unsigned short v16;  // keep the table resident in the (small) L1 next to the streaming traffic
+  asm("ld.global.nc.L1::evict_last.u16 %0, [%1];" : "=h"(v16) : "l"(pij + p));
+  const unsigned v = v16;
   hi = (int)(v >> 8);
   lo = (int)(v & 255u);
 }
@@ -500,7 +528,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const int p = near[t];
         int i, j;
         pair_lookup(tab.pij, p, i, j);
-        const T r = d4_sqrt(pa[p]);
+        const T r2n = pa[p];
+        const T r = r2n * d4_rsqrt(r2n);
         const T r0 = ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j];
         const T xx = T(7.5) * (r * d4_rcp(r0) - T(1));
         if (xx < d4_erfc_cut(T(0))) pu[p] = tab.den[zs[i] * NELEM + zs[j]] * T(0.5) * d4_erfc(xx);
@@ -691,15 +720,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           out0[p] = e;
         }
         if (P.has_atm) {
-          const T r = d4_sqrt(r2);
-          const T rinv = d4_rcp(r);
+          const T rinv = d4_rsqrt(r2);
           const bool inside = r2 <= P.disp3_sq;
           if (!inside) misc[2] = 1;
           pa[p] = inside ? r2 : -r2;
-          {
-            const T ri2 = rinv * rinv;
-            pP[p] = P.fac9 * d4_sqrt(fabs(c60)) * (ri2 * ri2 * rinv);  // P' = P / r^2
-          }
+          pP[p] = d4_stash_p(P.fac9, c60, rinv);  // P' = P / r^2
           pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
         }
       }
@@ -762,13 +787,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           T c60;
           if constexpr (sizeof(T) == 8) c60 = pP[p];
           else c60 = dot23<T, AS>(A0, i, j);
-          const T r = d4_sqrt(r2);
-          const T rinv = d4_rcp(r);
-          const T ri2 = rinv * rinv;
+          const T rinv = d4_rsqrt(r2);
           const bool inside = r2 <= P.disp3_sq;
           if (!inside) misc[2] = 1;
           pa[p] = inside ? r2 : -r2;
-          pP[p] = P.fac9 * d4_sqrt(fabs(c60)) * (ri2 * ri2 * rinv);  // P' = P / r^2
+          pP[p] = d4_stash_p(P.fac9, c60, rinv);  // P' = P / r^2
           pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
         }
       }
@@ -789,8 +812,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         int i, j;
         pair_lookup(tab.pij, p, i, j);
         const T r2 = pa[p];
-        const T r = d4_sqrt(r2);
-        const T rinv = d4_rcp(r);
+        const T rinv = d4_rsqrt(r2);
         T c6;
         if constexpr (sizeof(T) == 8) c6 = pP[p];
         else c6 = dot23<T, AS>(A0, i, j);
@@ -798,10 +820,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const bool inside = r2 <= P.disp3_sq;
         if (!inside) misc[2] = 1;
         pa[p] = inside ? r2 : -r2;
-        {
-          const T ri2 = rinv * rinv;
-          pP[p] = P.fac9 * d4_sqrt(fabs(c6)) * (ri2 * ri2 * rinv);  // P' = P / r^2
-        }
+        pP[p] = d4_stash_p(P.fac9, c6, rinv);  // P' = P / r^2
         pu[p] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
       }
       __syncthreads();
@@ -1191,13 +1210,14 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         const T dz = ATOM(AT_Z)[i] - ATOM(AT_Z)[j];
         const T r2 = dx * dx + dy * dy + dz * dz;
         if (r2 <= P.cn_sq) {
-          const T r = d4_sqrt(r2);
+          const T rinv = d4_rsqrt(r2);
+          const T r = r2 * rinv;
           const T r0inv = d4_rcp(ATOM(AT_RCOV)[i] + ATOM(AT_RCOV)[j]);
           const T xx = T(7.5) * (r * r0inv - T(1));
           if (fabs(xx) < T(8.7)) {  // exp(-x^2) < 1e-32 beyond
             const T dcn = -tab.den[zs[i] * NELEM + zs[j]] * T(7.5) * T(0.5641895835477563) *
                           r0inv * d4_exp(-xx * xx);
-            pu[p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn * d4_rcp(r);
+            pu[p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn * rinv;
           }
         }
       }
