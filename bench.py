@@ -59,6 +59,11 @@ WORKLOADS = {
                name="4096 synthetic 20-60-atom organics, D4 energy (two-body + ATM), padded to 60"),
     "c3": dict(nbatch=1024, lo=100, hi=100, seed=3, grad=True,
                name="1024 synthetic 100-atom molecules, D4 energy + analytic gradient incl. ATM"),
+    "c5": dict(nbatch=1024, lo=100, hi=100, seed=3, grad=True, model="d4s",
+               name="1024 synthetic 100-atom molecules (the C3 inputs), D4S model, energy + analytic gradient "
+                    "incl. ATM; --dtype f32|f64, error against the float64 oracle reported in cpu_baseline.parity"),
+    "c1": dict(single=True, nbatch=1, grad=False, seed=0,
+               name="examples/single.py 12-atom molecule, D4 energy, PBE0 parameters (one structure: latency)"),
     "c4": dict(nmol=6667, seed=4, grad=False, large=True,
                name="single 20001-atom water cluster (6667 H2O), D4 energy, default 60/40/30 Bohr cutoffs, "
                     "row-block split over the GPUs + all-reduce"),
@@ -102,8 +107,24 @@ def oracle():
     return d4_oracle
 
 
+SINGLE_Z = [6, 6, 6, 6, 7, 6, 16, 1, 1, 1, 1, 1]  # examples/single.py:7-27 of the reference
+SINGLE_XYZ = [
+    [-2.56745685564671, -0.02509985979910, 0.0], [-1.39177582455797, +2.27696188880014, 0.0],
+    [+1.27784995624894, +2.45107479759386, 0.0], [+2.62801937615793, +0.25927727028120, 0.0],
+    [+1.41097033661123, -1.99890996077412, 0.0], [-1.17186102298849, -2.34220576284180, 0.0],
+    [-2.39505990368378, -5.22635838332362, 0.0], [+2.41961980455457, -3.62158019253045, 0.0],
+    [-2.51744374846065, +3.98181713686746, 0.0], [+2.24269048384775, +4.24389473203647, 0.0],
+    [+4.66488984573956, +0.17907568006409, 0.0], [-4.60044244782237, -0.17794734637413, 0.0],
+]  # fmt: skip
+
+
 def make_batch(wl: dict, rank: int):
     orc = oracle()
+    if wl.get("single"):
+        numbers = torch.tensor([SINGLE_Z])
+        positions = torch.tensor([SINGLE_XYZ], dtype=torch.float64)
+        q = 0.1 * torch.randn(numbers.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+        return numbers, positions, q - q.mean()
     rng = np.random.default_rng(wl["seed"] + 1000 * rank)
     sizes = rng.integers(wl["lo"], wl["hi"] + 1, size=wl["nbatch"])
     return orc.organic_batch_parallel(sizes, seed=wl["seed"] + 1000 * rank)
@@ -183,18 +204,29 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------
-def cpu_time_sample(wl: dict, numbers, positions, q, nsample: int, chunk: int):
+def cpu_time_sample(wl: dict, numbers, positions, q, nsample: int, chunk: int, eeq: bool = False, keep=None):
     """Seconds the dense CPU formulation needs for ``nsample`` structures of the
-    workload (model rebuilt per call like the reference, dispersion/base.py:363)."""
+    workload (model rebuilt per call like the reference, dispersion/base.py:363).
+    ``keep`` (a list) receives the (energy, gradient) of every chunk for the parity report."""
     orc = oracle()
+    model = wl.get("model", "d4")
     torch.set_num_threads(os.cpu_count() or 1)
+    if eeq:
+        import eeq_oracle
     t0 = time.perf_counter()
     for s in range(0, nsample, chunk):
         sl = slice(s, min(s + chunk, nsample))
-        if wl["grad"]:
-            orc.energy_and_gradient(numbers[sl], positions[sl], PBE0, q[sl])
+        if eeq:  # default q=None path of the reference: EEQ charges on the tape
+            pos = positions[sl].clone().requires_grad_(wl["grad"])
+            e = orc.dftd4(numbers[sl], pos, PBE0, eeq_oracle.get_eeq_charges(numbers[sl], pos, 0.0), model=model)
+            g = torch.autograd.grad(e.sum(), pos)[0] if wl["grad"] else None
+            e = e.detach()
+        elif wl["grad"]:
+            e, g = orc.energy_and_gradient(numbers[sl], positions[sl], PBE0, q[sl], model=model)
         else:
-            orc.dftd4(numbers[sl], positions[sl], PBE0, q[sl])
+            e, g = orc.dftd4(numbers[sl], positions[sl], PBE0, q[sl], model=model), None
+        if keep is not None:
+            keep.append((e, g))
     return time.perf_counter() - t0
 
 
@@ -203,10 +235,10 @@ def run_reference(args, wl, rank, world):
         return
     numbers, positions, q = make_batch(wl, 0)
     chunk = 8 if wl["grad"] else 64
-    nsample = chunk * (2 if wl["grad"] else 2)
+    nsample = min(chunk * 2, numbers.shape[0])
     times = []
     for it in range(args.warmup + args.steps):
-        dt = cpu_time_sample(wl, numbers, positions, q, nsample, chunk)
+        dt = cpu_time_sample(wl, numbers, positions, q, nsample, chunk, eeq=args.eeq)
         if it >= args.warmup:
             times.append(dt)
     sec = sum(times) / len(times)
@@ -256,13 +288,19 @@ def run_b200(args, wl, rank, world, local_rank):
     numbers, positions, q = numbers_h.to(dev), positions_h.to(dev), q_h.to(dev)
     d4.set_checks(False)  # fully asynchronous steps; parity is the tests' job
 
+    model = wl.get("model", "d4")
+    use_eeq = bool(args.eeq)  # q=None: EEQ charges computed on device inside the step (and on the tape)
+
+    def call(n, p, qq):
+        return d4.dftd4(n, p, 0.0, PBE0, q=None if use_eeq else qq, model=model)
+
     def step_resident():
         if wl["grad"]:
             pos = positions.detach().requires_grad_(True)
-            e = d4.dftd4(numbers, pos, 0.0, PBE0, q=q)
+            e = call(numbers, pos, q)
             (g,) = torch.autograd.grad(e.sum(), pos)
             return e, g
-        return d4.dftd4(numbers, positions, 0.0, PBE0, q=q), None
+        return call(numbers, positions, q), None
 
     out_e = torch.empty(numbers_h.shape, dtype=dtype).pin_memory()
     out_g = torch.empty(positions_h.shape, dtype=dtype).pin_memory() if wl["grad"] else None
@@ -270,24 +308,26 @@ def run_b200(args, wl, rank, world, local_rank):
     def step_e2e_host():
         # public host-buffer API: pinned host tensors in, pinned host tensor out; the C ABI
         # pipelines H2D copy / kernels / D2H copy in chunks (d4b200_energy_host_*)
-        d4.dftd4_host(numbers_h, positions_h, 0.0, PBE0, q=q_h, device=dev, out=out_e)
+        d4.dftd4_host(numbers_h, positions_h, 0.0, PBE0, q=q_h, model=model, device=dev, out=out_e)
+
+    host_api = not wl["grad"] and not use_eeq
 
     def step_e2e():
-        if not wl["grad"]:
+        if host_api:
             return step_e2e_host()
         n = numbers_h.to(dev, non_blocking=True)
         p = positions_h.to(dev, non_blocking=True)
-        qq = q_h.to(dev, non_blocking=True)
+        qq = None if use_eeq else q_h.to(dev, non_blocking=True)
         if wl["grad"]:
             p.requires_grad_(True)
-            e = d4.dftd4(n, p, 0.0, PBE0, q=qq)
+            e = call(n, p, qq)
             (g,) = torch.autograd.grad(e.sum(), p)
             out_g.copy_(g, non_blocking=True)
         else:
-            e = d4.dftd4(n, p, 0.0, PBE0, q=qq)
+            e = call(n, p, qq)
         out_e.copy_(e.detach(), non_blocking=True)
 
-    h2d = numbers_h.numel() * 8 + (positions_h.numel() + q_h.numel()) * positions_h.element_size()
+    h2d = numbers_h.numel() * 8 + (positions_h.numel() + (0 if use_eeq else q_h.numel())) * positions_h.element_size()
     d2h = out_e.numel() * out_e.element_size() + (out_g.numel() * out_g.element_size() if wl["grad"] else 0)
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
@@ -318,13 +358,13 @@ def run_b200(args, wl, rank, world, local_rank):
     engine = _Engine.get(dev, 3.0, 2.0)
     lib = _lib.load()
     step_resident()  # builds tables / workspace
-    n0 = int(lib.d4b200_total_launch_count())
+    n0 = int(lib.d4b200_total_launch_count()) + int(lib.d4b200_eeq_launch_count())
     step_resident()
-    launches_per_step = int(lib.d4b200_total_launch_count()) - n0
+    launches_per_step = int(lib.d4b200_total_launch_count()) + int(lib.d4b200_eeq_launch_count()) - n0
 
     with ClockSampler(local_rank) as clocks:
         total_ms, _ = timed(step_resident, args.steps, args.warmup)
-        e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 3), host_call=not wl["grad"])
+        e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 3), host_call=host_api)
         # keep the same load running (untimed) until nvidia-smi has had time to sample it
         t_end = time.perf_counter() + 1.5
         while time.perf_counter() < t_end:
@@ -336,7 +376,8 @@ def run_b200(args, wl, rank, world, local_rank):
     # ---- dominant kernel: per-launch duration measured live with CUDA events
     lib.d4b200_profile_enable(engine.handle, 1)
     caps = (C.c_int * NCLS)()
-    lib.d4b200_class_caps(engine.handle, int(dtype == torch.float32), int(wl["grad"]), caps)
+    lib.d4b200_class_caps_model(engine.handle, int(dtype == torch.float32), int(wl["grad"]),
+                                int(model == "d4s"), caps)
     per_class = [[] for _ in range(NCLS)]
     prep_ms, call_ms = [], []
     for s in range(max(3, min(args.steps, 10))):
@@ -381,12 +422,23 @@ def run_b200(args, wl, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         chunk = 8 if wl["grad"] else 64
-        nsample = chunk * 2
-        sec = cpu_time_sample(wl, numbers_h, positions_h.double(), q_h.double(), nsample, chunk)
+        nsample = min(chunk * 2, numbers_h.shape[0])
+        keep: list = []
+        sec = cpu_time_sample(wl, numbers_h, positions_h.double(), q_h.double(), nsample, chunk, eeq=use_eeq, keep=keep)
+        # the float64 oracle results of the sample double as the checker of this run's GPU results
+        e_gpu, g_gpu = step_resident()
+        e_ref = torch.cat([k[0] for k in keep])
+        scale = e_ref.abs().amax(-1, keepdim=True)
+        parity = {"against": "float64 oracle, same sample", "structures": nsample,
+                  "max_rel_energy": float(((e_gpu[:nsample].detach().double().cpu() - e_ref).abs() / scale).max())}
+        if wl["grad"]:
+            g_ref = torch.cat([k[1] for k in keep])
+            parity["max_abs_gradient"] = float((g_gpu[:nsample].double().cpu() - g_ref).abs().max())
         cpu = {"value": nsample / sec, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"first {nsample} structures of the workload, chunks of {chunk}, float64, "
                          f"torch threads = {torch.get_num_threads()} (oracle/d4_oracle.py: the reference's "
-                         "dense torch formulation; the reference itself is not installable here)"}  # fmt: skip
+                         "dense torch formulation; the reference itself is not installable here)",
+               "parity": parity}  # fmt: skip
 
     if rank == 0:
         achieved = class_flop[dom] / (class_ms[dom] * 1e-3) / 1e12 if class_ms[dom] > 0 else 0.0
@@ -399,7 +451,10 @@ def run_b200(args, wl, rank, world, local_rank):
             "config": {"workload": wl["name"], "structures_per_gpu": int(numbers.shape[0]),
                        "global_batch": int(nmol), "parallelism": f"structure-sharded x{world}, no collective",
                        "l2": "flushed (256 MB write) between timed iterations",
-                       "param": "PBE0-D4 (s8 1.20065498, a1 0.40085597, a2 5.02928789), explicit charges q"},
+                       "param": "PBE0-D4 (s8 1.20065498, a1 0.40085597, a2 5.02928789), "
+                                + ("q=None: EEQ-2019 charges solved on device inside every step" if use_eeq
+                                   else "explicit charges q"),
+                       "model": model},
             "pair_terms_per_s": npair / sec_per_step, "triple_terms_per_s": ntrip / sec_per_step,
             "algorithmic_tflops": nflop / sec_per_step / 1e12,
             "e2e": {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
@@ -408,7 +463,7 @@ def run_b200(args, wl, rank, world, local_rank):
             "roofline": {
                 "bound": "fp64" if dtype == torch.float64 else "fp32",
                 "kernel": f"small_kernel<{'double' if dtype == torch.float64 else 'float'},"
-                          f"{'grad' if wl['grad'] else 'energy'}> size class <= {caps[dom]} atoms",
+                          f"{'grad' if wl['grad'] else 'energy'},{model}> size class <= {caps[dom]} atoms",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.workload, args.dtype),
                 "peak_source": "measured in this run: DFMA chain microbenchmark (d4b200_measure_fp64_peak); "
@@ -519,6 +574,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--eeq", action="store_true",
+                    help="default q=None path: EEQ charges on device inside the step (and on the autograd tape)")
     ap.add_argument("--nmol", type=int, default=0, help="c4: number of water molecules (default 6667)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

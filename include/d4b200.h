@@ -218,6 +218,39 @@ int d4b200_large_cn_chain_f32(d4b200_tables_t tables, const d4b200_params* par, 
                               const float* dcn_total_dev, int row_begin, int row_end,
                               float* force_dev, void* stream);
 
+/* ---- EEQ-2019 atomic partial charges (the step before the hot path) ---------------------
+ * Replaces tad_multicharge.get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)
+ * (third-party tad-multicharge==0.5.0; call sites src/tad_dftd4/dispersion/base.py:401-407 and
+ * src/tad_dftd4/disp.py:190) for padded batches of structures with nat <= d4b200_eeq_limit():
+ * one CTA per structure builds the bordered Coulomb system in shared memory and solves it.
+ * ``param_host`` = [5][87] doubles: chi, eta, kappa (CN scaling), charge width, covalent radius
+ * (Bohr), index 0 = padding.  ``charge_dev`` [nbatch] total charges; ``q_dev`` [nbatch, nat]
+ * (0 on padding).  ``status_dev`` (optional, one int the caller zeroes) receives
+ * D4B200_STATUS_BAD_NUMBER when an atomic number is outside 0..86.  The arithmetic is float64
+ * for both I/O types. */
+typedef struct d4b200_eeq* d4b200_eeq_t;
+int d4b200_eeq_create(int device, const double* param_host, size_t n, d4b200_eeq_t* out);
+int d4b200_eeq_destroy(d4b200_eeq_t eeq);
+int d4b200_eeq_limit(void);
+long long d4b200_eeq_launch_count(void);
+int d4b200_eeq_charges_f64(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                           const double* positions_dev, const double* charge_dev, double cn_cutoff,
+                           double* q_dev, int* status_dev, void* stream);
+int d4b200_eeq_charges_f32(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                           const float* positions_dev, const float* charge_dev, double cn_cutoff,
+                           float* q_dev, int* status_dev, void* stream);
+/* Vector-Jacobian product of the charges: grad_positions [nbatch, nat, 3] =
+ * (dq/dpositions)^T grad_q for the charges ``q_dev`` returned by d4b200_eeq_charges_*
+ * (what torch.autograd does on the reference's tape when q is not given). */
+int d4b200_eeq_vjp_f64(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                       const double* positions_dev, double cn_cutoff, const double* q_dev,
+                       const double* grad_q_dev, double* grad_positions_dev, int* status_dev,
+                       void* stream);
+int d4b200_eeq_vjp_f32(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                       const float* positions_dev, double cn_cutoff, const float* q_dev,
+                       const float* grad_q_dev, float* grad_positions_dev, int* status_dev,
+                       void* stream);
+
 /* Synchronises ``stream`` and returns the device status bits recorded by the
  * last energy/gradient call that used ``workspace_dev``. */
 int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);
@@ -236,6 +269,8 @@ int d4b200_profile_enable(d4b200_tables_t tables, int enable);
 int d4b200_profile_read(d4b200_tables_t tables, float* ms_out /*[D4B200_NCLASS + 2]*/);
 /* Inclusive atom-count bounds of the size classes for a kernel flavour. */
 int d4b200_class_caps(d4b200_tables_t tables, int fp32, int grad, int* caps_out /*[D4B200_NCLASS]*/);
+int d4b200_class_caps_model(d4b200_tables_t tables, int fp32, int grad, int model,
+                            int* caps_out /*[D4B200_NCLASS]*/);
 /* Largest structure (atoms) the one-CTA-per-structure kernels of a flavour accept; larger
  * structures go through the d4b200_large_* entry points.  model: D4B200_MODEL_D4 / _D4S. */
 int d4b200_small_limit(d4b200_tables_t tables, int fp32, int grad, int model);

@@ -54,12 +54,21 @@ _SIGS = {
     "d4b200_large_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_large_cn_chain_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "d4b200_large_cn_chain_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
+    "d4b200_eeq_create": (C.c_int, [C.c_int, _VP, C.c_size_t, C.POINTER(_VP)]),
+    "d4b200_eeq_destroy": (C.c_int, [_VP]),
+    "d4b200_eeq_limit": (C.c_int, []),
+    "d4b200_eeq_launch_count": (C.c_longlong, []),
+    "d4b200_eeq_charges_f64": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP]),
+    "d4b200_eeq_charges_f32": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP]),
+    "d4b200_eeq_vjp_f64": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "d4b200_eeq_vjp_f32": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "d4b200_status": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
     "d4b200_last_launch_count": (C.c_int, []),
     "d4b200_total_launch_count": (C.c_longlong, []),
     "d4b200_profile_enable": (C.c_int, [_VP, C.c_int]),
     "d4b200_profile_read": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "d4b200_class_caps": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "d4b200_class_caps_model": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "d4b200_small_limit": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int]),
     "d4b200_phase_profile": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_ulonglong)]),
     "d4b200_measure_fp64_peak": (C.c_int, [_VP, _VP, C.c_size_t, _VP, C.POINTER(C.c_double)]),

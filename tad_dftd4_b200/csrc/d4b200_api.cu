@@ -694,6 +694,12 @@ int d4b200_class_caps(d4b200_tables_t h, int fp32, int grad, int* caps_out) {
   return 0;
 }
 
+int d4b200_class_caps_model(d4b200_tables_t h, int fp32, int grad, int model, int* caps_out) {
+  if (!h || !caps_out || model < 0 || model > 1) return D4B200_EINVAL;
+  for (int c = 0; c < NCLASS; ++c) caps_out[c] = h->caps[model][fp32 ? 1 : 0][grad ? 1 : 0][c];
+  return 0;
+}
+
 int d4b200_small_limit(d4b200_tables_t h, int fp32, int grad, int model) {
   if (!h || model < 0 || model > 1) return D4B200_EINVAL;
   return h->caps[model][fp32 ? 1 : 0][grad ? 1 : 0][NCLASS - 1];

@@ -1,0 +1,385 @@
+// EEQ-2019 atomic partial charges for padded batches of small structures, and the
+// vector-Jacobian product of the charges with respect to the positions.
+//
+// Replaces tad_multicharge.get_eeq_charges (third-party, tad-multicharge==0.5.0;
+// call sites /root/reference/src/tad_dftd4/dispersion/base.py:401-407 and disp.py:190),
+// the step immediately before the D4 hot path.
+//
+// One CTA per structure, everything in shared memory:
+//   compact real atoms -> erf coordination number (near pairs only) -> bordered matrix
+//   [[A, 1], [1^T, 0]] with A_ij = erf(gamma_ij r_ij)/r_ij built once per unordered pair ->
+//   right-looking elimination of [M | rhs] without pivoting (A is the Gram matrix of
+//   Gaussian charges plus the hardness: positive definite for physical geometries; the
+//   border pivot is -1^T A^-1 1) -> back substitution.
+// VJP kernel: same matrix, rhs = (dL/dq, 0) -> mu; then
+//   dL/dx = mu^T (d rhs/dx - dM/dx (q, lambda))
+// as one weight per unordered pair (stored in the dead matrix) and a row sweep.
+// The arithmetic is float64 for both I/O types (the system is ill-suited to float32 and
+// costs a few per cent of the D4 kernels).  Model in numpy: tests/eeq_model.py.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/d4b200.h"
+
+namespace {
+
+constexpr int EEQ_NELEM = 87;  // Z = 0 (padding) .. 86
+constexpr int EEQ_NT = 256;
+constexpr int EEQ_NW = EEQ_NT / 32;
+constexpr int EEQ_MAX_NAT = 160;  // (14 (nat+1) + (nat+1) ld) doubles <= 227 KB
+constexpr int EEQ_NARR = 14;
+
+constexpr double KCN = 7.5;
+constexpr double CN_MAX = 8.0;
+constexpr double SQRT_2_OVER_PI = 0.79788456080286535588;
+constexpr double TWO_OVER_SQRT_PI = 1.12837916709551257390;
+constexpr double ONE_OVER_SQRT_PI = 0.56418958354775628695;
+constexpr double DBL_EPS = 2.220446049250313e-16;
+
+struct EeqTables {
+  const double *chi, *eta, *kcn, *rad, *rcov;
+};
+
+__host__ __device__ inline int eeq_ld(int nat) { return (nat + 2) | 1; }
+__host__ inline size_t eeq_smem(int nat) {
+  return sizeof(double) * ((size_t)EEQ_NARR * (nat + 1) + (size_t)(nat + 1) * eeq_ld(nat));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// pair index p -> (i, j), i > j >= 0, p = i (i - 1) / 2 + j
+__device__ __forceinline__ void pair_of(int p, int& i, int& j) {
+  i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+  while (i * (i - 1) / 2 > p) --i;
+  while ((i + 1) * i / 2 <= p) ++i;
+  j = p - i * (i - 1) / 2;
+}
+
+template <typename T, bool VJP>
+__global__ void __launch_bounds__(EEQ_NT)
+eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* __restrict__ pos,
+           const T* __restrict__ charge, double cutoff2, const T* __restrict__ q_in,
+           const T* __restrict__ gq, T* __restrict__ out, int* __restrict__ status) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int na1 = nat + 1;
+  double* xs = sm;
+  double* ys = xs + na1;
+  double* zs = ys + na1;
+  double* rad = zs + na1;
+  double* rcv = rad + na1;
+  double* kap = rcv + na1;
+  double* cnr = kap + na1;   // raw coordination number; later force x
+  double* cnc = cnr + na1;   // cut coordination number; later force y
+  double* sol = cnc + na1;   // solution of the bordered system
+  double* dinv = sol + na1;  // reciprocal pivots; later force z
+  double* qv = dinv + na1;   // VJP: charges
+  double* big = qv + na1;    // VJP: dL/dcn_raw
+  int* zat = reinterpret_cast<int*>(big + na1);  // [nat] atomic number by padded slot
+  int* idx = zat + na1;                          // [nat] compact -> padded slot
+  int* inv = idx + na1;                          // [nat] padded slot -> compact (-1 = padding)
+  int* cnt = inv + na1;                          // [1]
+  double* M = sm + (size_t)EEQ_NARR * na1;
+
+  const int64_t* zrow = numbers + (size_t)b * nat;
+  for (int a = tid; a < nat; a += EEQ_NT) {
+    long long z = zrow[a];
+    if (z < 0 || z >= EEQ_NELEM) {
+      if (status) atomicOr(status, D4B200_STATUS_BAD_NUMBER);
+      z = 0;
+    }
+    zat[a] = (int)z;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int n = 0;
+    for (int base = 0; base < nat; base += 32) {
+      const int a = base + lane;
+      const bool real = a < nat && zat[a] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, real);
+      const int c = n + __popc(m & ((1u << lane) - 1u));
+      if (a < nat) inv[a] = real ? c : -1;
+      if (real) idx[c] = a;
+      n += __popc(m);
+    }
+    if (lane == 0) *cnt = n;
+  }
+  __syncthreads();
+  const int n = *cnt;
+  const int m = n + 1;       // bordered system size; the rhs is column m
+  const int ld = (m + 1) | 1;  // odd stride: conflict-free column walks
+  T* orow = out + (size_t)b * nat * (VJP ? 3 : 1);
+  if (n == 0) {
+    for (int a = tid; a < nat * (VJP ? 3 : 1); a += EEQ_NT) orow[a] = T(0);
+    return;
+  }
+  for (int c = tid; c < n; c += EEQ_NT) {
+    const int a = idx[c];
+    const int z = zat[a];
+    const T* p = pos + ((size_t)b * nat + a) * 3;
+    xs[c] = (double)p[0];
+    ys[c] = (double)p[1];
+    zs[c] = (double)p[2];
+    rad[c] = tb.rad[z];
+    rcv[c] = tb.rcov[z];
+    kap[c] = tb.kcn[z];
+    if (VJP) qv[c] = (double)q_in[(size_t)b * nat + a];
+  }
+  __syncthreads();
+
+  // ---- coordination number: ordered rows, erfc only for near pairs ------------------------
+  for (int i = warp; i < n; i += EEQ_NW) {
+    const double xi = xs[i], yi = ys[i], zi = zs[i], ri = rcv[i];
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      const double dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const double r0 = ri + rcv[j];
+      // KCN (r/r0 - 1) < 6  <=>  r < 1.8 r0: beyond, erfc/2 < 1e-17
+      if (j != i && r2 <= cutoff2 && r2 < 3.24 * r0 * r0) {
+        acc += 0.5 * erfc(KCN * (sqrt(r2) / r0 - 1.0));
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      cnr[i] = acc;
+      cnc[i] = log1p(exp(CN_MAX)) - log1p(exp(CN_MAX - acc));
+    }
+  }
+
+  // ---- Coulomb block, once per unordered pair --------------------------------------------
+  const int npair = n * (n - 1) / 2;
+  for (int p = tid; p < npair; p += EEQ_NT) {
+    int i, j;
+    pair_of(p, i, j);
+    const double dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    const double g = 1.0 / sqrt(rad[i] * rad[i] + rad[j] * rad[j]);
+    const double a = erf(g * r) / r;
+    M[i * ld + j] = a;
+    M[j * ld + i] = a;
+  }
+  __syncthreads();
+  for (int c = tid; c < n; c += EEQ_NT) {
+    const int a = idx[c];
+    const int z = zat[a];
+    M[c * ld + c] = tb.eta[z] + SQRT_2_OVER_PI / rad[c];
+    M[c * ld + n] = 1.0;
+    M[n * ld + c] = 1.0;
+    M[c * ld + m] = VJP ? (double)gq[(size_t)b * nat + a]
+                        : -tb.chi[z] + kap[c] * sqrt(fmax(cnc[c], DBL_EPS));
+  }
+  if (tid == 0) {
+    M[n * ld + n] = 0.0;
+    M[n * ld + m] = VJP ? 0.0 : (double)charge[b];
+  }
+  __syncthreads();
+
+  // ---- elimination of [M | rhs], no pivoting ----------------------------------------------
+  for (int k = 0; k < m; ++k) {
+    const double pinv = 1.0 / M[k * ld + k];
+    if (tid == 0) dinv[k] = pinv;
+    const double* rk = M + k * ld;
+    for (int i = k + 1 + warp; i < m; i += EEQ_NW) {
+      double* ri = M + i * ld;
+      const double f = ri[k] * pinv;
+      for (int j = k + 1 + lane; j <= m; j += 32) ri[j] = fma(-f, rk[j], ri[j]);
+    }
+    __syncthreads();
+  }
+  // ---- back substitution --------------------------------------------------------------------
+  for (int k = m - 1; k >= 0; --k) {
+    const double xk = M[k * ld + m] * dinv[k];
+    if (tid == 0) sol[k] = xk;
+    for (int i = tid; i < k; i += EEQ_NT) M[i * ld + m] = fma(-M[i * ld + k], xk, M[i * ld + m]);
+    __syncthreads();
+  }
+
+  if constexpr (!VJP) {
+    for (int a = tid; a < nat; a += EEQ_NT) {
+      const int c = inv[a];
+      orow[a] = c >= 0 ? (T)sol[c] : T(0);
+    }
+  } else {
+  // ---- vector-Jacobian product ---------------------------------------------------------------
+  for (int c = tid; c < n; c += EEQ_NT) {
+    const double cc = cnc[c];
+    const double dsq = cc > DBL_EPS ? 0.5 * sol[c] * kap[c] / sqrt(cc) : 0.0;
+    big[c] = dsq / (1.0 + exp(cnr[c] - CN_MAX));
+  }
+  __syncthreads();
+  for (int p = tid; p < npair; p += EEQ_NT) {
+    int i, j;
+    pair_of(p, i, j);
+    const double dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double r = sqrt(r2);
+    const double rinv = 1.0 / r;
+    const double g = 1.0 / sqrt(rad[i] * rad[i] + rad[j] * rad[j]);
+    const double da = (TWO_OVER_SQRT_PI * g * exp(-g * g * r2) - erf(g * r) * rinv) * rinv;
+    double w = -(sol[i] * qv[j] + sol[j] * qv[i]) * da;
+    const double r0 = rcv[i] + rcv[j];
+    const double za = KCN * (r / r0 - 1.0);
+    if (r2 <= cutoff2 && za * za < 40.0) {
+      w -= (big[i] + big[j]) * (KCN * ONE_OVER_SQRT_PI / r0) * exp(-za * za);
+    }
+    w *= rinv;
+    M[i * ld + j] = w;
+    M[j * ld + i] = w;
+  }
+  __syncthreads();
+  double* fx = cnr;
+  double* fy = cnc;
+  double* fz = dinv;
+  for (int i = warp; i < n; i += EEQ_NW) {
+    const double xi = xs[i], yi = ys[i], zi = zs[i];
+    const double* wi = M + i * ld;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int j = lane; j < n; j += 32) {
+      if (j != i) {
+        const double w = wi[j];
+        ax = fma(w, xi - xs[j], ax);
+        ay = fma(w, yi - ys[j], ay);
+        az = fma(w, zi - zs[j], az);
+      }
+    }
+    ax = warp_sum(ax);
+    ay = warp_sum(ay);
+    az = warp_sum(az);
+    if (lane == 0) {
+      fx[i] = ax;
+      fy[i] = ay;
+      fz[i] = az;
+    }
+  }
+  __syncthreads();
+  for (int a = tid; a < nat; a += EEQ_NT) {
+    const int c = inv[a];
+    orow[a * 3 + 0] = c >= 0 ? (T)fx[c] : T(0);
+    orow[a * 3 + 1] = c >= 0 ? (T)fy[c] : T(0);
+    orow[a * 3 + 2] = c >= 0 ? (T)fz[c] : T(0);
+  }
+  }  // VJP
+}
+
+}  // namespace
+
+struct d4b200_eeq {
+  int device;
+  double* blob;
+  EeqTables t;
+};
+
+static thread_local long long g_eeq_launches = 0;
+
+extern "C" {
+
+int d4b200_eeq_limit(void) { return EEQ_MAX_NAT; }
+long long d4b200_eeq_launch_count(void) { return g_eeq_launches; }
+
+int d4b200_eeq_create(int device, const double* param_host, size_t n, d4b200_eeq_t* out) {
+  if (!param_host || !out) return D4B200_EINVAL;
+  if (n != (size_t)5 * EEQ_NELEM) return D4B200_ETABLE;
+  int prev = 0;
+  cudaError_t e = cudaGetDevice(&prev);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return (int)e;
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return (int)e;
+  if (prop.major != 10) {
+    cudaSetDevice(prev);
+    return D4B200_EARCH;
+  }
+  d4b200_eeq* h = new d4b200_eeq();
+  h->device = device;
+  if ((e = cudaMalloc(&h->blob, n * sizeof(double))) != cudaSuccess) {
+    delete h;
+    cudaSetDevice(prev);
+    return (int)e;
+  }
+  e = cudaMemcpy(h->blob, param_host, n * sizeof(double), cudaMemcpyHostToDevice);
+  h->t.chi = h->blob;
+  h->t.eta = h->blob + EEQ_NELEM;
+  h->t.kcn = h->blob + 2 * EEQ_NELEM;
+  h->t.rad = h->blob + 3 * EEQ_NELEM;
+  h->t.rcov = h->blob + 4 * EEQ_NELEM;
+  const int smem = (int)eeq_smem(EEQ_MAX_NAT);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(eeq_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(eeq_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(eeq_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(eeq_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    cudaFree(h->blob);
+    delete h;
+    return (int)e;
+  }
+  *out = h;
+  return 0;
+}
+
+int d4b200_eeq_destroy(d4b200_eeq_t h) {
+  if (!h) return D4B200_EINVAL;
+  cudaFree(h->blob);
+  delete h;
+  return 0;
+}
+
+}  // extern "C"
+
+template <typename T, bool VJP>
+static int eeq_launch(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers, const T* pos,
+                      const T* charge, double cutoff, const T* q, const T* gq, T* out, int* status,
+                      void* stream) {
+  if (!h || nbatch < 0 || nat < 0) return D4B200_EINVAL;
+  if (nbatch == 0 || nat == 0) return 0;
+  if (!numbers || !pos || !out || (VJP ? (!q || !gq) : !charge)) return D4B200_EINVAL;
+  if (nat > EEQ_MAX_NAT) return D4B200_EINVAL;
+  if (!(cutoff > 0.0)) return D4B200_EPARAM;
+  eeq_kernel<T, VJP><<<nbatch, EEQ_NT, eeq_smem(nat), (cudaStream_t)stream>>>(
+      h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status);
+  ++g_eeq_launches;
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+int d4b200_eeq_charges_f64(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                           const double* positions_dev, const double* charge_dev, double cn_cutoff,
+                           double* q_dev, int* status_dev, void* stream) {
+  return eeq_launch<double, false>(h, nbatch, nat, numbers_dev, positions_dev, charge_dev, cn_cutoff,
+                                   nullptr, nullptr, q_dev, status_dev, stream);
+}
+int d4b200_eeq_charges_f32(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                           const float* positions_dev, const float* charge_dev, double cn_cutoff,
+                           float* q_dev, int* status_dev, void* stream) {
+  return eeq_launch<float, false>(h, nbatch, nat, numbers_dev, positions_dev, charge_dev, cn_cutoff,
+                                  nullptr, nullptr, q_dev, status_dev, stream);
+}
+int d4b200_eeq_vjp_f64(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                       const double* positions_dev, double cn_cutoff, const double* q_dev,
+                       const double* grad_q_dev, double* grad_positions_dev, int* status_dev,
+                       void* stream) {
+  return eeq_launch<double, true>(h, nbatch, nat, numbers_dev, positions_dev, nullptr, cn_cutoff, q_dev,
+                                  grad_q_dev, grad_positions_dev, status_dev, stream);
+}
+int d4b200_eeq_vjp_f32(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                       const float* positions_dev, double cn_cutoff, const float* q_dev,
+                       const float* grad_q_dev, float* grad_positions_dev, int* status_dev,
+                       void* stream) {
+  return eeq_launch<float, true>(h, nbatch, nat, numbers_dev, positions_dev, nullptr, cn_cutoff, q_dev,
+                                 grad_q_dev, grad_positions_dev, status_dev, stream);
+}
+
+}  // extern "C"

@@ -324,14 +324,11 @@ def _scatter_back(values: Tensor, order: Tensor, nat: int) -> Tensor:
 
 
 def _eeq_charges(numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: Cutoff) -> Tensor:
-    try:
-        from tad_multicharge import get_eeq_charges  # type: ignore
-    except ImportError as e:  # pragma: no cover - depends on the environment
-        raise ImportError(
-            "EEQ charges are not part of the accelerated hot path: install tad-multicharge or "
-            "pass atomic partial charges explicitly via `q=`."
-        ) from e
-    return get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)
+    """``get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)`` of the reference
+    (dispersion/base.py:401-407) on device: ``tad_dftd4_b200.eeq``."""
+    from .eeq import get_eeq_charges
+
+    return get_eeq_charges(numbers, positions, charge, cutoff=cutoff.as_float("cn_eeq"))
 
 
 def dftd4(
