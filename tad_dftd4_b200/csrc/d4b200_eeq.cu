@@ -8,9 +8,9 @@
 // One CTA per structure, everything in shared memory:
 //   compact real atoms -> erf coordination number (near pairs only) -> bordered matrix
 //   [[A, 1], [1^T, 0]] with A_ij = erf(gamma_ij r_ij)/r_ij built once per unordered pair ->
-//   right-looking elimination of [M | rhs] without pivoting (A is the Gram matrix of
-//   Gaussian charges plus the hardness: positive definite for physical geometries; the
-//   border pivot is -1^T A^-1 1) -> back substitution.
+//   right-looking elimination of the upper triangle of [M | rhs] without pivoting (A is the
+//   Gram matrix of Gaussian charges plus the hardness: positive definite for physical
+//   geometries; the border pivot is -1^T A^-1 1) -> back substitution by one warp.
 // VJP kernel: same matrix, rhs = (dL/dq, 0) -> mu; then
 //   dL/dx = mu^T (d rhs/dx - dM/dx (q, lambda))
 // as one weight per unordered pair (stored in the dead matrix) and a row sweep.
@@ -26,13 +26,14 @@
 namespace {
 
 constexpr int EEQ_NELEM = 87;  // Z = 0 (padding) .. 86
-constexpr int EEQ_NT = 256;
-constexpr int EEQ_NW = EEQ_NT / 32;
+constexpr int EEQ_NT_SMALL = 128;  // structures padded to <= 64 atoms (several CTAs per SM)
+constexpr int EEQ_NT_LARGE = 512;  // beyond: one or two CTAs per SM, more warps per elimination step
 constexpr int EEQ_MAX_NAT = 160;  // (14 (nat+1) + (nat+1) ld) doubles <= 227 KB
 constexpr int EEQ_NARR = 14;
 
 constexpr double KCN = 7.5;
 constexpr double CN_MAX = 8.0;
+constexpr double LOG1P_EXP_CN_MAX = 8.0003354063728956;  // log(1 + exp(8))
 constexpr double SQRT_2_OVER_PI = 0.79788456080286535588;
 constexpr double TWO_OVER_SQRT_PI = 1.12837916709551257390;
 constexpr double ONE_OVER_SQRT_PI = 0.56418958354775628695;
@@ -61,13 +62,14 @@ __device__ __forceinline__ void pair_of(int p, int& i, int& j) {
   j = p - i * (i - 1) / 2;
 }
 
-template <typename T, bool VJP>
+template <typename T, bool VJP, int EEQ_NT>
 __global__ void __launch_bounds__(EEQ_NT)
 eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* __restrict__ pos,
            const T* __restrict__ charge, double cutoff2, const T* __restrict__ q_in,
            const T* __restrict__ gq, T* __restrict__ out, int* __restrict__ status) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
+  constexpr int NW = EEQ_NT / 32, EEQ_NW = NW;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int na1 = nat + 1;
   double* xs = sm;
@@ -134,25 +136,43 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
   }
   __syncthreads();
 
-  // ---- coordination number: ordered rows, erfc only for near pairs ------------------------
-  for (int i = warp; i < n; i += EEQ_NW) {
-    const double xi = xs[i], yi = ys[i], zi = zs[i], ri = rcv[i];
-    double acc = 0.0;
-    for (int j = lane; j < n; j += 32) {
-      const double dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
-      const double r2 = dx * dx + dy * dy + dz * dz;
-      const double r0 = ri + rcv[j];
-      // KCN (r/r0 - 1) < 6  <=>  r < 1.8 r0: beyond, erfc/2 < 1e-17
-      if (j != i && r2 <= cutoff2 && r2 < 3.24 * r0 * r0) {
-        acc += 0.5 * erfc(KCN * (sqrt(r2) / r0 - 1.0));
+  // ---- coordination number: ordered rows; the few near pairs of a row (r < 1.8 r0, beyond
+  // which erfc/2 < 1e-17) are first compacted into a per-warp list (in the not yet used matrix
+  // area) so that the expensive erfc runs once per 32 near pairs, not once per 32 pairs.
+  {
+    int* near = reinterpret_cast<int*>(M) + warp * n;  // <= n - 1 entries; 4 NW n bytes fit the matrix
+    for (int i = warp; i < n; i += EEQ_NW) {
+      const double xi = xs[i], yi = ys[i], zi = zs[i], ri = rcv[i];
+      int cntn = 0;
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        bool isnear = false;
+        if (j < n && j != i) {
+          const double dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
+          const double r2 = dx * dx + dy * dy + dz * dz;
+          const double r0 = ri + rcv[j];
+          isnear = r2 <= cutoff2 && r2 < 3.24 * r0 * r0;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, isnear);
+        if (isnear) near[cntn + __popc(mk & ((1u << lane) - 1u))] = j;
+        cntn += __popc(mk);
       }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      cnr[i] = acc;
-      cnc[i] = log1p(exp(CN_MAX)) - log1p(exp(CN_MAX - acc));
+      __syncwarp();
+      double acc = 0.0;
+      for (int e = lane; e < cntn; e += 32) {
+        const int j = near[e];
+        const double dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        acc += 0.5 * erfc(KCN * (sqrt(r2) / (ri + rcv[j]) - 1.0));
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) cnr[i] = acc;
+      __syncwarp();
     }
   }
+  __syncthreads();  // the lists lived in the matrix area
+  // smooth cut at CN_MAX: log(1 + e^8) - log(1 + e^(8 - cn)), one atom per thread
+  for (int c = tid; c < n; c += EEQ_NT) cnc[c] = LOG1P_EXP_CN_MAX - log1p(exp(CN_MAX - cnr[c]));
 
   // ---- Coulomb block, once per unordered pair --------------------------------------------
   const int npair = n * (n - 1) / 2;
@@ -160,19 +180,19 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
     int i, j;
     pair_of(p, i, j);
     const double dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
-    const double r = sqrt(dx * dx + dy * dy + dz * dz);
-    const double g = 1.0 / sqrt(rad[i] * rad[i] + rad[j] * rad[j]);
-    const double a = erf(g * r) / r;
-    M[i * ld + j] = a;
-    M[j * ld + i] = a;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double rinv = rsqrt(r2);
+    const double g = rsqrt(rad[i] * rad[i] + rad[j] * rad[j]);
+    M[j * ld + i] = erf(g * (r2 * rinv)) * rinv;  // upper triangle (j < i)
   }
   __syncthreads();
   for (int c = tid; c < n; c += EEQ_NT) {
     const int a = idx[c];
     const int z = zat[a];
-    M[c * ld + c] = tb.eta[z] + SQRT_2_OVER_PI / rad[c];
+    const double dg = tb.eta[z] + SQRT_2_OVER_PI / rad[c];
+    M[c * ld + c] = dg;
+    if (c == 0) dinv[0] = 1.0 / dg;
     M[c * ld + n] = 1.0;
-    M[n * ld + c] = 1.0;
     M[c * ld + m] = VJP ? (double)gq[(size_t)b * nat + a]
                         : -tb.chi[z] + kap[c] * sqrt(fmax(cnc[c], DBL_EPS));
   }
@@ -183,24 +203,65 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
   __syncthreads();
 
   // ---- elimination of [M | rhs], no pivoting ----------------------------------------------
+  // The trailing matrix stays symmetric, so only its upper triangle (j >= i) and the rhs are
+  // updated, and the multiplier of row i comes from the pivot ROW: f_i = a_ki / a_kk.  One
+  // block barrier per column.  A warp updates four of its rows at a time (loads grouped before
+  // the stores, so the shared-memory latencies overlap); the reciprocal of the next pivot is
+  // produced by the lane that has just updated it, off the other warps' path.
   for (int k = 0; k < m; ++k) {
-    const double pinv = 1.0 / M[k * ld + k];
-    if (tid == 0) dinv[k] = pinv;
+    const double pinv = dinv[k];
     const double* rk = M + k * ld;
-    for (int i = k + 1 + warp; i < m; i += EEQ_NW) {
-      double* ri = M + i * ld;
-      const double f = ri[k] * pinv;
-      for (int j = k + 1 + lane; j <= m; j += 32) ri[j] = fma(-f, rk[j], ri[j]);
+    for (int i0 = k + 1 + warp; i0 < m; i0 += 4 * NW) {
+      double* r0 = M + i0 * ld;
+      const bool v1 = i0 + NW < m, v2 = i0 + 2 * NW < m, v3 = i0 + 3 * NW < m;
+      const int o1 = v1 ? NW : 0, o2 = v2 ? 2 * NW : 0, o3 = v3 ? 3 * NW : 0;
+      double* r1 = r0 + o1 * ld;
+      double* r2 = r0 + o2 * ld;
+      double* r3 = r0 + o3 * ld;
+      const double f0 = rk[i0] * pinv, f1 = rk[i0 + o1] * pinv, f2 = rk[i0 + o2] * pinv,
+                   f3 = rk[i0 + o3] * pinv;
+      for (int j = i0 + lane; j <= m; j += 32) {  // columns left of a row's diagonal: harmless
+        const double p = rk[j];
+        double a0 = r0[j], a1 = r1[j], a2 = r2[j], a3 = r3[j];
+        a0 = fma(-f0, p, a0);
+        a1 = fma(-f1, p, a1);
+        a2 = fma(-f2, p, a2);
+        a3 = fma(-f3, p, a3);
+        r0[j] = a0;
+        if (v1) r1[j] = a1;
+        if (v2) r2[j] = a2;
+        if (v3) r3[j] = a3;
+        if (i0 == k + 1 && j == k + 1) dinv[k + 1] = 1.0 / a0;
+      }
     }
     __syncthreads();
   }
-  // ---- back substitution --------------------------------------------------------------------
-  for (int k = m - 1; k >= 0; --k) {
-    const double xk = M[k * ld + m] * dinv[k];
-    if (tid == 0) sol[k] = xk;
-    for (int i = tid; i < k; i += EEQ_NT) M[i * ld + m] = fma(-M[i * ld + k], xk, M[i * ld + m]);
-    __syncthreads();
+  // ---- back substitution: warp 0, right-hand side in registers, no block barriers -----------
+  if (warp == 0) {
+    constexpr int MAXC = (EEQ_MAX_NAT + 1 + 31) / 32;
+    double bb[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int i = lane + 32 * c;
+      bb[c] = i < m ? M[i * ld + m] : 0.0;
+    }
+#pragma unroll
+    for (int c = MAXC - 1; c >= 0; --c) {
+      if (32 * c < m) {
+        for (int kk = min(31, m - 1 - 32 * c); kk >= 0; --kk) {
+          const int k = 32 * c + kk;
+          const double xk = __shfl_sync(0xffffffffu, bb[c], kk) * dinv[k];
+          if (lane == kk) sol[k] = xk;
+#pragma unroll
+          for (int cc = 0; cc <= c; ++cc) {
+            const int i = lane + 32 * cc;
+            if (i < k) bb[cc] = fma(-M[i * ld + k], xk, bb[cc]);
+          }
+        }
+      }
+    }
   }
+  __syncthreads();
 
   if constexpr (!VJP) {
     for (int a = tid; a < nat; a += EEQ_NT) {
@@ -220,9 +281,9 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
     pair_of(p, i, j);
     const double dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
     const double r2 = dx * dx + dy * dy + dz * dz;
-    const double r = sqrt(r2);
-    const double rinv = 1.0 / r;
-    const double g = 1.0 / sqrt(rad[i] * rad[i] + rad[j] * rad[j]);
+    const double rinv = rsqrt(r2);
+    const double r = r2 * rinv;
+    const double g = rsqrt(rad[i] * rad[i] + rad[j] * rad[j]);
     const double da = (TWO_OVER_SQRT_PI * g * exp(-g * g * r2) - erf(g * r) * rinv) * rinv;
     double w = -(sol[i] * qv[j] + sol[j] * qv[i]) * da;
     const double r0 = rcv[i] + rcv[j];
@@ -311,14 +372,17 @@ int d4b200_eeq_create(int device, const double* param_host, size_t n, d4b200_eeq
   h->t.rad = h->blob + 3 * EEQ_NELEM;
   h->t.rcov = h->blob + 4 * EEQ_NELEM;
   const int smem = (int)eeq_smem(EEQ_MAX_NAT);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(eeq_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(eeq_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(eeq_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(eeq_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  auto attr = [&](auto kern) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  };
+  attr(eeq_kernel<double, false, EEQ_NT_SMALL>);
+  attr(eeq_kernel<double, true, EEQ_NT_SMALL>);
+  attr(eeq_kernel<float, false, EEQ_NT_SMALL>);
+  attr(eeq_kernel<float, true, EEQ_NT_SMALL>);
+  attr(eeq_kernel<double, false, EEQ_NT_LARGE>);
+  attr(eeq_kernel<double, true, EEQ_NT_LARGE>);
+  attr(eeq_kernel<float, false, EEQ_NT_LARGE>);
+  attr(eeq_kernel<float, true, EEQ_NT_LARGE>);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     cudaFree(h->blob);
@@ -347,8 +411,12 @@ static int eeq_launch(d4b200_eeq_t h, int nbatch, int nat, const int64_t* number
   if (!numbers || !pos || !out || (VJP ? (!q || !gq) : !charge)) return D4B200_EINVAL;
   if (nat > EEQ_MAX_NAT) return D4B200_EINVAL;
   if (!(cutoff > 0.0)) return D4B200_EPARAM;
-  eeq_kernel<T, VJP><<<nbatch, EEQ_NT, eeq_smem(nat), (cudaStream_t)stream>>>(
-      h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status);
+  if (nat <= 64)
+    eeq_kernel<T, VJP, EEQ_NT_SMALL><<<nbatch, EEQ_NT_SMALL, eeq_smem(nat), (cudaStream_t)stream>>>(
+        h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status);
+  else
+    eeq_kernel<T, VJP, EEQ_NT_LARGE><<<nbatch, EEQ_NT_LARGE, eeq_smem(nat), (cudaStream_t)stream>>>(
+        h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status);
   ++g_eeq_launches;
   return (int)cudaGetLastError();
 }

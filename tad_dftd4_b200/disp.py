@@ -323,12 +323,13 @@ def _scatter_back(values: Tensor, order: Tensor, nat: int) -> Tensor:
     return values.new_zeros((values.shape[0], nat)).scatter(1, order, values)
 
 
-def _eeq_charges(numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: Cutoff) -> Tensor:
+def _eeq_charges(numbers: Tensor, positions: Tensor, charge, cutoff: Cutoff | None) -> Tensor:
     """``get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)`` of the reference
     (dispersion/base.py:401-407) on device: ``tad_dftd4_b200.eeq``."""
     from .eeq import get_eeq_charges
 
-    return get_eeq_charges(numbers, positions, charge, cutoff=cutoff.as_float("cn_eeq"))
+    cut = defaults.D4_CN_EEQ_CUTOFF if cutoff is None else cutoff.as_float("cn_eeq")
+    return get_eeq_charges(numbers, positions, charge, cutoff=cut)
 
 
 def dftd4(
@@ -391,9 +392,7 @@ def dftd4(
             f"to a CUDA device (got {positions.device})."
         )
     if q is None:
-        chg = charge if isinstance(charge, Tensor) else torch.tensor(charge)
-        eeq_cut = cutoff if cutoff is not None else Cutoff(device=positions.device, dtype=positions.dtype)
-        q = _eeq_charges(numbers, positions, chg.to(positions.device, positions.dtype), eeq_cut)
+        q = _eeq_charges(numbers, positions, charge, cutoff)
     if numbers.shape != q.shape:
         raise ValueError(
             f"Shape of atomic charges ({q.shape}) is not consistent "
@@ -500,7 +499,7 @@ def get_properties(
     """``(cn, q, c6, alpha)`` as ``tad_dftd4.get_properties`` (``disp.py:149-197``):
     D4 coordination numbers, atomic charges, pair C6 ``(..., nat, nat)`` and static
     polarizabilities.  ``q`` (keyword, extension of the reference signature) passes
-    explicit charges; without it EEQ charges come from ``tad-multicharge``."""
+    explicit charges; without it EEQ charges are solved on device (``tad_dftd4_b200.eeq``)."""
     if numbers.shape != positions.shape[:-1]:
         raise ValueError(
             f"Shape of positions ({positions.shape}) is not consistent "
@@ -509,9 +508,7 @@ def get_properties(
     if positions.device.type != "cuda":
         raise RuntimeError("tad_dftd4_b200 runs on B200 GPUs only (no CPU fallback).")
     if q is None:
-        eeq_cut = cutoff if cutoff is not None else Cutoff(device=positions.device, dtype=positions.dtype)
-        chg = torch.tensor(0.0) if charge is None else (charge if isinstance(charge, Tensor) else torch.tensor(charge))
-        q = _eeq_charges(numbers, positions, chg.to(positions.device, positions.dtype), eeq_cut)
+        q = _eeq_charges(numbers, positions, 0.0 if charge is None else charge, cutoff)
     if numbers.shape != q.shape:
         raise ValueError(
             f"Shape of atomic charges ({q.shape}) is not consistent with atomic numbers ({numbers.shape})."

@@ -181,8 +181,13 @@ def get_eeq_charges(numbers: Tensor, positions: Tensor, chrg: Tensor | float | i
     batch_shape = numbers.shape[:-1]
     num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
     pos2 = positions.reshape(-1, nat, 3).contiguous()
-    chg = chrg if isinstance(chrg, Tensor) else torch.tensor(chrg)
-    chg = chg.to(positions.device, positions.dtype).expand(batch_shape).reshape(-1).contiguous()
+    nb = num2.shape[0]
+    if isinstance(chrg, Tensor) and chrg.device.type == "cuda":
+        chg = chrg.to(positions.device, positions.dtype).expand(batch_shape).reshape(-1).contiguous()
+    elif isinstance(chrg, Tensor) and chrg.numel() > 1:
+        chg = chrg.to(positions.device, positions.dtype, non_blocking=True).expand(batch_shape).reshape(-1).contiguous()
+    else:  # host scalar: a device-side fill, no host-to-device copy and no synchronisation
+        chg = torch.full((nb,), float(chrg), dtype=positions.dtype, device=positions.device)
     engine = _EeqEngine.get(positions.device)
     with torch.cuda.device(positions.device):
         if nat <= engine.limit:
