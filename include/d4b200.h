@@ -218,6 +218,37 @@ int d4b200_large_cn_chain_f32(d4b200_tables_t tables, const d4b200_params* par, 
                               const float* dcn_total_dev, int row_begin, int row_end,
                               float* force_dev, void* stream);
 
+/* ---- model-level entry points (the reference's D4Model / D4SModel methods) ---------------
+ * weight_references: zeta(q) * Gaussian weights, == D4Model.weight_references(cn, q)
+ * (src/tad_dftd4/model/d4.py:103-228) -> gw [nbatch, nat, 7], or for par->model ==
+ * D4B200_MODEL_D4S == D4SModel.weight_references (model/d4s.py:109-266) -> gw
+ * [nbatch, nat(m), nat(n), 7] (weights of atom n as seen by partner m).  ``cn_dev`` / ``q_dev``
+ * may be NULL (= 0, like the reference's defaults); ``dgwdcn_dev`` / ``dgwdq_dev`` (optional,
+ * same shape) receive the derivatives returned by with_dgwdcn / with_dgwdq.  Only
+ * par->model and par->wf are read.  ``status_dev``: optional int for D4B200_STATUS_BAD_NUMBER. */
+int d4b200_weight_references_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                                 const int64_t* numbers_dev, const double* cn_dev, const double* q_dev,
+                                 double* gw_dev, double* dgwdcn_dev, double* dgwdq_dev, int* status_dev,
+                                 void* stream);
+int d4b200_weight_references_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                                 const int64_t* numbers_dev, const float* cn_dev, const float* q_dev,
+                                 float* gw_dev, float* dgwdcn_dev, float* dgwdq_dev, int* status_dev,
+                                 void* stream);
+/* get_atomic_c6(gw) -> [nbatch, nat, nat]: einsum('ijab,ia,jb->ij', rc6, gw, gw) (model/d4.py:268-289),
+ * or for D4S einsum('ijab,jia,ijb->ij', rc6, gw, gw) (model/d4s.py:268-290). */
+int d4b200_atomic_c6_f64(d4b200_tables_t tables, int model, int nbatch, int nat, const int64_t* numbers_dev,
+                         const double* gw_dev, double* c6_dev, void* stream);
+int d4b200_atomic_c6_f32(d4b200_tables_t tables, int model, int nbatch, int nat, const int64_t* numbers_dev,
+                         const float* gw_dev, float* c6_dev, void* stream);
+/* get_weighted_pols(gw) -> [nbatch, nat, nfreq] with nfreq = 23 (model/d4.py:291-307);
+ * nfreq = 1 gives get_polarizabilities(gw) -> [nbatch, nat] (model/base.py:286-302). */
+int d4b200_weighted_pols_f64(d4b200_tables_t tables, int nbatch, int nat, int nfreq,
+                             const int64_t* numbers_dev, const double* gw_dev, double* alpha_dev,
+                             void* stream);
+int d4b200_weighted_pols_f32(d4b200_tables_t tables, int nbatch, int nat, int nfreq,
+                             const int64_t* numbers_dev, const float* gw_dev, float* alpha_dev,
+                             void* stream);
+
 /* ---- EEQ-2019 atomic partial charges (the step before the hot path) ---------------------
  * Replaces tad_multicharge.get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)
  * (third-party tad-multicharge==0.5.0; call sites src/tad_dftd4/dispersion/base.py:401-407 and

@@ -211,16 +211,16 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
   for (int k = 0; k < m; ++k) {
     const double pinv = dinv[k];
     const double* rk = M + k * ld;
-    for (int i0 = k + 1 + warp; i0 < m; i0 += 4 * NW) {
+    // blocks of four ADJACENT rows (their upper-triangle column ranges nearly coincide)
+    for (int i0 = k + 1 + 4 * warp; i0 < m; i0 += 4 * NW) {
       double* r0 = M + i0 * ld;
-      const bool v1 = i0 + NW < m, v2 = i0 + 2 * NW < m, v3 = i0 + 3 * NW < m;
-      const int o1 = v1 ? NW : 0, o2 = v2 ? 2 * NW : 0, o3 = v3 ? 3 * NW : 0;
-      double* r1 = r0 + o1 * ld;
-      double* r2 = r0 + o2 * ld;
-      double* r3 = r0 + o3 * ld;
-      const double f0 = rk[i0] * pinv, f1 = rk[i0 + o1] * pinv, f2 = rk[i0 + o2] * pinv,
-                   f3 = rk[i0 + o3] * pinv;
-      for (int j = i0 + lane; j <= m; j += 32) {  // columns left of a row's diagonal: harmless
+      const bool v1 = i0 + 1 < m, v2 = i0 + 2 < m, v3 = i0 + 3 < m;
+      double* r1 = v1 ? r0 + ld : r0;
+      double* r2 = v2 ? r0 + 2 * ld : r0;
+      double* r3 = v3 ? r0 + 3 * ld : r0;
+      const double f0 = rk[i0] * pinv, f1 = v1 ? rk[i0 + 1] * pinv : 0.0,
+                   f2 = v2 ? rk[i0 + 2] * pinv : 0.0, f3 = v3 ? rk[i0 + 3] * pinv : 0.0;
+      for (int j = i0 + lane; j <= m; j += 32) {  // up to three columns left of a diagonal: harmless
         const double p = rk[j];
         double a0 = r0[j], a1 = r1[j], a2 = r2[j], a3 = r3[j];
         a0 = fma(-f0, p, a0);
@@ -231,8 +231,8 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
         if (v1) r1[j] = a1;
         if (v2) r2[j] = a2;
         if (v3) r3[j] = a3;
-        if (i0 == k + 1 && j == k + 1) dinv[k + 1] = 1.0 / a0;
       }
+      if (i0 == k + 1 && lane == 0) dinv[k + 1] = 1.0 / r0[k + 1];
     }
     __syncthreads();
   }
