@@ -249,6 +249,29 @@ int d4b200_weighted_pols_f32(d4b200_tables_t tables, int nbatch, int nat, int nf
                              const int64_t* numbers_dev, const float* gw_dev, float* alpha_dev,
                              void* stream);
 
+/* ---- parameter gradients ------------------------------------------------
+ * Vector-Jacobian product of the atom-resolved energy with respect to the damping
+ * parameters: out[b] = d(sum_i g_bi E_bi)/d(s6, s8, s9, s10, a1, a2, alp), float64
+ * [nbatch, 7], one row per structure.  Replaces torch autograd through
+ * RationalDamping._f / dispersion2 / get_atm_dispersion with ``Param`` values that require
+ * grad (test/test_grad/test_param.py:40-100 of the reference).  ``c6q`` / ``c60`` are the
+ * pair C6 matrices [nbatch, nat, nat] built from weight_references(cn, q) and
+ * weight_references(cn, None) (two-body and ATM flavours, dispersion/twobody.py:72-74,
+ * dispersion/threebody.py:313-315) with d4b200_atomic_c6_*, so both models are served.
+ * ``grad_energy`` is the upstream gradient [nbatch, nat] (NULL = ones).  The s10 entry is 0
+ * unless ``has_s10`` is set (the reference has no tensor to differentiate otherwise). */
+size_t d4b200_param_vjp_workspace_bytes(int nbatch, int nat);
+int d4b200_param_vjp_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                         const int64_t* numbers_dev, const double* positions_dev,
+                         const double* c6q_dev, const double* c60_dev,
+                         const double* grad_energy_dev, double* out_dev, void* workspace_dev,
+                         size_t workspace_bytes, void* stream);
+int d4b200_param_vjp_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                         const int64_t* numbers_dev, const float* positions_dev,
+                         const float* c6q_dev, const float* c60_dev,
+                         const float* grad_energy_dev, double* out_dev, void* workspace_dev,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- EEQ-2019 atomic partial charges (the step before the hot path) ---------------------
  * Replaces tad_multicharge.get_eeq_charges(numbers, positions, charge, cutoff=cutoff.cn_eeq)
  * (third-party tad-multicharge==0.5.0; call sites src/tad_dftd4/dispersion/base.py:401-407 and

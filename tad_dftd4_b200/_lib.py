@@ -60,6 +60,9 @@ _SIGS = {
     "d4b200_atomic_c6_f32": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
     "d4b200_weighted_pols_f64": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
     "d4b200_weighted_pols_f32": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
+    "d4b200_param_vjp_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "d4b200_param_vjp_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_param_vjp_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_eeq_create": (C.c_int, [C.c_int, _VP, C.c_size_t, C.POINTER(_VP)]),
     "d4b200_eeq_destroy": (C.c_int, [_VP]),
     "d4b200_eeq_limit": (C.c_int, []),

@@ -71,6 +71,7 @@ class _Engine:
         )
         self.lib = lib
         self.handle = handle
+        self.ga, self.gc = float(ga), float(gc)
         self.limits: dict[tuple[bool, bool, int], int] = {}
         self.device = torch.device("cuda", index)
         self._ws: Tensor | None = None
@@ -188,8 +189,11 @@ class _D4Function(torch.autograd.Function):
     """energy[b, i] = D4(numbers, positions, q); backward = fused analytic VJP."""
 
     @staticmethod
-    def forward(ctx, positions: Tensor, q: Tensor, numbers: Tensor, par, engine: _Engine):
+    def forward(ctx, positions: Tensor, q: Tensor, numbers: Tensor, par, engine: _Engine, *ptens):
+        # ptens: the seven damping parameters (s6, s8, s9, s10, a1, a2, alp) as tensors where the
+        # caller differentiates them (None otherwise); their values are already in ``par``
         need_pos, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        ctx.ptens = tuple((t.dtype, t.device, t.shape) if t is not None else None for t in ptens)
         ctx.cached = None
         if _FUSED_FORWARD and (need_pos or need_q):
             gpos, gq, energy = engine.gradient(par, numbers, positions, q, None, need_pos, need_q,
@@ -207,15 +211,69 @@ class _D4Function(torch.autograd.Function):
     def backward(ctx, gout: Tensor):
         positions, q, numbers = ctx.saved_tensors
         need_pos, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gpar: tuple = ()
+        if ctx.ptens:
+            want = [ctx.needs_input_grad[5 + k] for k in range(len(ctx.ptens))]
+            gpar = (None,) * len(ctx.ptens)
+            if any(want):
+                vec = _param_vjp(ctx.engine, ctx.par, numbers, positions, q, gout.contiguous())
+                gpar = tuple(
+                    vec[k].to(device=meta[1], dtype=meta[0]).reshape(meta[2]) if (w and meta is not None) else None
+                    for k, (w, meta) in enumerate(zip(want, ctx.ptens))
+                )
+        if not (need_pos or need_q):
+            return (None, None, None, None, None, *gpar)
         if ctx.cached is not None and all(s == 0 for s in gout.stride()):
             # upstream gradient is one broadcast scalar c: dL/dx = c * d(sum E)/dx (no sync)
             c = gout.reshape(-1)[0]
             gpos, gq = ctx.cached
-            return (gpos * c if need_pos else None), (gq * c if need_q else None), None, None, None
+            return ((gpos * c if need_pos else None), (gq * c if need_q else None), None, None, None, *gpar)
         gpos, gq = ctx.engine.gradient(
             ctx.par, numbers, positions, q, gout.contiguous(), need_pos, need_q
         )
-        return gpos, gq, None, None, None
+        return (gpos, gq, None, None, None, *gpar)
+
+
+_PARAM_ORDER = ("s6", "s8", "s9", "s10", "a1", "a2", "alp")
+
+
+def _param_tensors(param: Param) -> tuple:
+    """The damping parameters the caller differentiates (tensors with ``requires_grad``), in the
+    order of :data:`_PARAM_ORDER`; empty when there is none."""
+    out = tuple(
+        v if isinstance(v, Tensor) and v.requires_grad else None for v in (param.get(k) for k in _PARAM_ORDER)
+    )
+    return out if any(t is not None for t in out) else ()
+
+
+def _param_vjp(engine: _Engine, par: _lib.Params, numbers: Tensor, positions: Tensor, q: Tensor,
+               gout: Tensor) -> Tensor:  # fmt: skip
+    """``d(sum g E)/d(s6, s8, s9, s10, a1, a2, alp)`` (float64 ``[7]``) on device: coordination
+    numbers, reference weights and pair C6 of both flavours from the model-level kernels, then
+    ``d4b200_param_vjp_*`` (csrc/d4b200_param.cu).  The reference differentiates its dense tape
+    instead (test/test_grad/test_param.py:40-100)."""
+    from .model import D4Model, D4SModel
+
+    nbatch, nat = numbers.shape
+    with torch.no_grad():
+        pos = positions.detach()
+        qd = q.detach()
+        cn = get_properties(numbers, pos, q=torch.zeros_like(qd))[0]
+        cls = D4SModel if par.model == 1 else D4Model
+        model = cls(numbers, ga=engine.ga, gc=engine.gc, wf=par.wf, dtype=pos.dtype)
+        c6q = model.get_atomic_c6(model.weight_references(cn, qd))
+        c60 = model.get_atomic_c6(model.weight_references(cn, None))
+        need = int(engine.lib.d4b200_param_vjp_workspace_bytes(nbatch, nat))
+        ws = torch.empty(max(need, 8), dtype=torch.uint8, device=pos.device)
+        out = torch.empty((nbatch, 7), dtype=torch.float64, device=pos.device)
+        stream = torch.cuda.current_stream(pos.device).cuda_stream
+        fn = engine.lib.d4b200_param_vjp_f64 if pos.dtype == torch.float64 else engine.lib.d4b200_param_vjp_f32
+        _lib.check(
+            fn(engine.handle, C.byref(par), nbatch, nat, numbers.data_ptr(), pos.data_ptr(), c6q.data_ptr(),
+               c60.data_ptr(), gout.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+            "d4b200_param_vjp",
+        )  # fmt: skip
+        return out.sum(0)
 
 
 # ---------------------------------------------------------------------------
@@ -229,11 +287,8 @@ def _scalar(v: Any, name: str) -> float:
     examples build them with ``positions.new_tensor``) cost one synchronisation
     the first time they are seen; the value is cached per tensor version."""
     if isinstance(v, Tensor):
-        if v.requires_grad:
-            raise NotImplementedError(
-                f"gradients with respect to the damping parameter '{name}' are not provided "
-                "by the fused kernels (SURVEY.md 8f-3)"
-            )
+        if v.requires_grad:  # differentiated parameter: value here, gradient through _param_vjp
+            return float(v.detach())
         if v.device.type == "cpu":
             return float(v)
         hit = _SCALAR_CACHE.get(id(v))
@@ -399,6 +454,7 @@ def dftd4(
             f"with atomic numbers ({numbers.shape}).",
         )
     par = _flatten_param(param, cutoff, model_id, wf)
+    ptens = _param_tensors(param)
 
     engine = _Engine.get(positions.device, ga, gc)
     nat = numbers.shape[-1]
@@ -414,6 +470,11 @@ def dftd4(
         counts = (num2 != 0).sum(-1)
         big = torch.nonzero(counts > limit).flatten().tolist()
         if big:
+            if ptens:
+                raise NotImplementedError(
+                    "gradients with respect to the damping parameters are provided for structures "
+                    "of the one-CTA-per-structure kernels only"
+                )
             if model_id != 0:
                 raise NotImplementedError("the tiled large-system path supports model='d4' only")
             from .large import dftd4_large
@@ -427,12 +488,12 @@ def dftd4(
                 sel = torch.tensor(small, device=num2.device)
                 ns, ps, qs, back = _compact_front(num2[sel], pos2[sel], q2[sel], limit)
                 with torch.cuda.device(positions.device):
-                    es = _scatter_back(_D4Function.apply(ps, qs, ns, par, engine), back, nat)
+                    es = _scatter_back(_D4Function.apply(ps, qs, ns, par, engine, *ptens), back, nat)
                 for n, b in enumerate(small):
                     rows[b] = es[n]
             return torch.stack(rows).reshape(*batch_shape, nat)
     with torch.cuda.device(positions.device):
-        energy = _D4Function.apply(pos2, q2, num2, par, engine)
+        energy = _D4Function.apply(pos2, q2, num2, par, engine, *ptens)
     return energy.reshape(*batch_shape, nat)
 
 

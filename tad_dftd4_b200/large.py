@@ -111,8 +111,13 @@ class _Plan:
 
 def _kernel_backend(positions: Tensor, param, cutoff):
     from . import _lib, defaults
-    from .disp import _Engine, _flatten_param
+    from .disp import _Engine, _flatten_param, _param_tensors
 
+    if _param_tensors(param):
+        raise NotImplementedError(
+            "gradients with respect to the damping parameters are provided for structures of the "
+            "one-CTA-per-structure kernels only (detach the parameters for the tiled large-system path)"
+        )
     engine = _Engine.get(positions.device, defaults.GA_DEFAULT, defaults.GC_DEFAULT)
     par = _flatten_param(param, cutoff, 0, defaults.WF_DEFAULT)
     lib = engine.lib

@@ -162,3 +162,73 @@ def energy_and_gradient(numbers, positions, q, param, g=None, disp2=60.0, disp3=
     fc = np.where(off, G2 * c6q * dF / r + 2.0 * D + (dL_dcn[:, None] + dL_dcn[None, :]) * dcn_dr / r, 0.0)
     grad = (fc[:, :, None] * dx).sum(1)
     return e2 + e3, grad, dL_dq, cn
+
+
+def param_gradient(numbers, positions, q, param, g=None, disp2=60.0, disp3=40.0, cn_cut=30.0,
+                   wf=6.0, ga=3.0, gc=2.0):  # fmt: skip
+    """dL/d(s6, s8, s9, s10, a1, a2, alp) for L = sum_i g_i E_i, the algebra of
+    ``csrc/d4b200_param.cu`` (single structure, D4 model): the energy is linear in the
+    scaling factors; a1/a2 enter through R0 = a1 sqrt(3 r4r2_i r4r2_j) + a2 in the rational
+    damping and, together with alp, through u = (R0/r)^(alp/3) in the ATM damping
+    f = 1/(1 + 6 u_ij u_ik u_jk), so d e/d ln u_p = -6 t f e for each pair of a triple."""
+    tab = build_tables(ga, gc)
+    z = np.asarray(numbers)
+    x = np.asarray(positions, dtype=np.float64)
+    n = len(z)
+    g = np.ones(n) if g is None else np.asarray(g, dtype=np.float64)
+    s6, s8, s9 = param.get("s6", 1.0), param.get("s8", 1.0), param.get("s9", 1.0)
+    has_s10 = "s10" in param
+    s10 = param.get("s10", 0.0) if has_s10 else 0.0
+    a1, a2, alp = param["a1"], param["a2"], param.get("alp", 16.0)
+
+    dx = x[:, None, :] - x[None, :, :]
+    r2 = (dx * dx).sum(-1)
+    off = ~np.eye(n, dtype=bool)
+    r = np.sqrt(np.where(off, r2, 1.0))
+    r0 = tab.rcov[z][:, None] + tab.rcov[z][None, :]
+    den = tab.den[z][:, z]
+    cn = np.where(off & (r <= cn_cut), den * 0.5 * erfc(KCN * (r / r0 - 1.0)), 0.0).sum(1)
+    gw, _, zeta, _, zeta0 = _weights(tab, z, cn, np.asarray(q, dtype=np.float64), wf, ga)
+    aw = tab.alpha_w[z]
+    Aq = np.einsum("ia,iaw->iw", zeta * gw, aw)
+    A0 = np.einsum("ia,iaw->iw", zeta0 * gw, aw)
+    c6q, c60 = Aq @ Aq.T, A0 @ A0.T
+
+    sq = tab.sqrt_r4r2[z]
+    ss = sq[:, None] * sq[None, :]
+    R0 = a1 * ss + a2
+    qq = ss * ss
+    in2 = off & (r <= disp2)
+    t6, t8, t10 = 1.0 / (r**6 + R0**6), 1.0 / (r**8 + R0**8), 1.0 / (r**10 + R0**10)
+    k10 = 49.0 / 40.0 * qq * qq
+    G2c = np.where(in2, -0.25 * (g[:, None] + g[None, :]) * c6q, 0.0)  # every pair appears twice
+    dFdR0 = -(6 * s6 * R0**5 * t6**2 + 8 * s8 * qq * R0**7 * t8**2 + 10 * s10 * k10 * R0**9 * t10**2)
+    out = np.zeros(7)
+    out[0] = (G2c * t6).sum()
+    out[1] = (G2c * qq * t8).sum()
+    out[3] = (G2c * k10 * t10).sum() if has_s10 else 0.0
+    out[4] = (G2c * dFdR0 * ss).sum()
+    out[5] = (G2c * dFdR0).sum()
+
+    Pt = np.where(off, np.sqrt(np.abs(c60)) / (r2 * r2 * r), 0.0)
+    u = np.where(off, (R0 / r) ** (alp / 3.0), 0.0)
+    lg = np.log(np.where(off, R0 / r, 1.0))
+    cflag = (off & (r <= disp3)).astype(np.float64)
+    for i in range(n):
+        for j in range(i):
+            for k in range(j):
+                a, b, c = r2[i, j], r2[j, k], r2[i, k]
+                cij, cik, cjk = cflag[i, j], cflag[i, k], cflag[j, k]
+                W = g[i] * cjk * (cij + cik) + g[j] * cik * (cij + cjk) + g[k] * cij * (cik + cjk)
+                if W == 0.0:
+                    continue
+                s = (b * b - (a - c) ** 2) * (a + c - b)
+                t = u[i, j] * u[i, k] * u[j, k]
+                f = 1.0 / (1.0 + 6.0 * t)
+                e = W * (0.375 * s + a * b * c) * Pt[i, j] * Pt[i, k] * Pt[j, k] * f / 6.0
+                out[2] += e
+                h = -6.0 * t * f * e * s9
+                out[4] += h * alp / 3.0 * (ss[i, j] / R0[i, j] + ss[i, k] / R0[i, k] + ss[j, k] / R0[j, k])
+                out[5] += h * alp / 3.0 * (1.0 / R0[i, j] + 1.0 / R0[i, k] + 1.0 / R0[j, k])
+                out[6] += h * (lg[i, j] + lg[i, k] + lg[j, k]) / 3.0
+    return out

@@ -91,8 +91,16 @@ def test_missing_damping_parameters_raise_type_error():
     par = _flatten_param({"a1": 0.4, "a2": 5.0, "s10": 0.0}, d4.Cutoff(disp2=50, cn=20.0), 0, 6.0)
     assert par.has_s10 == 1 and par.disp2_cutoff == 50.0
     assert par.cn_cutoff == 30.0  # Cutoff.cn is not forwarded (reference dispersion/base.py:390)
-    with pytest.raises(NotImplementedError):
-        _flatten_param({"a1": torch.tensor(0.4, requires_grad=True), "a2": 5.0}, None, 0, 6.0)
+    # differentiated parameters (test/test_grad/test_param.py of the reference): value flattened,
+    # the tensors are handed to the autograd function
+    from tad_dftd4_b200.disp import _param_tensors
+
+    a1 = torch.tensor(0.4, dtype=torch.float64, requires_grad=True)
+    par = _flatten_param({"a1": a1, "a2": 5.0}, None, 0, 6.0)
+    assert par.a1 == 0.4
+    pt = _param_tensors({"a1": a1, "a2": torch.tensor(5.0), "s8": 1.0})
+    assert len(pt) == 7 and pt[4] is a1 and all(t is None for k, t in enumerate(pt) if k != 4)
+    assert _param_tensors({"a1": 0.4, "a2": torch.tensor(5.0)}) == ()
 
 
 def test_get_params():

@@ -38,3 +38,33 @@ def test_dq_and_weighted_upstream():
     _, grad, dq, _ = energy_and_gradient(case["numbers"], case["positions"], case["q"], case["param"], g=g)
     assert np.abs(grad - gp.numpy()).max() < 1e-9
     assert np.abs(dq - gq.numpy()).max() < 1e-9
+
+
+PARAM_KEYS = ("s6", "s8", "s9", "s10", "a1", "a2", "alp")
+
+
+@pytest.mark.parametrize("name,with_s10", [("sih4_tpssh", True), ("organic_20", False), ("tight_cutoffs", True),
+                                           ("single_pbe0", True)])  # fmt: skip
+def test_param_gradient_model(name, with_s10):
+    """dL/d(damping parameters) (test/test_grad/test_param.py of the reference differentiates
+    the same seven) vs oracle autograd, with random upstream weights."""
+    from kernel_model import param_gradient
+
+    case = load_golden(name)
+    numbers, positions, q = as_torch(case)
+    base = {"s6": 1.0, "s8": 0.78981345, "s9": 1.0, "a1": 0.49484001, "a2": 5.73083694, "alp": 16.0}
+    base.update({k: float(v) for k, v in case["param"].items()})
+    if with_s10:
+        base.setdefault("s10", 0.0)
+    else:
+        base.pop("s10", None)
+    rng = np.random.default_rng(11)
+    g = rng.normal(size=len(case["numbers"]))
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in base.items()}
+    e = orc.dftd4(numbers, positions, tp, q, **case["cutoff"])
+    keys = [k for k in PARAM_KEYS if k in tp]
+    ref = torch.autograd.grad((e * torch.from_numpy(g)).sum(), [tp[k] for k in keys])
+    got = param_gradient(case["numbers"], case["positions"], case["q"], base, g=g, **case["cutoff"])
+    for k, r in zip(keys, ref):
+        v = got[PARAM_KEYS.index(k)]
+        assert abs(v - r.item()) <= 1e-12 + 1e-9 * abs(r.item()), (k, v, r.item())
