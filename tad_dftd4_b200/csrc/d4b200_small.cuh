@@ -263,11 +263,16 @@ __device__ __forceinline__ T row_sum2_8(const T* __restrict__ lo, const T* __res
 // stash entries of (i,j) and (i,k).
 //   e' = (0.375 s + abc) * P'_ij P'_ik P'_jk / (1 + 6 u_ij u_ik u_jk),  P' = P / r^2
 // (threebody.py:113-160 factorised per pair; e' = e_ijk/6 with s9 folded in; the stash
-// holds P' so that 1/(abc) never has to be formed).
-template <typename T, bool OPEN>
+// holds P' so that 1/(abc) never has to be formed).  With f = 1/(1 + 6 t):
+//   d e'/d b = [ e' (alp f t - 2.5) + pf abc ] / b + 0.375 pf ds/db,   f t = (1 - f)/6
+// The sweep accumulates  G = sum W e',  C = sum W [..],  S = sum W pf ds/db  and the caller
+// forms  D = C / b + 0.375 S  once per owner pair (1/b and 0.375 are loop invariants).
+// UNIT (closed structure, no upstream weights: d(sum E)): W = 6 for every triple, the sums
+// are accumulated unweighted and G doubles as the energy share.
+template <typename T, bool OPEN, bool UNIT>
 __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T b2, T twob,
-                                           T cjk, T Pjk, T ujk, T inv_b, T alp3x3, T gi2, T gjk2,
-                                           T gj, T gk, T& accG, T& accD, T& accH, T& accL) {
+                                           T cjk, T Pjk, T ujk, T kA, T kB, T gi2, T gjk2,
+                                           T gj, T gk, T& accG, T& accC, T& accS, T& accH, T& accL) {
   T a = a_s, c = c_s;
   T W = gi2 + gjk2;  // closed triple: multiplicity 2 for every atom (g*2 = 2 g*)
   T mj = T(2), mk = T(2);
@@ -291,15 +296,21 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   const T pf = Pij * Pik * Pjk * f;  // P' = P / r^2: P_ij P_ik P_jk / (abc d)
   const T psf = pf * abc;
   const T e = pf * fma(T(0.375), s, abc);
-  const T common = fma(e, fma(alp3x3 * f, t, T(-2.5)), psf);
-  const T de = fma(common, inv_b, T(0.375) * pf * dsdb);
-  accG = fma(W, e, accG);
-  accD = fma(W, de, accD);
-  if (OPEN) {
-    accH = fma(mj, e, accH);  // energy shares of the owner pair's atoms (fused energy + gradient call)
-    accL = fma(mk, e, accL);
+  const T common = fma(e, fma(-kA, f, kB), psf);  // alp f t - 2.5 = (alp/6 - 2.5) - (alp/6) f
+  if (UNIT && !OPEN) {
+    accG += e;
+    accC += common;
+    accS = fma(pf, dsdb, accS);
   } else {
-    accH += e;  // both atoms of the owner pair have multiplicity 2 (applied by the caller)
+    accG = fma(W, e, accG);
+    accC = fma(W, common, accC);
+    accS = fma(W * pf, dsdb, accS);
+    if (OPEN) {
+      accH = fma(mj, e, accH);  // energy shares of the owner pair's atoms (fused energy + gradient call)
+      accL = fma(mk, e, accL);
+    } else {
+      accH += e;  // both atoms of the owner pair have multiplicity 2 (applied by the caller)
+    }
   }
 }
 
@@ -542,6 +553,132 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     // Eight lanes per atom (one per reference, one idle): the row sum, the shift (min
     // exponent) and the normalisation are 8-lane shuffle reductions; the weights stay in
     // registers for the weighted polarizability vectors (three frequencies per lane).
+#ifndef D4_WEIGHTS_LANES8
+    if constexpr (!GRAD && !D4S) {
+      // D4 energy kernel: FOUR lanes per atom (references a and a + 4 per lane, frequencies
+      // a, a + 4, ..., a + 20), so that the whole structure is one pass of the CTA for every
+      // size class (CAP atoms x 4 lanes = NT threads): the phase is a single latency chain
+      // (row sum -> shift -> exponentials -> normalisation -> vectors), two passes of eight
+      // lanes per atom cost that chain twice.
+      for (int t0 = warp * 32; t0 < 4 * n; t0 += NT) {
+        const int i = (t0 + lane) >> 2, a = lane & 3;
+        const bool row = i < n;
+        const int z = row ? zs[i] : 0;
+        // table entries first (independent of the row sum)
+        int rc[2];
+        double rcn[2], qref[2], z0[2];
+        int za[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ar = a + 4 * h;
+          za[h] = z * NREF + (ar < NREF ? ar : 0);
+          rc[h] = (row && ar < NREF) ? tab.refc[za[h]] : 0;
+          rcn[h] = tab.refcn[za[h]];
+          qref[h] = tab.refq[za[h]];
+          z0[h] = tab.zeta0[za[h]];
+        }
+        const double gam = tab.gamgc[z], zeff = tab.zeff[z];
+        const double qat = row ? (double)A.q[(size_t)b * A.nat + idx[i]] : 0.0;
+        T c0 = T(0), c1 = T(0);
+        if (row) {
+          const T* r = pu + i * (i - 1) / 2;
+          int j = a;
+          for (; j + 4 < i; j += 8) {
+            c0 += r[j];
+            c1 += r[j + 4];
+          }
+          if (j < i) c0 += r[j];
+          j = i + 1 + a;
+          for (; j + 4 < n; j += 8) {
+            c0 += pu[j * (j - 1) / 2 + i];
+            c1 += pu[(j + 4) * (j + 3) / 2 + i];
+          }
+          if (j < n) c0 += pu[j * (j - 1) / 2 + i];
+        }
+        T cn_row = c0 + c1;
+        cn_row += __shfl_xor_sync(0xffffffffu, cn_row, 2);
+        cn_row += __shfl_xor_sync(0xffffffffu, cn_row, 1);
+        if (a == 0 && row && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = cn_row;
+        double arg[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double d = (double)cn_row - rcn[h];
+          arg[h] = rc[h] > 0 ? P.wf * d * d : 1e300;
+        }
+        double shift = fmin(arg[0], arg[1]);
+        shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, 2));
+        shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, 1));
+        double S[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double t1 = exp(shift - arg[h]), x = exp(-arg[h]);
+          double pw = 1.0, acc = 0.0;
+#pragma unroll
+          for (int k = 1; k <= 3; ++k) {
+            acc += k <= rc[h] ? pw : 0.0;
+            pw *= x;
+          }
+          for (int k = 4; k <= rc[h]; ++k) {
+            acc += pw;
+            pw *= x;
+          }
+          S[h] = rc[h] > 0 ? t1 * acc : 0.0;
+        }
+        double norm = S[0] + S[1];
+        norm += __shfl_xor_sync(0xffffffffu, norm, 2);
+        norm += __shfl_xor_sync(0xffffffffu, norm, 1);
+        const double qmod = qat + zeff;
+        const bool qpos = qmod > 0.0;
+        const double qinv = 1.0 / (qpos ? qmod - (double)d4_eps<T>() : 1.0);
+        const bool nz = norm > 0.0;
+        const double inv = d4_rcp(nz ? norm : 1.0);
+        T wq[2], w0[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double scale = qpos ? exp(gam * (1.0 - qref[h] * qinv)) : 0.0;
+          const double zeta = rc[h] > 0 ? exp(P.ga * (1.0 - scale)) : 0.0;
+          const double gw = nz ? S[h] * inv : 0.0;
+          wq[h] = (T)(zeta * gw);
+          w0[h] = (T)(z0[h] * gw);
+        }
+        if (A.alpha_out) {  // properties mode: alpha_i = sum_a zeta gw alpha_a(0)
+          T al = wq[0] * tab.alpha0[za[0]] + (a + 4 < NREF ? wq[1] * tab.alpha0[za[1]] : T(0));
+          al += __shfl_xor_sync(0xffffffffu, al, 2);
+          al += __shfl_xor_sync(0xffffffffu, al, 1);
+          if (a == 0 && row) A.alpha_out[(size_t)b * A.nat + idx[i]] = al;
+        }
+        // weighted polarizability vectors, both flavours: lane a takes w = a + 4 k
+        const T* const al = tab.alpha_w + (size_t)z * NREF * NFREQ;
+        T sq[6], s0[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sq[k] = s0[k] = T(0);
+#pragma unroll
+        for (int ar = 0; ar < NREF; ++ar) {
+          const T vq = __shfl_sync(0xffffffffu, wq[ar >> 2], (lane & 28) + (ar & 3));
+          const T v0 = __shfl_sync(0xffffffffu, w0[ar >> 2], (lane & 28) + (ar & 3));
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int w = a + 4 * k;
+            if (w < NFREQ) {
+              const T av = al[ar * NFREQ + w];
+              sq[k] += vq * av;
+              s0[k] += v0 * av;
+            }
+          }
+        }
+        if (row) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int w = a + 4 * k;
+            if (w < NFREQ) {
+              Aq[w * AS + i] = sq[k];
+              A0[w * AS + i] = s0[k];
+            }
+          }
+        }
+      }
+    } else
+#endif
     D4_ROWS8(i, a) {
       const T cn_row = row_sum2_8(pu, pu, i, a, n);  // every lane of the row holds the sum
       if (a == 0 && i < n) {
@@ -844,32 +981,43 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const T Pjk = pP[p], ujk = pu[p];
           const T inv_b = d4_rcp(bb), b2 = bb * bb, twob = bb + bb;
           const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
-          const T gjk2 = T(2) * (gj + gk), alp3x3 = T(3) * P.alp3;
+          const T gjk2 = T(2) * (gj + gk);
+          const T kA = T(0.5) * P.alp3, kB = kA - T(2.5);  // alp / 6, alp / 6 - 2.5
           const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
-          T accG = T(0), accD = T(0), accH = T(0), accL = T(0);
+          T accG = T(0), accC = T(0), accS = T(0), accH = T(0), accL = T(0);
           // branch-free sweep over the third atom: for i == j or i == k the visit runs on
           // the owner's own entry with a zero pair factor (contributes exactly 0), so the
           // body is straight-line code and two visits can be in flight per thread
-#define D4_SWEEP(OPENV)                                                                         \
+#define D4_SWEEP(OPENV, UNITV)                                                                  \
   _Pragma("unroll 4") for (int i = 0; i < n; ++i) {                                             \
     const int ti = i * (i - 1) / 2;                                                             \
     const bool ok = (i != j) & (i != k);                                                        \
     const int pij = ok ? (i > j ? ti + j : tj + i) : p;                                         \
     const int pik = ok ? (i > k ? ti + k : tk + i) : p;                                         \
-    grad_visit<T, OPENV>(pa[pij], ok ? pP[pij] : T(0), pu[pij], pa[pik], pP[pik], pu[pik], bb,  \
-                         b2, twob, cjk, Pjk, ujk, inv_b, alp3x3, T(2) * ATOM(AT_G)[i], gjk2,    \
-                         gj, gk, accG, accD, accH, accL);                                       \
+    grad_visit<T, OPENV, UNITV>(pa[pij], ok ? pP[pij] : T(0), pu[pij], pa[pik], pP[pik],        \
+                                pu[pik], bb, b2, twob, cjk, Pjk, ujk, kA, kB,                   \
+                                UNITV ? T(0) : T(2) * ATOM(AT_G)[i], gjk2, gj, gk, accG, accC,  \
+                                accS, accH, accL);                                              \
   }
           if (open) {
-            D4_SWEEP(true)
+            D4_SWEEP(true, false)
+          } else if (A.gin == nullptr) {
+            D4_SWEEP(false, true)
           } else {
-            D4_SWEEP(false)
+            D4_SWEEP(false, false)
           }
 #undef D4_SWEEP
           if (!open) {
+            if (A.gin == nullptr) {  // unit upstream weights: W = 6, G is also the energy share
+              accH = accG;
+              accG *= T(6);
+              accC *= T(6);
+              accS *= T(6);
+            }
             accH += accH;
             accL = accH;
           }
+          const T accD = fma(accC, inv_b, T(0.375) * accS);
           out0[p] = accG;
           out1[p] = accD;
           if (A.energy) {
