@@ -268,10 +268,11 @@ __device__ __forceinline__ T row_sum2_8(const T* __restrict__ lo, const T* __res
 // The sweep accumulates  G = sum W e',  C = sum W [..],  S = sum W pf ds/db  and the caller
 // forms  D = C / b + 0.375 S  once per owner pair (1/b and 0.375 are loop invariants).
 // UNIT (closed structure, no upstream weights: d(sum E)): W = 6 for every triple, the sums
-// are accumulated unweighted and G doubles as the energy share.
+// are accumulated unweighted and G doubles as the energy share.  24 FP64 operations per
+// visit (UNIT), one MUFU.
 template <typename T, bool OPEN, bool UNIT>
 __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T b2, T twob,
-                                           T cjk, T Pjk, T ujk, T kA, T kB, T gi2, T gjk2,
+                                           T cjk, T iP, T sPu, T kAi, T kB, T gi2, T gjk2,
                                            T gj, T gk, T& accG, T& accC, T& accS, T& accH, T& accL) {
   T a = a_s, c = c_s;
   T W = gi2 + gjk2;  // closed triple: multiplicity 2 for every atom (g*2 = 2 g*)
@@ -291,12 +292,14 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   const T s = XZ * Y;
   const T dsdb = fma(twob, Y, -XZ);  // d s / d b = Y Z - X Z + X Y
   const T abc = (a * c) * b;
-  const T t = uij * uik * ujk;
-  const T f = d4_rcp(fma(T(6), t, T(1)));
-  const T pf = Pij * Pik * Pjk * f;  // P' = P / r^2: P_ij P_ik P_jk / (abc d)
+  // owner-pair invariants folded into the damping denominator: iP = 1/P'_jk, sPu = 6 u_jk / P'_jk,
+  // so that fp = P'_jk f = 1 / (iP + sPu u_ij u_ik) and pf = P'_ij P'_ik fp
+  const T fp = d4_rcp(fma(sPu, uij * uik, iP));
+  const T pf = (Pij * Pik) * fp;  // P' = P / r^2: P_ij P_ik P_jk / (abc d)
   const T psf = pf * abc;
   const T e = pf * fma(T(0.375), s, abc);
-  const T common = fma(e, fma(-kA, f, kB), psf);  // alp f t - 2.5 = (alp/6 - 2.5) - (alp/6) f
+  // alp f t - 2.5 = (alp/6 - 2.5) - (alp/6) f,  f = fp / P'_jk  (kAi = alp / (6 P'_jk))
+  const T common = fma(e, fma(-kAi, fp, kB), psf);
   if (UNIT && !OPEN) {
     accG += e;
     accC += common;
@@ -983,6 +986,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const T gj = ATOM(AT_G)[j], gk = ATOM(AT_G)[k];
           const T gjk2 = T(2) * (gj + gk);
           const T kA = T(0.5) * P.alp3, kB = kA - T(2.5);  // alp / 6, alp / 6 - 2.5
+          const bool pz = Pjk == T(0);  // no ATM contribution through this pair (C6(q=0) = 0)
+          const T iP = pz ? T(1) : d4_rcp(Pjk);
+          const T sPu = T(6) * ujk * iP, kAi = kA * iP;
           const int tj = j * (j - 1) / 2, tk = k * (k - 1) / 2;
           T accG = T(0), accC = T(0), accS = T(0), accH = T(0), accL = T(0);
           // branch-free sweep over the third atom: for i == j or i == k the visit runs on
@@ -995,7 +1001,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     const int pij = ok ? (i > j ? ti + j : tj + i) : p;                                         \
     const int pik = ok ? (i > k ? ti + k : tk + i) : p;                                         \
     grad_visit<T, OPENV, UNITV>(pa[pij], ok ? pP[pij] : T(0), pu[pij], pa[pik], pP[pik],        \
-                                pu[pik], bb, b2, twob, cjk, Pjk, ujk, kA, kB,                   \
+                                pu[pik], bb, b2, twob, cjk, iP, sPu, kAi, kB,                   \
                                 UNITV ? T(0) : T(2) * ATOM(AT_G)[i], gjk2, gj, gk, accG, accC,  \
                                 accS, accH, accL);                                              \
   }
@@ -1017,6 +1023,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             accH += accH;
             accL = accH;
           }
+          if (pz) accG = accC = accS = accH = accL = T(0);
           const T accD = fma(accC, inv_b, T(0.375) * accS);
           out0[p] = accG;
           out1[p] = accD;
