@@ -67,6 +67,19 @@ __device__ __forceinline__ double d4_rcp(double x) {
   return fma(y, fma(e, e, e), y);
 }
 __device__ __forceinline__ float d4_rcp(float x) { return __frcp_rn(x); }
+// Damping reciprocal of the gradient triple sweep: MUFU seed + ONE Newton step (two FMAs).
+// Relative error ~ e^2 < 1e-12 on the three-body terms only, which are ~1e-2 of the energy
+// and ~1e-5 Eh/Bohr in the gradient: four orders of magnitude inside the 1e-10 / 1e-9 bars.
+__device__ __forceinline__ double d4_rcp_sweep(double x) {
+#ifdef D4_RCP_SWEEP_CUBIC
+  return d4_rcp(x);
+#else
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return fma(y, fma(-x, y, 1.0), y);
+#endif
+}
+__device__ __forceinline__ float d4_rcp_sweep(float x) { return __frcp_rn(x); }
 
 template <typename T>
 __device__ __forceinline__ T d4_eps();
@@ -268,7 +281,7 @@ __device__ __forceinline__ T row_sum2_8(const T* __restrict__ lo, const T* __res
 // The sweep accumulates  G = sum W e',  C = sum W [..],  S = sum W pf ds/db  and the caller
 // forms  D = C / b + 0.375 S  once per owner pair (1/b and 0.375 are loop invariants).
 // UNIT (closed structure, no upstream weights: d(sum E)): W = 6 for every triple, the sums
-// are accumulated unweighted and G doubles as the energy share.  24 FP64 operations per
+// are accumulated unweighted and G doubles as the energy share.  21 FP64 operations per
 // visit (UNIT), one MUFU.
 template <typename T, bool OPEN, bool UNIT>
 __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T uik, T b, T b2, T twob,
@@ -294,25 +307,28 @@ __device__ __forceinline__ void grad_visit(T a_s, T Pij, T uij, T c_s, T Pik, T 
   const T abc = (a * c) * b;
   // owner-pair invariants folded into the damping denominator: iP = 1/P'_jk, sPu = 6 u_jk / P'_jk,
   // so that fp = P'_jk f = 1 / (iP + sPu u_ij u_ik) and pf = P'_ij P'_ik fp
-  const T fp = d4_rcp(fma(sPu, uij * uik, iP));
+  const T fp = d4_rcp_sweep(fma(sPu, uij * uik, iP));
   const T pf = (Pij * Pik) * fp;  // P' = P / r^2: P_ij P_ik P_jk / (abc d)
-  const T psf = pf * abc;
-  const T e = pf * fma(T(0.375), s, abc);
-  // alp f t - 2.5 = (alp/6 - 2.5) - (alp/6) f,  f = fp / P'_jk  (kAi = alp / (6 P'_jk))
-  const T common = fma(e, fma(-kAi, fp, kB), psf);
+  // e' = pf wa;  e' (alp f t - 2.5) + pf abc = pf (wa k + abc) with
+  // k = alp f t - 2.5 = (alp/6 - 2.5) - (alp/6) f,  f = fp / P'_jk  (kAi = alp / (6 P'_jk)):
+  // pf is applied in the accumulating FMAs, e' itself is never formed
+  const T wa = fma(T(0.375), s, abc);
+  const T inner = fma(wa, fma(-kAi, fp, kB), abc);
   if (UNIT && !OPEN) {
-    accG += e;
-    accC += common;
+    accG = fma(pf, wa, accG);
+    accC = fma(pf, inner, accC);
     accS = fma(pf, dsdb, accS);
   } else {
-    accG = fma(W, e, accG);
-    accC = fma(W, common, accC);
-    accS = fma(W * pf, dsdb, accS);
+    const T Wpf = W * pf;
+    accG = fma(Wpf, wa, accG);
+    accC = fma(Wpf, inner, accC);
+    accS = fma(Wpf, dsdb, accS);
     if (OPEN) {
+      const T e = pf * wa;
       accH = fma(mj, e, accH);  // energy shares of the owner pair's atoms (fused energy + gradient call)
       accL = fma(mk, e, accL);
     } else {
-      accH += e;  // both atoms of the owner pair have multiplicity 2 (applied by the caller)
+      accH = fma(pf, wa, accH);  // both atoms of the owner pair have multiplicity 2 (applied by the caller)
     }
   }
 }
