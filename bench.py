@@ -578,6 +578,9 @@ def main():
                     help="default q=None path: EEQ charges on device inside the step (and on the autograd tape)")
     ap.add_argument("--nmol", type=int, default=0, help="c4: number of water molecules (default 6667)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
