@@ -306,11 +306,13 @@ def run_b200(args, wl, rank, world, local_rank):
     out_g = torch.empty(positions_h.shape, dtype=dtype).pin_memory() if wl["grad"] else None
 
     def step_e2e_host():
-        # public host-buffer API: pinned host tensors in, pinned host tensor out; the C ABI
-        # pipelines H2D copy / kernels / D2H copy in chunks (d4b200_energy_host_*)
-        d4.dftd4_host(numbers_h, positions_h, 0.0, PBE0, q=q_h, model=model, device=dev, out=out_e)
+        # public host-buffer API: pinned host tensors in, pinned host tensors out; the C ABI
+        # pipelines H2D copy / kernels / D2H copy in chunks (d4b200_energy_host_*,
+        # d4b200_energy_gradient_host_* for the workloads with forces)
+        d4.dftd4_host(numbers_h, positions_h, 0.0, PBE0, q=q_h, model=model, device=dev, out=out_e,
+                      with_gradient=wl["grad"], out_gradient=out_g)
 
-    host_api = not wl["grad"] and not use_eeq
+    host_api = not use_eeq
 
     def step_e2e():
         if host_api:

@@ -116,6 +116,18 @@ int d4b200_energy_host_f64(d4b200_tables_t tables, const d4b200_params* par, int
 int d4b200_energy_host_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
                            const int64_t* numbers_host, const float* positions_host,
                            const float* q_host, float* energy_host, int chunks);
+/* Host-buffer energy + forces: as d4b200_energy_host_* with the fused energy+gradient kernels per
+ * chunk; ``grad_host`` [nbatch, nat, 3] receives d(sum_i E_i)/d positions (what
+ * ``torch.autograd.grad(energy.sum(), positions)`` returns in examples/forces.py:47-50 of the
+ * reference), ``gradq_host`` [nbatch, nat] (optional, may be NULL) d(sum_i E_i)/dq. */
+int d4b200_energy_gradient_host_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                                    const int64_t* numbers_host, const double* positions_host,
+                                    const double* q_host, double* energy_host, double* grad_host,
+                                    double* gradq_host, int chunks);
+int d4b200_energy_gradient_host_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                                    const int64_t* numbers_host, const float* positions_host,
+                                    const float* q_host, float* energy_host, float* grad_host,
+                                    float* gradq_host, int chunks);
 
 /* Vector-Jacobian product of the energy: for upstream weights
  * g = dL/dE [nbatch, nat] (NULL = all ones, i.e. L = sum E) returns

@@ -351,22 +351,28 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
 // overlap the kernels of the others.  Pinned host memory is needed for the overlap (pageable
 // memory still works, serialised by the driver).  Synchronous: returns when
 // ``energy_host`` is complete.
-template <typename T>
+// GRAD: the fused energy + gradient kernels (d(sum E)/d positions, optionally d(sum E)/dq) run
+// per chunk and the gradient planes travel back with the energies.
+template <typename T, bool GRAD>
 static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
-                           const int64_t* numbers, const T* pos, const T* q, T* energy, int chunks) {
+                           const int64_t* numbers, const T* pos, const T* q, T* energy, int chunks,
+                           T* grad = nullptr, T* gradq = nullptr) {
   if (!h || !par || !numbers || !pos || !q || !energy || nbatch < 0 || nat < 0) return D4B200_EINVAL;
+  if (GRAD && !grad) return D4B200_EINVAL;
   if (nbatch == 0 || nat == 0) return 0;
   int prev_dev = 0;
   cudaGetDevice(&prev_dev);
   cudaSetDevice(h->device);
-  if (chunks <= 0) chunks = nbatch >= 2048 ? 4 : nbatch >= 512 ? 2 : 1;
+  if (chunks <= 0) chunks = nbatch >= 2048 ? 4 : nbatch >= 512 ? (GRAD ? 4 : 2) : 1;
   if (chunks > nbatch) chunks = nbatch;
   const int cb = (nbatch + chunks - 1) / chunks;  // structures per chunk
   const size_t rows = (size_t)cb * nat;
   const size_t off_pos = align_up(rows * sizeof(int64_t), 256);
   const size_t off_q = off_pos + align_up(rows * 3 * sizeof(T), 256);
   const size_t off_e = off_q + align_up(rows * sizeof(T), 256);
-  const size_t off_ws = off_e + align_up(rows * sizeof(T), 256);
+  const size_t off_g = off_e + align_up(rows * sizeof(T), 256);
+  const size_t off_gq = off_g + (GRAD ? align_up(rows * 3 * sizeof(T), 256) : 0);
+  const size_t off_ws = off_gq + (GRAD ? align_up(rows * sizeof(T), 256) : 0);
   const size_t ws_bytes = d4b200_workspace_bytes(cb, nat);
   const size_t need = off_ws + ws_bytes;
   cudaError_t e = cudaSuccess;
@@ -402,12 +408,18 @@ static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatc
     cudaMemcpyAsync(d + off_q, q + o, r * sizeof(T), cudaMemcpyHostToDevice, h->hcopy);
     cudaEventRecord(h->hev_in[s], h->hcopy);
     cudaStreamWaitEvent(st, h->hev_in[s], 0);
-    rc = run_small<T, false>(h, par, nb, nat, reinterpret_cast<const int64_t*>(d),
-                             reinterpret_cast<const T*>(d + off_pos), reinterpret_cast<const T*>(d + off_q),
-                             nullptr, reinterpret_cast<T*>(d + off_e), nullptr, nullptr, nullptr,
-                             d + off_ws, ws_bytes, st, nullptr, nullptr, 1 + s);
+    rc = run_small<T, GRAD>(h, par, nb, nat, reinterpret_cast<const int64_t*>(d),
+                            reinterpret_cast<const T*>(d + off_pos), reinterpret_cast<const T*>(d + off_q),
+                            nullptr, reinterpret_cast<T*>(d + off_e), nullptr,
+                            GRAD ? reinterpret_cast<T*>(d + off_g) : nullptr,
+                            GRAD && gradq ? reinterpret_cast<T*>(d + off_gq) : nullptr, d + off_ws, ws_bytes,
+                            st, nullptr, nullptr, 1 + s);
     launches += g_launches;
     e = cudaMemcpyAsync(energy + o, d + off_e, r * sizeof(T), cudaMemcpyDeviceToHost, st);
+    if (GRAD) {
+      cudaMemcpyAsync(grad + 3 * o, d + off_g, r * 3 * sizeof(T), cudaMemcpyDeviceToHost, st);
+      if (gradq) cudaMemcpyAsync(gradq + o, d + off_gq, r * sizeof(T), cudaMemcpyDeviceToHost, st);
+    }
     cudaEventRecord(h->hev_done[s], st);
   }
   for (int s = 0; s < D4_HOST_SLOTS; ++s)
@@ -569,12 +581,25 @@ int d4b200_energy_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, i
 int d4b200_energy_host_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                            const int64_t* numbers_host, const double* pos_host,
                            const double* q_host, double* energy_host, int chunks) {
-  return run_energy_host<double>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
+  return run_energy_host<double, false>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
 }
 int d4b200_energy_host_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                            const int64_t* numbers_host, const float* pos_host, const float* q_host,
                            float* energy_host, int chunks) {
-  return run_energy_host<float>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
+  return run_energy_host<float, false>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
+}
+int d4b200_energy_gradient_host_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                                    const int64_t* numbers_host, const double* pos_host,
+                                    const double* q_host, double* energy_host, double* grad_host,
+                                    double* gradq_host, int chunks) {
+  return run_energy_host<double, true>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks,
+                                       grad_host, gradq_host);
+}
+int d4b200_energy_gradient_host_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                                    const int64_t* numbers_host, const float* pos_host, const float* q_host,
+                                    float* energy_host, float* grad_host, float* gradq_host, int chunks) {
+  return run_energy_host<float, true>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks,
+                                      grad_host, gradq_host);
 }
 int d4b200_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                         const int64_t* numbers, const double* pos, const double* q,

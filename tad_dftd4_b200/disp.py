@@ -509,14 +509,21 @@ def dftd4_host(
     device: int | torch.device = 0,
     chunks: int = 0,
     out: Tensor | None = None,
-) -> Tensor:
+    with_gradient: bool = False,
+    out_gradient: Tensor | None = None,
+):
     """Atom-resolved D4 energy for inputs that live in HOST memory, evaluated on the B200.
 
     Same arguments as :func:`dftd4` but ``numbers`` / ``positions`` / ``q`` are CPU tensors
     (pin them for full copy/compute overlap) and the result is a (pinned) CPU tensor.  The
     batch is pipelined in chunks through the C ABI (``d4b200_energy_host_*``): the
-    host-to-device copy of one chunk overlaps the kernels of the previous one.  Energies
-    only (use :func:`dftd4` with CUDA tensors for gradients)."""
+    host-to-device copy of one chunk overlaps the kernels of the previous one.
+
+    ``with_gradient=True`` returns ``(energy, gradient)`` with ``gradient = d(energy.sum())/d
+    positions`` (what ``torch.autograd.grad(energy.sum(), positions)`` gives in the reference's
+    ``examples/forces.py``) from the fused energy+gradient kernels
+    (``d4b200_energy_gradient_host_*``); for other upstream gradients use :func:`dftd4` with
+    CUDA tensors."""
     if numbers.shape != positions.shape[:-1]:
         raise ValueError(
             f"Shape of positions ({positions.shape}) is not consistent "
@@ -533,14 +540,25 @@ def dftd4_host(
     dev = torch.device("cuda", device) if isinstance(device, int) else device
     engine = _Engine.get(dev, ga, gc)
     nat = numbers.shape[-1]
-    if nat > _small_limit(engine, positions.dtype, False, model_id):
+    if nat > _small_limit(engine, positions.dtype, bool(with_gradient), model_id):
         raise NotImplementedError("dftd4_host handles batches of small structures; use dftd4 for large ones")
     num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
     pos2 = positions.reshape(-1, nat, 3).contiguous()
     q2 = q.to(positions.dtype).reshape(-1, nat).contiguous()
     if out is None:
         out = torch.empty(num2.shape, dtype=positions.dtype, pin_memory=True)
-    fn = engine.lib.d4b200_energy_host_f64 if positions.dtype == torch.float64 else engine.lib.d4b200_energy_host_f32
+    f64 = positions.dtype == torch.float64
+    if with_gradient:
+        if out_gradient is None:
+            out_gradient = torch.empty(pos2.shape, dtype=positions.dtype, pin_memory=True)
+        fn = engine.lib.d4b200_energy_gradient_host_f64 if f64 else engine.lib.d4b200_energy_gradient_host_f32
+        _lib.check(
+            fn(engine.handle, C.byref(par), num2.shape[0], nat, num2.data_ptr(), pos2.data_ptr(),
+               q2.data_ptr(), out.data_ptr(), out_gradient.data_ptr(), None, int(chunks)),
+            "d4b200_energy_gradient_host",
+        )  # fmt: skip
+        return out.reshape(numbers.shape), out_gradient.reshape(positions.shape)
+    fn = engine.lib.d4b200_energy_host_f64 if f64 else engine.lib.d4b200_energy_host_f32
     _lib.check(
         fn(engine.handle, C.byref(par), num2.shape[0], nat, num2.data_ptr(), pos2.data_ptr(),
            q2.data_ptr(), out.data_ptr(), int(chunks)),

@@ -150,6 +150,11 @@ def test_c3_full_batch_forces(c3):
     an = (g * d).sum((-2, -1))
     assert ((fd - an).abs() / (g.norm(dim=(-2, -1)) + 1e-300)).max() < 1e-5
 
+    # host-buffer forces entry (chunked H2D / kernels / D2H pipeline): same bits
+    e_h, g_h = d4.dftd4_host(numbers_h.pin_memory(), positions_h.pin_memory(), 0.0, PBE0, q=q_h.pin_memory(),
+                             with_gradient=True)
+    assert torch.equal(e_h, e.detach().cpu()) and torch.equal(g_h, g.cpu())
+
     # the fused forward (energy + gradient in one launch) and the energy-only kernel agree
     e_only = d4.dftd4(numbers, positions, 0.0, PBE0, q=q)
     assert ((e.detach() - e_only).abs() / e_only.abs().amax(-1, keepdim=True)).max() < 1e-13

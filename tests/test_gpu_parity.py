@@ -232,3 +232,30 @@ def test_host_buffer_entry_matches_device_entry(dtype, chunks):
     # pageable host memory works too (the driver stages it)
     e_page = d4.dftd4_host(numbers, positions, 0.0, param, q=q, chunks=2)
     assert torch.equal(e_page, e_dev)
+
+
+@pytest.mark.parametrize("model", ["d4", "d4s"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("chunks", [0, 1, 5])
+def test_host_buffer_forces_entry_matches_device_entry(dtype, chunks, model):
+    """d4b200_energy_gradient_host_* == device-pointer call + autograd, bitwise, for every chunking;
+    FP64 results within the north_star tolerances of the golden vectors."""
+    d4 = _d4()
+    case = load_golden("ragged_batch")
+    numbers, positions, q = as_torch(case, torch.device("cpu"), dtype)
+    rep = 5
+    numbers, positions, q = numbers.repeat(rep, 1), positions.repeat(rep, 1, 1), q.repeat(rep, 1)
+    param = dict(case["param"])
+    e_host, g_host = d4.dftd4_host(numbers.pin_memory(), positions.pin_memory(), 0.0, param, q=q.pin_memory(),
+                                   chunks=chunks, model=model, with_gradient=True)
+    assert g_host.device.type == "cpu" and g_host.shape == positions.shape and e_host.shape == numbers.shape
+    pos = positions.cuda().requires_grad_(True)
+    e_dev = d4.dftd4(numbers.cuda(), pos, 0.0, param, q=q.cuda(), model=model)
+    (g_dev,) = torch.autograd.grad(e_dev.sum(), pos)
+    assert torch.equal(e_host, e_dev.detach().cpu())
+    assert torch.equal(g_host, g_dev.cpu())
+    if dtype == torch.float64:
+        key = "d4" if model == "d4" else "d4s"
+        ref, gref = np.tile(case[f"energy_{key}"], (rep, 1)), np.tile(case[f"grad_{key}"], (rep, 1, 1))
+        assert np.abs(e_host.numpy() - ref).max() / np.abs(ref).max() < E_RTOL64
+        assert np.abs(g_host.numpy() - gref).max() < G_ATOL64
