@@ -991,7 +991,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         // Gradient: one thread per owner pair (j,k), all third atoms i.  Every
         // triple is visited from each of its three pairs, so the per-pair sums
         // Gamma (dL/dC60 numerator) and D (dL/d r^2) need no communication.
-        for (int p = tid; p < np; p += NT) {
+        // Whole warps walk the pair list (lanes past the end repeat the last pair and skip the
+        // stores) so that the sweep can use warp-uniform loop bounds.
+        for (int p0 = warp * 32; p0 < np; p0 += NT) {
+          const bool valid = p0 + lane < np;
+          const int p = valid ? p0 + lane : np - 1;
           int j, k;
           pair_lookup(tab.pij, p, j, k);
           const T bs = pa[p];
@@ -1009,9 +1013,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           T accG = T(0), accC = T(0), accS = T(0), accH = T(0), accL = T(0);
           // branch-free sweep over the third atom: for i == j or i == k the visit runs on
           // the owner's own entry with a zero pair factor (contributes exactly 0), so the
-          // body is straight-line code and two visits can be in flight per thread
-#define D4_SWEEP(OPENV, UNITV)                                                                  \
-  _Pragma("unroll 4") for (int i = 0; i < n; ++i) {                                             \
+          // body is straight-line code and four visits can be in flight per thread
+#define D4_SWEEP(OPENV, UNITV, LO, HI)                                                          \
+  _Pragma("unroll 4") for (int i = (LO); i < (HI); ++i) {                                       \
     const int ti = i * (i - 1) / 2;                                                             \
     const bool ok = (i != j) & (i != k);                                                        \
     const int pij = ok ? (i > j ? ti + j : tj + i) : p;                                         \
@@ -1021,13 +1025,42 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
                                 UNITV ? T(0) : T(2) * ATOM(AT_G)[i], gjk2, gj, gk, accG, accC,  \
                                 accS, accH, accL);                                              \
   }
+          // closed structure, unit upstream weights: the two stash indices of a visit are affine
+          // in i inside each of the ranges i < k, k < i < j, j < i -- no selects, no index
+          // arithmetic beyond one running triangle offset
+#define D4_VISIT_U(PIJ, PIK)                                                                     \
+  grad_visit<T, false, true>(pa[PIJ], pP[PIJ], pu[PIJ], pa[PIK], pP[PIK], pu[PIK], bb, b2, twob,  \
+                             cjk, iP, sPu, kAi, kB, T(0), gjk2, gj, gk, accG, accC, accS, accH, accL);
           if (open) {
-            D4_SWEEP(true, false)
+            D4_SWEEP(true, false, 0, n)
           } else if (A.gin == nullptr) {
-            D4_SWEEP(false, true)
+            const int jlo = __reduce_min_sync(0xffffffffu, j), jhi = __reduce_max_sync(0xffffffffu, j);
+            if (jlo == jhi) {  // the warp's pairs share j (rows of 32 or more pairs: always)
+              const int klo = __reduce_min_sync(0xffffffffu, k), khi = __reduce_max_sync(0xffffffffu, k);
+#pragma unroll 4
+              for (int i = 0; i < klo; ++i) {  // i < k < j
+                D4_VISIT_U(tj + i, tk + i)
+              }
+              D4_SWEEP(false, true, klo, khi + 1)  // i crosses the k of some lanes
+              int ti = (khi + 1) * khi / 2;
+#pragma unroll 4
+              for (int i = khi + 1; i < j; ++i) {  // k < i < j
+                D4_VISIT_U(tj + i, ti + k)
+                ti += i;
+              }
+              ti = (j + 1) * j / 2;
+#pragma unroll 4
+              for (int i = j + 1; i < n; ++i) {  // k < j < i
+                D4_VISIT_U(ti + j, ti + k)
+                ti += i;
+              }
+            } else {
+              D4_SWEEP(false, true, 0, n)
+            }
           } else {
-            D4_SWEEP(false, false)
+            D4_SWEEP(false, false, 0, n)
           }
+#undef D4_VISIT_U
 #undef D4_SWEEP
           if (!open) {
             if (A.gin == nullptr) {  // unit upstream weights: W = 6, G is also the energy share
@@ -1041,11 +1074,13 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           }
           if (pz) accG = accC = accS = accH = accL = T(0);
           const T accD = fma(accC, inv_b, T(0.375) * accS);
-          out0[p] = accG;
-          out1[p] = accD;
-          if (A.energy) {
-            out0[2 * CP + p] = accH;
-            out0[3 * CP + p] = accL;
+          if (valid) {
+            out0[p] = accG;
+            out1[p] = accD;
+            if (A.energy) {
+              out0[2 * CP + p] = accH;
+              out0[3 * CP + p] = accL;
+            }
           }
         }
         __syncthreads();  // all reads of the stash done -> planes become outputs
