@@ -993,6 +993,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         // Gamma (dL/dC60 numerator) and D (dL/d r^2) need no communication.
         // Whole warps walk the pair list (lanes past the end repeat the last pair and skip the
         // stores) so that the sweep can use warp-uniform loop bounds.
+        const T ifac9 = d4_rcp(P.fac9);
         for (int p0 = warp * 32; p0 < np; p0 += NT) {
           const bool valid = p0 + lane < np;
           const int p = valid ? p0 + lane : np - 1;
@@ -1074,6 +1075,12 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           }
           if (pz) accG = accC = accS = accH = accL = T(0);
           const T accD = fma(accC, inv_b, T(0.375) * accS);
+          if constexpr (!D4S) {
+            // dL/dC6(q=0)_jk = Gamma / (2 C6): C6(q=0) = (P'_jk r^5 / fac9)^2 >= 0 is recovered from
+            // the stash instead of a second 23-term dot product in the coefficient pass
+            const T w = (Pjk * ifac9) * b2;
+            accG = pz ? T(0) : accG * (T(0.5) * d4_rcp((w * w) * bb));
+          }
           if (valid) {
             out0[p] = accG;
             out1[p] = accD;
@@ -1288,13 +1295,19 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       } else {
       // phase 7: per-pair coefficients
       //   pa <- G2 F          (dL/dC6q)
-      //   pP <- Gamma/(2 C60) (dL/dC60)
+      //   pP =  Gamma/(2 C60) (dL/dC60, from the sweep)
       //   pu <- 2 D + G2 C6q F'/r   (radial force coefficient, CN chain added later)
+      if constexpr (sizeof(T) == 8) {  // C6(q) of all pairs on the tensor path -> scratch plane out1 (free again)
+        c6_tiles<AS>(Aq, out1, tab.pij, n, warp, lane, NW);
+        __syncthreads();
+      }
       for (int p = tid; p < np; p += NT) {
         int i, j;
         pair_lookup(tab.pij, p, i, j);
         const T r2 = fabs(pa[p]);  // stash: signed squared distance
-        const T c6q = dot23<T, AS>(Aq, i, j), c60 = dot23<T, AS>(A0, i, j);
+        T c6q;
+        if constexpr (sizeof(T) == 8) c6q = out1[p];
+        else c6q = dot23<T, AS>(Aq, i, j);
         const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
         T coefq = T(0), fc = T(2) * pu[p], e2 = T(0);
         if (r2 <= P.disp2_sq) {
@@ -1317,8 +1330,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           e2 = c6q * F;
         }
         if (A.energy) out0[4 * CP + p] = e2;
-        pa[p] = coefq;
-        pP[p] = c60 != T(0) ? pP[p] / (T(2) * c60) : T(0);
+        pa[p] = coefq;  // pP already holds Gamma / (2 C60) (scaled at the end of the sweep)
         pu[p] = fc;
       }
       __syncthreads();
