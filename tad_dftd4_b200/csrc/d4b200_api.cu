@@ -214,7 +214,9 @@ Work carve_work(void* ws, int nbatch) {
 constexpr int MAX_SMS = 160;
 
 size_t scratch_bytes_class(int c, int cap, size_t elem) {
-  return align_up((size_t)MAX_SMS * class_occ_cap(c) * 5 * (cap * (cap - 1) / 2) * elem, 256);
+  // per CTA: five pair planes + the D4S weight table [cap][D4S_ECAP][D4S_WSTR] (Lay<>::scratch_stride)
+  const size_t per_cta = (size_t)5 * (cap * (cap - 1) / 2) + (size_t)cap * D4S_ECAP * D4S_WSTR;
+  return align_up((size_t)MAX_SMS * class_occ_cap(c) * per_cta * elem, 256);
 }
 
 template <typename T>

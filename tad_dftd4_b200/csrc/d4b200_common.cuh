@@ -14,6 +14,8 @@ constexpr int NFREQ = 23;
 constexpr int SMALL_MAX = 128;  // largest structure of the one-CTA-per-structure family
 constexpr int NCLASS = 5;       // size classes of the small family
 constexpr int HIST_BINS = SMALL_MAX + 2;
+constexpr int D4S_ECAP = 8;         // D4S weight table: distinct elements per structure it can hold
+constexpr int D4S_WSTR = 2 * NREF;  // table entry: gw[7], d gw/d cn [7]
 
 // Per-element tables in device memory (layout: tad_dftd4_b200/tables.py).
 // Weight-related tables are always double (the reference evaluates the

@@ -122,6 +122,12 @@ enum { WT_Q = 0, WT_0, WT_ZGD, WT_Z0GD, WT_DZG };
 // tensor-core contraction (mma.m8n8k4) bank-conflict free.
 constexpr int a_stride(int cap) { return cap + (4 - cap % 16 + 16) % 16; }
 
+// D4S: the Gaussian weights of an atom depend on the partner only through the partner's ELEMENT
+// (model/d4s.py:61-67, 191-198), so they are tabulated once per (atom, distinct element of the
+// structure) instead of being re-evaluated for every pair (14 float64 exponentials per side).
+// Structures with more than D4S_ECAP distinct elements use the per-pair evaluation
+// (D4S_ECAP, D4S_WSTR: d4b200_common.cuh).
+
 template <typename T, bool GRAD, bool D4S, int CAP>
 struct Lay {
   static constexpr int CP = CAP * (CAP - 1) / 2;
@@ -140,8 +146,11 @@ struct Lay {
   static constexpr size_t atoms = abuf + al16(abuf_elems * sizeof(T));
   static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
   static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
-  static constexpr size_t total = ints + al16((2 * CAP + 8) * sizeof(int));
+  // zs[CAP], idx[CAP], (D4S: element index per atom [CAP]), misc[32]
+  static constexpr size_t total = ints + al16(((D4S ? 3 : 2) * CAP + 32) * sizeof(int));
   static constexpr int scratch_planes = GRAD ? 5 : 3;  // gradient: Gamma, D, E3 shares (2), E2; energy: E3 shares (2), E2
+  // per-CTA stride of the L2 scratch: the planes, then (D4S) the weight table [CAP][D4S_ECAP][D4S_WSTR]
+  static constexpr size_t scratch_stride = size_t(scratch_planes) * CP + (D4S ? size_t(CAP) * D4S_ECAP * D4S_WSTR : 0);
 };
 
 // Unnormalised Gaussian weights S_a (and dS_a/dcn) of one atom for a given weighting
@@ -180,6 +189,21 @@ __device__ __forceinline__ void d4s_gauss(const double* __restrict__ refcn, cons
     dS[a] = ds;
     norm += s;
     dnorm += ds;
+  }
+}
+
+// normalised weights gw_a (and d gw_a/d cn) of one atom for a weighting factor, as the compute type
+template <typename T, bool DERIV>
+__device__ __forceinline__ void d4s_weights(const double* __restrict__ refcn, const int* __restrict__ refc, int z,
+                                            double cn, double wf, T (&g)[NREF], T (&dg)[NREF]) {
+  double S[NREF], dS[NREF], norm, dnorm;
+  d4s_gauss<DERIV>(refcn, refc, z, cn, wf, S, dS, norm, dnorm);
+  const double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+#pragma unroll
+  for (int a = 0; a < NREF; ++a) {
+    const double gg = S[a] * inv;
+    g[a] = (T)gg;
+    dg[a] = DERIV ? (T)((dS[a] - gg * dnorm) * inv) : T(0);
   }
 }
 
@@ -424,7 +448,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
                             : reinterpret_cast<T*>(smem + L::wts);
   int* const zs = reinterpret_cast<int*>(smem + L::ints);
   int* const idx = zs + CAP;
-  int* const misc = idx + CAP;  // [0]=work item, [1]=n, [2]=any_open, [3]=skip, [4]=chunk counter, [5]=near pairs
+  int* const ei = idx + CAP;  // D4S: index of the atom's element among the distinct elements of the structure
+  // [0]=work item, [1]=n, [2]=any_open, [3]=skip, [4]=chunk counter, [5]=near pairs,
+  // D4S: [8..11]=element bit set, [12..12+D4S_ECAP)=distinct elements
+  int* const misc = idx + (D4S ? 2 : 1) * CAP;
 #define ATOM(k) (at + (k) * CAP)
 #define WT(k) (wt + (k) * NREF * CAP)
 
@@ -436,8 +463,9 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   const int range_begin = A.wk.class_range[2 * A.cls];
   const int range_end = A.wk.class_range[2 * A.cls + 1];
   // per-CTA, L2-resident scratch planes for per-pair results
-  T* const out0 = A.scratch + (size_t)blockIdx.x * L::scratch_planes * CP;
+  T* const out0 = A.scratch + (size_t)blockIdx.x * L::scratch_stride;
   T* const out1 = out0 + CP;
+  T* const wtab = out0 + size_t(L::scratch_planes) * CP;  // D4S weight table of the current structure
   long long tlast = A.phase ? clock64() : 0;
 #define PHASE(k)                                                        \
   if (A.phase && tid == 0) {                                            \
@@ -481,6 +509,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         misc[3] = count > CAP;
         misc[4] = 0;
         misc[5] = 0;
+        if (D4S) misc[8] = misc[9] = misc[10] = misc[11] = 0;
         if (bad) atomicOr(A.wk.status, D4B200_STATUS_BAD_NUMBER);
         if (count > CAP) atomicOr(A.wk.status, D4B200_STATUS_TOO_LARGE);
       }
@@ -823,6 +852,37 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     PHASE(3);
 
     bool open = false;
+    int nel = 0;           // D4S: distinct elements of the structure
+    bool use_tab = false;  // D4S: weights come from the per-(atom, element) table
+    if constexpr (D4S) {
+      for (int i = tid; i < n; i += NT) atomicOr(&misc[8 + (zs[i] >> 5)], (int)(1u << (zs[i] & 31)));
+      __syncthreads();
+      nel = __popc(misc[8]) + __popc(misc[9]) + __popc(misc[10]) + __popc(misc[11]);
+      use_tab = nel <= D4S_ECAP;
+      if (use_tab) {
+        for (int i = tid; i < n; i += NT) {
+          const int z = zs[i], w = z >> 5;
+          int e = __popc((unsigned)misc[8 + w] & ((1u << (z & 31)) - 1u));
+          for (int ww = 0; ww < w; ++ww) e += __popc(misc[8 + ww]);
+          ei[i] = e;
+          misc[12 + e] = z;  // every atom of the element writes the same value
+        }
+        __syncthreads();
+        for (int t = tid; t < n * nel; t += NT) {
+          const int i = t / nel, e = t - i * nel;
+          const int zi = zs[i];
+          T g[NREF], dg[NREF];
+          d4s_weights<T, GRAD>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i],
+                               tab.wfpair[zi * NELEM + misc[12 + e]], g, dg);
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) {
+            wtab[(size_t)t * D4S_WSTR + a] = g[a];
+            if (GRAD) wtab[(size_t)t * D4S_WSTR + NREF + a] = dg[a];
+          }
+        }
+        __syncthreads();
+      }
+    }
     if constexpr (D4S) {
       // ---- D4S: pair-dependent Gaussian weights (model/d4s.py:109-290) ------
       // C6_ij = sum_ab rc6[Zi,Zj,a,b] (zeta_ia gw_ia|Zj) (zeta_jb gw_jb|Zi) with the weights
@@ -833,19 +893,25 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         pair_lookup(tab.pij, p, i, j);
         const T r2 = pa[p];
         const int zi = zs[i], zj = zs[j];
-        double S[NREF], dS[NREF], norm, dnorm;
-        // partner j as seen by i
-        d4s_gauss<false>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], S, dS, norm, dnorm);
-        double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+        T gi[NREF], gj[NREF], dgu[NREF];
+        if (use_tab) {
+          const T* wj = wtab + (size_t)(j * nel + ei[i]) * D4S_WSTR;  // partner j as seen by i
+          const T* wi = wtab + (size_t)(i * nel + ei[j]) * D4S_WSTR;
+#pragma unroll
+          for (int a = 0; a < NREF; ++a) {
+            gj[a] = wj[a];
+            gi[a] = wi[a];
+          }
+        } else {
+          d4s_weights<T, false>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], gj, dgu);
+          d4s_weights<T, false>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], gi, dgu);
+        }
         T v[NREF], v0[NREF];
 #pragma unroll
         for (int bq = 0; bq < NREF; ++bq) {
-          const T g = (T)(S[bq] * inv);
-          v[bq] = WT(WT_Q)[j * NREF + bq] * g;
-          v0[bq] = WT(WT_0)[j * NREF + bq] * g;
+          v[bq] = WT(WT_Q)[j * NREF + bq] * gj[bq];
+          v0[bq] = WT(WT_0)[j * NREF + bq] * gj[bq];
         }
-        d4s_gauss<false>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], S, dS, norm, dnorm);
-        inv = norm > 0.0 ? 1.0 / norm : 0.0;
         const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
         T c6q = T(0), c60 = T(0);
 #pragma unroll
@@ -857,7 +923,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             t += rab * v[bq];
             t0 += rab * v0[bq];
           }
-          const T g = (T)(S[a] * inv);
+          const T g = gi[a];
           c6q += WT(WT_Q)[i * NREF + a] * g * t;
           c60 += WT(WT_0)[i * NREF + a] * g * t0;
         }
@@ -1203,23 +1269,20 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const T r2 = fabs(pa[p]);  // stash: signed squared distance
           const int zi = zs[i], zj = zs[j];
           const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
-          double S[NREF], dS[NREF], norm, dnorm;
           T gi[NREF], dgi[NREF], gj[NREF], dgj[NREF];
-          d4s_gauss<true>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], S, dS, norm, dnorm);
-          double inv = norm > 0.0 ? 1.0 / norm : 0.0;
+          if (use_tab) {
+            const T* wi = wtab + (size_t)(i * nel + ei[j]) * D4S_WSTR;
+            const T* wj = wtab + (size_t)(j * nel + ei[i]) * D4S_WSTR;
 #pragma unroll
-          for (int a = 0; a < NREF; ++a) {
-            const double g = S[a] * inv;
-            gi[a] = (T)g;
-            dgi[a] = (T)((dS[a] - g * dnorm) * inv);
-          }
-          d4s_gauss<true>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], S, dS, norm, dnorm);
-          inv = norm > 0.0 ? 1.0 / norm : 0.0;
-#pragma unroll
-          for (int a = 0; a < NREF; ++a) {
-            const double g = S[a] * inv;
-            gj[a] = (T)g;
-            dgj[a] = (T)((dS[a] - g * dnorm) * inv);
+            for (int a = 0; a < NREF; ++a) {
+              gi[a] = wi[a];
+              dgi[a] = wi[NREF + a];
+              gj[a] = wj[a];
+              dgj[a] = wj[NREF + a];
+            }
+          } else {
+            d4s_weights<T, true>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], gi, dgi);
+            d4s_weights<T, true>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], gj, dgj);
           }
           // t = R v, s = R^T u for both flavours
           T c6q = T(0), c60 = T(0), dq_cni = T(0), d0_cni = T(0), dq_qi = T(0);
