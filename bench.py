@@ -598,3 +598,9 @@ def main():
 
 if __name__ == "__main__":
     main()
+    # The JSON line is out: leave without interpreter / library teardown.  One run in a few dozen
+    # aborted AFTER printing its result (daemon sampler thread, fork-based generator pool, OpenMP and
+    # CUDA runtimes all unwinding at once); a benchmark has nothing to save at that point.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
