@@ -232,3 +232,38 @@ def param_gradient(numbers, positions, q, param, g=None, disp2=60.0, disp3=40.0,
                 out[5] += h * alp / 3.0 * (1.0 / R0[i, j] + 1.0 / R0[i, k] + 1.0 / R0[j, k])
                 out[6] += h * (lg[i, j] + lg[i, k] + lg[j, k]) / 3.0
     return out
+
+
+def grad_visit_reference(a, b, c, Pij, Pik, Pjk, uij, uik, ujk, alp):
+    """One owner-pair visit, textbook form: e' and d e'/d b for the owner pair (j,k) with
+    squared distances a = r_ij^2, b = r_jk^2, c = r_ik^2 (threebody.py:113-160 per pair)."""
+    s = (a + b - c) * (a - b + c) * (b + c - a)
+    dsdb = (a - b + c) * (b + c - a) - (a + b - c) * (b + c - a) + (a + b - c) * (a - b + c)
+    t = uij * uik * ujk
+    f = 1.0 / (1.0 + 6.0 * t)
+    pf = Pij * Pik * Pjk * f
+    abc = a * b * c
+    e = pf * (0.375 * s + abc)
+    de = (e * (alp * f * t - 2.5) + pf * abc) / b + 0.375 * pf * dsdb
+    return e, de
+
+
+def grad_visit_kernel(a, b, c, Pij, Pik, Pjk, uij, uik, ujk, alp):
+    """The same visit in the form ``grad_visit<T, false, true>`` of csrc/d4b200_small.cuh evaluates
+    it (21 FP64 instructions): owner-pair invariants folded into the damping denominator,
+    f t = (1 - f)/6, the pair factor applied in the accumulating FMAs, 1/b and 0.375 applied
+    once per owner pair.  Returns the three accumulator increments and the assembled (e', de')."""
+    iP = 1.0 / Pjk
+    sPu, kA = 6.0 * ujk * iP, alp / 6.0
+    kAi, kB = kA * iP, kA - 2.5
+    t1, Y = a - c, (a + c) - b
+    XZ = b * b - t1 * t1
+    s = XZ * Y
+    dsdb = 2.0 * b * Y - XZ
+    abc = (a * c) * b
+    fp = 1.0 / (iP + sPu * (uij * uik))  # = P'_jk f
+    pf = (Pij * Pik) * fp
+    wa = 0.375 * s + abc
+    inner = wa * (kB - kAi * fp) + abc
+    dG, dC, dS = pf * wa, pf * inner, pf * dsdb
+    return (dG, dC, dS), (dG, dC / b + 0.375 * dS)

@@ -68,3 +68,24 @@ def test_param_gradient_model(name, with_s10):
     for k, r in zip(keys, ref):
         v = got[PARAM_KEYS.index(k)]
         assert abs(v - r.item()) <= 1e-12 + 1e-9 * abs(r.item()), (k, v, r.item())
+
+
+def test_gradient_visit_factorisation():
+    """The 21-instruction gradient visit of the kernel equals the textbook expression
+    (random triangles, damping arguments and alp)."""
+    from kernel_model import grad_visit_kernel, grad_visit_reference
+
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        x = rng.normal(size=(3, 3)) * 3.0
+        a, b, c = ((x[0] - x[1]) ** 2).sum(), ((x[1] - x[2]) ** 2).sum(), ((x[0] - x[2]) ** 2).sum()
+        P = rng.uniform(1e-6, 1e-2, size=3)
+        u = rng.uniform(1e-3, 30.0, size=3)
+        alp = rng.choice([16.0, 14.0, 12.5])
+        e_ref, de_ref = grad_visit_reference(a, b, c, *P, *u, alp)
+        _, (e, de) = grad_visit_kernel(a, b, c, *P, *u, alp)
+        # scale: the two terms of 0.375 s + abc can cancel (flat triangles)
+        f = 1.0 / (1.0 + 6.0 * u.prod())
+        scale = P.prod() * f * a * b * c
+        assert abs(e - e_ref) <= 1e-12 * scale
+        assert abs(de - de_ref) <= 1e-11 * scale * (alp + 10.0) / min(a, b, c)
