@@ -49,9 +49,9 @@ def get_params(*, method: str, functional: str | None, variant: str | None = Non
     ``get_params(method="d4", functional="pbe0")``.  Like the reference this
     returns only the functional's own block (no merge of s6/s9/alp defaults)."""
     method = getattr(method, "value", method)
-    if method not in ("d4",):
-        raise ValueError(f"'{method}' is not a valid DispersionMethod for this package")
-    table = _load(method)
+    if method not in ("d3", "d4", "d5"):  # the reference's DispersionMethod enum (parameters/base.py:88-93)
+        raise ValueError(f"'{method}' is not a valid DispersionMethod")
+    table = _load(method)  # only the D4 table ships with this package: d3/d5 -> FileNotFoundError
     if functional in (None, "default"):
         default_section = table["default"]
         if variant not in default_section[method]:

@@ -1,0 +1,192 @@
+"""
+Host-side interface tests written after the reference's own test-suite (same names, same
+assertions), run against ``tad_dftd4_b200`` on the CPU -- no kernels are involved:
+
+* ``test/test_param/test_read.py:29-51`` and ``test/test_param/test_fail.py:31-85``
+  (``get_params``: defaults, functionals, DOI, unknown functional / variant / method file),
+* ``test/test_cutoff/test_general.py:29-72`` and ``test/test_cutoff/test_types.py:30-65``
+  (``Cutoff``: dtype / device handling, defaults, tensors and numbers),
+* ``test/test_disp/test_general.py`` / ``test/test_d4/test_general.py`` style argument
+  checks of ``dftd4`` that fail before any device work (shape mismatches, unknown model,
+  missing damping parameters).
+"""
+from __future__ import annotations
+
+from unittest.mock import patch
+
+import pytest
+import torch
+
+import tad_dftd4_b200 as d4
+from tad_dftd4_b200 import damping, defaults
+from tad_dftd4_b200.cutoff import Cutoff
+from tad_dftd4_b200.damping import get_params
+
+
+# ---- test/test_param/test_read.py ------------------------------------------------------------
+def test_default() -> None:
+    params = get_params(method="d4", variant="bj-eeq-atm", functional=None)
+    assert isinstance(params, dict)
+    assert "s6" in params
+
+
+@pytest.mark.parametrize("func", ["pbe", "b3lyp", "revpbe"])
+def test_func(func: str) -> None:
+    params = get_params(method="d4", variant="bj-eeq-atm", functional=func)
+    assert isinstance(params, dict)
+    assert "a1" in params
+    assert "a2" in params
+
+
+def test_with_doi() -> None:
+    params = get_params(method="d4", variant="bj-eeq-atm", functional="pbe", keep_doi=True)
+    assert isinstance(params, dict)
+    assert "doi" in params
+    assert "doi" not in get_params(method="d4", variant="bj-eeq-atm", functional="pbe")
+
+
+# ---- test/test_param/test_fail.py ------------------------------------------------------------
+def test_unknown_func() -> None:
+    with pytest.raises(KeyError):
+        get_params(method="d4", variant="d4-eeq-bj", functional="unknown")
+
+
+def test_unknown_variant() -> None:
+    with pytest.raises(KeyError):
+        get_params(method="d4", functional="pbe", variant="unknown")
+
+
+def test_unknown_variant_default() -> None:
+    with pytest.raises(KeyError, match="not found in default parameters"):
+        get_params(method="d4", functional=None, variant="no-such-variant")
+
+
+def test_unknown_variant_functional() -> None:
+    with pytest.raises(KeyError, match="not found for functional"):
+        get_params(method="d4", functional="pbe", variant="no-such-variant")
+
+
+def test_missing_toml() -> None:
+    """Parameter file does not exist (d5 has none; this package ships the D4 table only)."""
+    with pytest.raises(FileNotFoundError, match="missing"):
+        get_params(method="d5", functional="pbe", variant="x")
+
+
+def test_invalid_method() -> None:
+    with pytest.raises(ValueError, match="not a valid DispersionMethod"):
+        get_params(method="dx", functional="pbe")
+
+
+def test_default_variant_for_functional() -> None:
+    params = get_params(method="d4", functional="pbe", variant=None)
+    assert isinstance(params, dict)
+    assert "a1" in params
+
+
+def test_method_missing_in_functional() -> None:
+    fake_table = {"default": {"d4": ["bj-eeq-atm"]}, "parameter": {"pbe": {"reference": {}}}}
+    with patch.object(damping, "_load", return_value=fake_table):
+        with pytest.raises(KeyError, match="Method"):
+            get_params(method="d4", functional="pbe", variant="bj-eeq-atm")
+
+
+# ---- test/test_cutoff/test_general.py --------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_change_type(dtype: torch.dtype) -> None:
+    cutoff = Cutoff().type(dtype)
+    assert cutoff.dtype == dtype
+    assert cutoff.disp2.dtype == dtype
+    assert cutoff.disp3.dtype == dtype
+    assert cutoff.cn.dtype == dtype
+    assert cutoff.cn_eeq.dtype == dtype
+
+
+def test_change_type_fail() -> None:
+    cutoff = Cutoff()
+    with pytest.raises(AttributeError):
+        cutoff.dtype = torch.float64
+    with pytest.raises(ValueError):
+        cutoff.type(torch.bool)
+
+
+def test_change_device_cpu() -> None:
+    device = torch.device("cpu")
+    cutoff = Cutoff().to(device)
+    assert cutoff.device == device
+    assert cutoff.disp2.device == device
+    assert cutoff.disp3.device == device
+    assert cutoff.cn.device == device
+    assert cutoff.cn_eeq.device == device
+
+
+def test_change_device_fail() -> None:
+    cutoff = Cutoff()
+    with pytest.raises(AttributeError):
+        cutoff.device = torch.device("cpu")
+
+
+# ---- test/test_cutoff/test_types.py ----------------------------------------------------------
+def test_defaults() -> None:
+    cutoff = Cutoff()
+    assert pytest.approx(defaults.D4_DISP2_CUTOFF) == cutoff.disp2.cpu()
+    assert pytest.approx(defaults.D4_DISP3_CUTOFF) == cutoff.disp3.cpu()
+    assert pytest.approx(defaults.D4_CN_CUTOFF) == cutoff.cn.cpu()
+    assert pytest.approx(defaults.D4_CN_EEQ_CUTOFF) == cutoff.cn_eeq.cpu()
+
+
+def test_tensor() -> None:
+    tmp = torch.tensor([1.0])
+    cutoff = Cutoff(disp2=tmp)
+    assert isinstance(cutoff.disp2, torch.Tensor)
+    assert isinstance(cutoff.disp3, torch.Tensor)
+    assert isinstance(cutoff.cn, torch.Tensor)
+    assert isinstance(cutoff.cn_eeq, torch.Tensor)
+    assert pytest.approx(tmp.cpu()) == cutoff.disp2.cpu()
+
+
+@pytest.mark.parametrize("vals", [(1, 2, -3, 4), (1.0, 2.0, 3.0, -4.0)])
+def test_int_float(vals) -> None:
+    disp2, disp3, cn, cn_eeq = vals
+    cutoff = Cutoff(disp2, disp3, cn, cn_eeq)
+    for name in ("disp2", "disp3", "cn", "cn_eeq"):
+        assert isinstance(getattr(cutoff, name), torch.Tensor)
+    assert pytest.approx(vals[0]) == cutoff.disp2.cpu()
+    assert pytest.approx(vals[1]) == cutoff.disp3.cpu()
+    assert pytest.approx(vals[2]) == cutoff.cn.cpu()
+    assert pytest.approx(vals[3]) == cutoff.cn_eeq.cpu()
+
+
+# ---- argument checks of dftd4 that precede any device work -------------------------------------
+PARAM = {"a1": 0.4, "a2": 5.0}
+
+
+def test_fail_shape_positions() -> None:
+    numbers = torch.tensor([1, 1])
+    positions = torch.zeros(3, 3)
+    with pytest.raises(ValueError, match="positions"):
+        d4.dftd4(numbers, positions, 0.0, PARAM)
+
+
+def test_fail_shape_q_and_radii() -> None:
+    numbers = torch.tensor([1, 1])
+    positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.4]])
+    with pytest.raises(ValueError, match="charges"):
+        d4.dftd4(numbers, positions, 0.0, PARAM, q=torch.zeros(3))
+    with pytest.raises(ValueError, match="covalent radii"):
+        d4.dftd4(numbers, positions, 0.0, PARAM, rcov=torch.zeros(3))
+    with pytest.raises(ValueError, match="r4r2"):
+        d4.dftd4(numbers, positions, 0.0, PARAM, r4r2=torch.zeros(3))
+
+
+def test_fail_unknown_model() -> None:
+    numbers = torch.tensor([1, 1])
+    positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.4]])
+    with pytest.raises(ValueError, match="Unknown model"):
+        d4.dftd4(numbers, positions, 0.0, PARAM, model="d6")
+
+
+def test_no_cpu_fallback() -> None:
+    numbers = torch.tensor([1, 1])
+    positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.4]])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d4.dftd4(numbers, positions, 0.0, PARAM, q=torch.zeros(2))
