@@ -439,6 +439,10 @@ def dftd4(
             f"Shape of atomic charges ({q.shape}) is not consistent "
             f"with atomic numbers ({numbers.shape}).",
         )
+    if param.get("a1") is None or param.get("a2") is None:
+        # raised by the reference's RationalDamping on any device (damping/functions.py:255-259)
+        missing = [k for k in ("a1", "a2") if param.get(k) is None]
+        raise TypeError(f"RationalDamping (order 6) requires keyword(s): {', '.join(missing)}")
     if positions.dtype not in (torch.float64, torch.float32):
         raise NotImplementedError(f"dtype {positions.dtype} is not supported (float64/float32)")
     if positions.device.type != "cuda":

@@ -190,3 +190,69 @@ def test_no_cpu_fallback() -> None:
     positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.4]])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         d4.dftd4(numbers, positions, 0.0, PARAM, q=torch.zeros(2))
+
+
+# ---- test/test_disp/test_general.py:31-145 (class interface) ------------------------------------
+def _h2():
+    return (torch.tensor([1, 1]), torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.0]]), torch.tensor(0.0),
+            d4.Param(s6=torch.tensor(1.0)))  # fmt: skip
+
+
+def test_fail_class() -> None:
+    from tad_dftd4_b200.damping import RationalDamping
+    from tad_dftd4_b200.dispersion import Disp, TwoBodyTerm
+
+    numbers, positions, charge, param = _h2()
+    disp = Disp()
+    disp.register(TwoBodyTerm(damping_fn=RationalDamping(), charge_dependent=True))
+    with pytest.raises(ValueError):  # rcov wrong shape
+        disp.calculate(numbers, positions, charge, param, rcov=torch.tensor([1.0]))
+    with pytest.raises(ValueError):  # r4r2 wrong shape
+        disp.calculate(numbers, positions, charge, param, r4r2=torch.tensor([1.0]))
+    with pytest.raises(ValueError):  # rvdw wrong shape
+        disp.calculate(numbers, positions, charge, param, rvdw=torch.tensor([1.0]))
+    with pytest.raises(ValueError):  # atomic partial charges wrong shape
+        disp.calculate(numbers, positions, charge, param, q=torch.tensor([1.0]))
+    with pytest.raises(ValueError):  # wrong numbers
+        disp.calculate(torch.tensor([1]), positions, charge, param, q=torch.tensor([0.5, -0.5]))
+
+
+def test_fail_charges_not_required() -> None:
+    from tad_dftd4_b200.damping import RationalDamping
+    from tad_dftd4_b200.dispersion import Disp, TwoBodyTerm
+
+    numbers, positions, charge, param = _h2()
+    disp = Disp()
+    disp.register(TwoBodyTerm(damping_fn=RationalDamping(), charge_dependent=False))
+    with pytest.raises(RuntimeError):
+        disp.calculate(numbers=numbers, positions=positions, charge=charge, param=param,
+                       q=torch.tensor([0.5, -0.5]))  # fmt: skip
+
+
+def test_fail_damping_param() -> None:
+    from tad_dftd4_b200.damping import RationalDamping
+    from tad_dftd4_b200.dispersion import Disp, TwoBodyTerm
+
+    numbers, positions, charge, param = _h2()
+    disp = Disp()
+    disp.register(TwoBodyTerm(damping_fn=RationalDamping()))
+    with pytest.raises(TypeError):  # a1 / a2 missing
+        disp.calculate(numbers=numbers, positions=positions, charge=charge, param=param)
+
+
+def test_fail_model() -> None:
+    from tad_dftd4_b200.dispersion import DispD4
+
+    with pytest.raises(ValueError):
+        DispD4(model="wrong")
+
+
+def test_terms() -> None:
+    from tad_dftd4_b200.dispersion import Disp, TwoBodyTerm
+
+    disp = Disp()
+    assert len(disp.terms) == 0
+    disp.register(TwoBodyTerm())
+    assert len(disp.terms) == 1
+    disp.deregister(TwoBodyTerm())
+    assert len(disp.terms) == 0
