@@ -162,3 +162,18 @@ def test_get_properties_default_charges():
     assert (q.cpu() - q_ref).abs().max().item() < 1e-12
     assert (c6.cpu() - c6_ref).abs().max().item() / c6_ref.abs().max().item() < 1e-10
     assert (alpha.cpu() - alpha_ref).abs().max().item() / alpha_ref.abs().max().item() < 1e-10
+
+
+def test_charge_as_int():
+    """test/test_d4/test_general.py:32-52 of the reference: the total charge may be a Python int,
+    a Python float or a tensor."""
+    d4 = _d4()
+    numbers = torch.tensor([1, 1], device=DEV)
+    positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.0]], dtype=F64, device=DEV)
+    param = d4.Param(s6=torch.tensor(1.0), s8=torch.tensor(1.0), a1=torch.tensor(0.4), a2=torch.tensor(5.0))
+    energy_int = d4.dftd4(numbers, positions, 0, param)
+    energy_float = d4.dftd4(numbers, positions, 0.0, param)
+    energy_tensor = d4.dftd4(numbers, positions, torch.tensor(0.0), param)
+    assert torch.allclose(energy_int, energy_tensor)
+    assert torch.allclose(energy_float, energy_tensor)
+    assert energy_int.shape == numbers.shape and bool((energy_int < 0).all())
