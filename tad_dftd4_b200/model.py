@@ -19,7 +19,7 @@ __all__ = ["D4Model", "D4SModel"]
 
 
 class _Model:
-    __slots__ = ("numbers", "ga", "gc", "wf", "ref_charges", "device", "dtype")
+    __slots__ = ("numbers", "ga", "gc", "wf", "ref_charges", "_device", "_dtype")
     _key = "d4"
 
     def __init__(self, numbers=None, ga: float = defaults.GA_DEFAULT, gc: float = defaults.GC_DEFAULT,
@@ -35,8 +35,36 @@ class _Model:
         self.gc = float(gc)
         self.wf = defaults.WF_DEFAULT if wf is None else float(wf)
         self.ref_charges = ref_charges
-        self.device = device
-        self.dtype = dtype if dtype is not None else torch.get_default_dtype()
+        self._device = device if device is not None else (
+            numbers.device if isinstance(numbers, torch.Tensor) else torch.device("cpu"))
+        self._dtype = dtype if dtype is not None else torch.get_default_dtype()
+
+    # read-only like the reference's TensorLike base (test/test_model/test_general.py:30-66)
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def _clone(self, **kw):
+        args = dict(numbers=self.numbers, ga=self.ga, gc=self.gc, wf=self.wf, ref_charges=self.ref_charges,
+                    device=self._device, dtype=self._dtype)  # fmt: skip
+        args.update(kw)
+        return type(self)(**args)
+
+    def type(self, dtype: torch.dtype):
+        """Copy of the model with another floating-point type."""
+        if dtype not in (torch.float16, torch.float32, torch.float64):
+            raise ValueError(f"Only float types are allowed (got {dtype}).")
+        return self._clone(dtype=dtype)
+
+    def to(self, device):
+        """Copy of the model on another device."""
+        device = torch.device(device)
+        numbers = self.numbers.to(device) if isinstance(self.numbers, torch.Tensor) else self.numbers
+        return self._clone(numbers=numbers, device=device)
 
     def __repr__(self) -> str:  # pragma: no cover
         return f"{type(self).__name__}(ga={self.ga}, gc={self.gc}, wf={self.wf}, ref_charges={self.ref_charges})"
@@ -76,6 +104,8 @@ class _Model:
         """``zeta(q) * gw`` of shape ``(..., nat, 7)`` -- D4S: ``(..., nat, nat, 7)``, the weights of
         atom n as seen by partner m -- and optionally the derivatives w.r.t. cn and q, in the
         reference's order ``(gw[, dgwdcn][, dgwdq])`` (model/d4.py:103-228, model/d4s.py:109-266)."""
+        if self.ref_charges not in ("eeq", "gfn2"):
+            raise ValueError(f"Unknown reference charges: {self.ref_charges}")
         C, _lib, engine, par, num2, nat, stream = self._call_setup()
         if self.dtype not in (torch.float64, torch.float32):
             raise NotImplementedError(f"dtype {self.dtype} is not supported (float64/float32)")

@@ -256,3 +256,51 @@ def test_terms() -> None:
     assert len(disp.terms) == 1
     disp.deregister(TwoBodyTerm())
     assert len(disp.terms) == 0
+
+
+# ---- test/test_model/test_general.py:30-103 (model descriptors) ---------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_model_change_type(dtype: torch.dtype) -> None:
+    numbers = torch.tensor([14, 1, 1, 1, 1])
+    model = d4.D4Model(numbers).type(dtype)
+    assert model.dtype == dtype
+
+
+def test_model_change_type_fail() -> None:
+    model = d4.D4Model(torch.tensor([14, 1, 1, 1, 1]))
+    with pytest.raises(AttributeError):
+        model.dtype = torch.float64
+    with pytest.raises(ValueError):
+        model.type(torch.bool)
+
+
+def test_model_change_device() -> None:
+    device = torch.device("cpu")
+    model = d4.D4Model(torch.tensor([14, 1, 1, 1, 1])).to(device)
+    assert model.device == device
+    with pytest.raises(AttributeError):
+        model.device = torch.device("cpu")
+
+
+@pytest.mark.parametrize("model", ["d4", "d4s"])
+def test_ref_charges_fail(model: str) -> None:
+    numbers = torch.tensor([14, 1, 1, 1, 1])
+    cls = d4.D4Model if model == "d4" else d4.D4SModel
+    with pytest.raises(ValueError):
+        cls(numbers, ref_charges="wrong")
+
+
+@pytest.mark.parametrize("model", ["d4", "d4s"])
+def test_ref_charges_fail_2(model: str) -> None:
+    numbers = torch.tensor([14, 1, 1, 1, 1])
+    cls = d4.D4Model if model == "d4" else d4.D4SModel
+    m = cls(numbers, ref_charges="eeq")
+    m.ref_charges = "wrong"
+    with pytest.raises(ValueError):
+        m.weight_references()
+
+
+def test_model_args() -> None:
+    numbers = torch.tensor([14, 1, 1, 1, 1])
+    model = d4.D4Model(numbers, wf=6)
+    assert model.wf == 6
