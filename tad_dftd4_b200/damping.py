@@ -13,25 +13,55 @@ from functools import lru_cache
 from pathlib import Path
 from typing import Any, Dict
 
-__all__ = ["Param", "get_params", "RationalDamping"]
+__all__ = ["Param", "get_params", "Damping", "RationalDamping", "ZeroDamping", "MZeroDamping",
+           "OptimisedPowerDamping"]
 
 # ``Param`` is a plain dict with (all optional) keys
 #   a1, a2, s6, s8, s9, s10, rs6, rs8, rs9, alp, bet, doi
 Param = dict
 
 
-class RationalDamping:
-    """Marker for Becke-Johnson rational damping (the only accelerated scheme);
-    equal to every other instance, like the reference's ``Damping.__eq__``
-    (``damping/functions.py:233-253``)."""
+class Damping:
+    """Base of the damping-function markers.  Instances carry no state; two are equal iff they
+    are of the same class, like the reference's ``Damping.__eq__``
+    (``damping/functions.py:233-253``).  Only :class:`RationalDamping` (two-body) and
+    :class:`ZeroDamping` (ATM) are evaluated by the kernels; the others exist so that code
+    written against the reference imports and compares them, and raise
+    ``NotImplementedError`` when a calculation is asked to use them."""
 
     radius_type = "r4r2"
 
     def __eq__(self, other: Any) -> bool:
-        return type(other).__name__ == "RationalDamping"
+        if not isinstance(other, Damping) and not hasattr(other, "radius_type"):
+            return NotImplemented
+        return type(other).__name__ == type(self).__name__
+
+    def __ne__(self, other: Any) -> bool:
+        res = self.__eq__(other)
+        return True if res is NotImplemented else not res
 
     def __hash__(self) -> int:
-        return hash("RationalDamping")
+        return hash(type(self).__name__)
+
+
+class RationalDamping(Damping):
+    """Becke-Johnson rational damping (``damping/functions.py:262-305``): fused into the kernels."""
+
+
+class ZeroDamping(Damping):
+    """Zero damping of the ATM term (``damping/functions.py:308-378``): fused into the kernels."""
+
+    radius_type = "rvdw"
+
+
+class MZeroDamping(Damping):
+    """Modified zero damping (``damping/functions.py:381-431``): not accelerated."""
+
+    radius_type = "rvdw"
+
+
+class OptimisedPowerDamping(Damping):
+    """Optimised-power damping (``damping/functions.py:434-484``): not accelerated."""
 
 
 @lru_cache(maxsize=None)

@@ -18,22 +18,10 @@ from typing import Any
 
 import torch
 
-from .damping import RationalDamping
+from .damping import RationalDamping, ZeroDamping
 from .disp import dftd4
 
 __all__ = ["Disp", "DispD4", "DispTerm", "TwoBodyTerm", "D4ATMApprox", "FusedD4Term", "ZeroDamping"]
-
-
-class ZeroDamping:
-    """Marker for the zero damping used by the ATM term (``damping/functions.py:308-378``)."""
-
-    radius_type = "rvdw"
-
-    def __eq__(self, other: Any) -> bool:
-        return type(other).__name__ == "ZeroDamping"
-
-    def __hash__(self) -> int:
-        return hash("ZeroDamping")
 
 
 class DispTerm:

@@ -304,3 +304,44 @@ def test_model_args() -> None:
     numbers = torch.tensor([14, 1, 1, 1, 1])
     model = d4.D4Model(numbers, wf=6)
     assert model.wf == 6
+
+
+# ---- test/test_disp/test_damping.py:29-98 (damping-function markers) ----------------------------
+def test_damping_equality() -> None:
+    from tad_dftd4_b200.damping import MZeroDamping, OptimisedPowerDamping, RationalDamping, ZeroDamping
+
+    damp = RationalDamping()
+    assert damp == damp
+    assert RationalDamping() == RationalDamping()
+    assert not (RationalDamping() != RationalDamping())
+    assert RationalDamping() != ZeroDamping()
+    assert not (RationalDamping() == ZeroDamping())
+    instances = [cls() for cls in (RationalDamping, ZeroDamping, MZeroDamping, OptimisedPowerDamping)]
+    for i, a in enumerate(instances):
+        for j, b in enumerate(instances):
+            assert (a == b) is (i == j)
+            assert (a != b) is (i != j)
+    assert damp != "a string"
+    assert damp != 123
+    assert damp != None  # noqa: E711
+    assert damp != [RationalDamping()]
+
+    class Unrelated:
+        def __eq__(self, other):
+            return NotImplemented
+
+    assert (damp == Unrelated()) is False
+
+
+def test_fail_damping_param_other_schemes() -> None:
+    """test_disp/test_general.py:95-112: missing parameters raise TypeError for every damping
+    function of the reference; the schemes the kernels do not evaluate raise NotImplementedError
+    once the parameters are complete."""
+    from tad_dftd4_b200.damping import OptimisedPowerDamping
+    from tad_dftd4_b200.dispersion import Disp, TwoBodyTerm
+
+    numbers, positions, charge, param = _h2()
+    disp = Disp()
+    disp.register(TwoBodyTerm(damping_fn=OptimisedPowerDamping()))
+    with pytest.raises((TypeError, NotImplementedError)):
+        disp.calculate(numbers=numbers, positions=positions, charge=charge, param=param)
