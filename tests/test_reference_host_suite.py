@@ -345,3 +345,20 @@ def test_fail_damping_param_other_schemes() -> None:
     disp.register(TwoBodyTerm(damping_fn=OptimisedPowerDamping()))
     with pytest.raises((TypeError, NotImplementedError)):
         disp.calculate(numbers=numbers, positions=positions, charge=charge, param=param)
+
+
+# ---- test/test_disp/test_term.py:31-80 (DispTerm equality) --------------------------------------
+def test_dispterm_equality() -> None:
+    from tad_dftd4_b200.damping import OptimisedPowerDamping, RationalDamping
+    from tad_dftd4_b200.dispersion import DispTerm
+
+    class DummyDispTerm(DispTerm):
+        def calculate(self, numbers, positions, param, cn, model, q, r4r2, rvdw, cutoff):
+            return torch.tensor(0.0)
+
+    t1 = DummyDispTerm(damping_fn=RationalDamping(), charge_dependent=True)
+    t2 = DummyDispTerm(damping_fn=RationalDamping(), charge_dependent=True)
+    assert t1 == t2
+    assert t1 != DummyDispTerm(damping_fn=OptimisedPowerDamping(), charge_dependent=True)
+    assert t1 != DummyDispTerm(damping_fn=RationalDamping(), charge_dependent=False)
+    assert t1 != "not a disp term"
