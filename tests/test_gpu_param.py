@@ -163,3 +163,18 @@ def test_param_gradient_optimizer_step_changes_energy():
         opt.step()
         losses.append(loss.item())
     assert losses[2] < losses[1] < losses[0]
+
+
+from helpers import PARAM_GOLDEN_CASES, load_param_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("model", ["d4", "d4s"])
+@pytest.mark.parametrize("name", PARAM_GOLDEN_CASES)
+def test_param_gradient_reference_golden(name, model):
+    """CUDA path vs parameter gradients produced by the UNMODIFIED reference
+    (tests/golden/param, oracle/make_golden_param.py)."""
+    case = load_param_golden(name)
+    keys, got = _cuda(case, case["pvalues"], model, case["g"])
+    assert keys == list(KEYS)
+    for k, r, v in zip(keys, case[f"grad_param_{model}"], got):
+        assert abs(v - r) <= 1e-12 + 1e-9 * abs(r), (k, float(v), float(r))
