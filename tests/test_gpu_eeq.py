@@ -164,16 +164,14 @@ def test_get_properties_default_charges():
     assert (alpha.cpu() - alpha_ref).abs().max().item() / alpha_ref.abs().max().item() < 1e-10
 
 
-def test_charge_as_int():
-    """test/test_d4/test_general.py:32-52 of the reference: the total charge may be a Python int,
-    a Python float or a tensor."""
+def test_total_charge_argument_types():
+    """The total charge may be a Python int, a Python float or a tensor (what
+    test/test_d4/test_general.py:32-52 of the reference pins): same energies for all three."""
     d4 = _d4()
     numbers = torch.tensor([1, 1], device=DEV)
     positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.0]], dtype=F64, device=DEV)
     param = d4.Param(s6=torch.tensor(1.0), s8=torch.tensor(1.0), a1=torch.tensor(0.4), a2=torch.tensor(5.0))
-    energy_int = d4.dftd4(numbers, positions, 0, param)
-    energy_float = d4.dftd4(numbers, positions, 0.0, param)
-    energy_tensor = d4.dftd4(numbers, positions, torch.tensor(0.0), param)
-    assert torch.allclose(energy_int, energy_tensor)
-    assert torch.allclose(energy_float, energy_tensor)
-    assert energy_int.shape == numbers.shape and bool((energy_int < 0).all())
+    results = [d4.dftd4(numbers, positions, chrg, param) for chrg in (0, 0.0, torch.tensor(0.0))]
+    for e in results:
+        assert e.shape == numbers.shape and bool((e < 0).all())
+        assert torch.allclose(e, results[-1])
