@@ -255,6 +255,18 @@ def _param_vjp(engine: _Engine, par: _lib.Params, numbers: Tensor, positions: Te
     from .model import D4Model, D4SModel
 
     nbatch, nat = numbers.shape
+    # the dense (N, N) intermediates (pair planes, C6 matrices, D4S weights) are processed in
+    # slices of the batch: at most 32768 structures (grid limit of the kernels) and ~2 GB of planes
+    per_structure = 8 * nat * nat * (6 + 2 + (14 if par.model == 1 else 0))
+    chunk = max(1, min(32768, int(2e9 // max(per_structure, 1))))
+    if nbatch > chunk:
+        total = None
+        for b0 in range(0, nbatch, chunk):
+            sl = slice(b0, min(b0 + chunk, nbatch))
+            part = _param_vjp(engine, par, numbers[sl].contiguous(), positions[sl].contiguous(),
+                              q[sl].contiguous(), gout[sl].contiguous())  # fmt: skip
+            total = part if total is None else total + part
+        return total
     with torch.no_grad():
         pos = positions.detach()
         qd = q.detach()
