@@ -3,29 +3,39 @@
 bench.py -- headline measurement of the B200-native DFT-D4 hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload c2|c3] [--dtype f64|f32]
+                    [--workload c3|c2|c5|c1|c4|c4g] [--dtype f64|f32] [--no-subs]
 
-A *step* is one pass of the hot path over one batch of synthetic structures:
+A *step* is one pass of the hot path over one batch of synthetic structures.  The
+headline workload is BASELINE.json's metric, "D4 energy+forces":
 
-* ``c2`` (default, BASELINE.json configs[1]): 4096 synthetic 20-60 atom
-  organics, atom-resolved D4 energy (two-body + ATM), PBE0-D4 parameters, FP64;
-* ``c3`` (configs[2]): 1024 synthetic 100-atom molecules, energy + analytic
-  gradient (``autograd.grad(E.sum(), positions)``).
+* ``c3`` (default, configs[2]): 1024 synthetic 100-atom molecules, atom-resolved D4
+  energy + analytic gradient (``autograd.grad(E.sum(), positions)``), PBE0-D4, FP64;
+* ``c2`` (configs[1]): 4096 synthetic 20-60-atom organics, energy only;
+* ``c5`` (configs[4]): the C3 inputs with the D4S model (``--dtype f32|f64``);
+* ``c4`` / ``c4g`` (configs[3]): one 20 001-atom water cluster, energy / energy+gradient,
+  row-block split over the ranks + NCCL all-reduces;
+* ``c1`` (configs[0]): the 12-atom molecule of ``examples/single.py`` (latency).
 
-With ``--gpus N`` (launched under torchrun, one rank per GPU) every rank works
-on its own batch of the same shape (structures are independent: no data-path
-collective, weak scaling); the reported value is all structures of all ranks
-divided by the slowest rank's device time.
+With ``--gpus N`` (launched under torchrun, one rank per GPU) the headline ``value`` is
+WEAK scaling: every rank works on its own batch of the workload's shape (structures are
+independent, no data-path collective), value = all structures of all ranks / slowest
+rank's device time.  The same JSON line carries, unless ``--no-subs``:
 
-Output: ONE JSON line on rank 0 (see DESIGN.md "Measurement").  ``value`` is
-measured with inputs resident in HBM, ``e2e`` through the public API from
-pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+* ``strong``: the FIXED global batch of C3 and C2 sharded over the ranks through
+  ``tad_dftd4_b200.parallel.dftd4_sharded`` (north_star: "4096 ... sharded 1/2/4/8");
+* ``sub``: C2, C5-FP64, C5-FP32 measured the same way as the headline (fewer steps);
+* ``c4``: the single large system with forces, STRONG scaling over the ranks, with the
+  time of the all-reduces split out and the work counted in SURVEY 8(d)'s units.
 
-``--impl reference`` times the CPU implementation of the same path on the
-host cores: the reference itself cannot be installed here (its dependencies
-tad-mctc / tad-multicharge are not in the image), so this arm runs the oracle
-restatement (``oracle/d4_oracle.py``, the reference's dense torch formulation,
-bit-identical to the reference on every golden case) and says so.
+``value`` is measured with inputs resident in HBM, ``e2e`` through the public
+host-buffer API from pinned HOST tensors (H2D + kernels + D2H inside the timed region).
+
+``--impl reference`` times the CPU implementation of the same path on the host cores:
+the reference itself cannot be installed here (its dependencies tad-mctc /
+tad-multicharge are not in the image), so this arm runs the oracle restatement
+(``oracle/d4_oracle.py``: the reference's dense torch formulation, bit-identical to
+the unmodified reference on every golden case) and says so (``cpu_baseline.kind =
+"port"``); each of its steps is a bounded sample of the workload.
 """
 
 from __future__ import annotations
@@ -47,87 +57,71 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+import bench_inputs  # noqa: E402  (synthetic input generators; numpy only)
+
 PBE0 = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)  # d4.toml:269 of the reference
 
 # algorithmic flop per unit of work (contract figures)
 F_PCN, F_P2, F_T, F_W = 18, 248, 30, 120
 F_PCN_G, F_P2_G, F_T_G = 30, 320, 90
 NCLS = 5  # D4B200_NCLASS
+METRIC = "D4 energy+forces throughput (batched molecules/s)"
 
 WORKLOADS = {
     "c2": dict(nbatch=4096, lo=20, hi=60, seed=2, grad=False,
-               name="4096 synthetic 20-60-atom organics, D4 energy (two-body + ATM), padded to 60"),
+               name="C2: 4096 synthetic 20-60-atom organics, D4 energy (two-body + ATM), padded to 60"),
     "c3": dict(nbatch=1024, lo=100, hi=100, seed=3, grad=True,
-               name="1024 synthetic 100-atom molecules, D4 energy + analytic gradient incl. ATM"),
+               name="C3: 1024 synthetic 100-atom molecules, D4 energy + analytic gradient incl. ATM"),
     "c5": dict(nbatch=1024, lo=100, hi=100, seed=3, grad=True, model="d4s",
-               name="1024 synthetic 100-atom molecules (the C3 inputs), D4S model, energy + analytic gradient "
-                    "incl. ATM; --dtype f32|f64, error against the float64 oracle reported in cpu_baseline.parity"),
+               name="C5: 1024 synthetic 100-atom molecules (the C3 inputs), D4S model, energy + analytic "
+                    "gradient incl. ATM"),
     "c1": dict(single=True, nbatch=1, grad=False, seed=0,
-               name="examples/single.py 12-atom molecule, D4 energy, PBE0 parameters (one structure: latency)"),
+               name="C1: examples/single.py 12-atom molecule, D4 energy, PBE0 parameters (one structure: latency)"),
     "c4": dict(nmol=6667, seed=4, grad=False, large=True,
-               name="single 20001-atom water cluster (6667 H2O), D4 energy, default 60/40/30 Bohr cutoffs, "
+               name="C4: single 20001-atom water cluster (6667 H2O), D4 energy, default 60/40/30 Bohr cutoffs, "
                     "row-block split over the GPUs + all-reduce"),
     "c4g": dict(nmol=6667, seed=4, grad=True, large=True,
-                name="single 20001-atom water cluster (6667 H2O), D4 energy + analytic gradient, default "
+                name="C4: single 20001-atom water cluster (6667 H2O), D4 energy + analytic gradient, default "
                      "60/40/30 Bohr cutoffs, row-block split over the GPUs + all-reduces"),
 }  # fmt: skip
 
 
-def water_cluster(nmol: int, seed: int):
-    """O on a jittered simple-cubic lattice (5.86 Bohr) clipped to a
-    sphere, random orientation per molecule, r_OH = 1.81 Bohr, HOH = 104.5 deg."""
-    rng = np.random.default_rng(seed)
-    m = int(np.ceil((nmol * 6 / np.pi) ** (1 / 3))) + 2
-    grid = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) - (m - 1) / 2
-    grid = grid[np.argsort(np.linalg.norm(grid, axis=1), kind="stable")][:nmol]
-    o = grid * 5.86 + rng.normal(scale=0.3, size=(nmol, 3))
-    a = np.deg2rad(104.5) / 2
-    h1 = np.array([np.sin(a), np.cos(a), 0.0]) * 1.81
-    h2 = np.array([-np.sin(a), np.cos(a), 0.0]) * 1.81
-    # random rotations from normalised quaternions
-    qn = rng.normal(size=(nmol, 4))
-    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
-    w, x, y, z = qn.T
-    R = np.stack([
-        np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
-        np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
-        np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1),
-    ], 1)  # fmt: skip
-    pos = np.stack([o, o + R @ h1, o + R @ h2], 1).reshape(-1, 3)
-    numbers = np.tile(np.array([8, 1, 1]), nmol)
-    q = np.tile(np.array([-0.66, 0.33, 0.33]), nmol) + 0.02 * rng.normal(size=3 * nmol)
-    q -= q.mean()
-    return torch.from_numpy(numbers), torch.from_numpy(pos), torch.from_numpy(q)
-
-
 def oracle():
+    """The CPU oracle: ONLY the cpu_baseline leg and the reference arm call this."""
     sys.path.insert(0, str(ROOT / "oracle"))
-    import d4_oracle  # noqa: E402  (bench's cpu_baseline / reference arm only)
+    import d4_oracle  # noqa: E402
 
     return d4_oracle
 
 
-SINGLE_Z = [6, 6, 6, 6, 7, 6, 16, 1, 1, 1, 1, 1]  # examples/single.py:7-27 of the reference
-SINGLE_XYZ = [
-    [-2.56745685564671, -0.02509985979910, 0.0], [-1.39177582455797, +2.27696188880014, 0.0],
-    [+1.27784995624894, +2.45107479759386, 0.0], [+2.62801937615793, +0.25927727028120, 0.0],
-    [+1.41097033661123, -1.99890996077412, 0.0], [-1.17186102298849, -2.34220576284180, 0.0],
-    [-2.39505990368378, -5.22635838332362, 0.0], [+2.41961980455457, -3.62158019253045, 0.0],
-    [-2.51744374846065, +3.98181713686746, 0.0], [+2.24269048384775, +4.24389473203647, 0.0],
-    [+4.66488984573956, +0.17907568006409, 0.0], [-4.60044244782237, -0.17794734637413, 0.0],
-]  # fmt: skip
-
-
 def make_batch(wl: dict, rank: int):
-    orc = oracle()
     if wl.get("single"):
-        numbers = torch.tensor([SINGLE_Z])
-        positions = torch.tensor([SINGLE_XYZ], dtype=torch.float64)
-        q = 0.1 * torch.randn(numbers.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
-        return numbers, positions, q - q.mean()
+        return bench_inputs.single_molecule()
     rng = np.random.default_rng(wl["seed"] + 1000 * rank)
     sizes = rng.integers(wl["lo"], wl["hi"] + 1, size=wl["nbatch"])
-    return orc.organic_batch_parallel(sizes, seed=wl["seed"] + 1000 * rank)
+    numbers, positions, q = bench_inputs.organic_batch_parallel(sizes, seed=wl["seed"] + 1000 * rank)
+    pad = wl["hi"] - numbers.shape[1]  # every rank's batch has the workload's padded width
+    if pad > 0:
+        numbers = torch.nn.functional.pad(numbers, (0, pad))
+        positions = torch.nn.functional.pad(positions, (0, 0, 0, pad))
+        q = torch.nn.functional.pad(q, (0, pad))
+    return numbers, positions, q
+
+
+def config_dict(wl: dict, world: int, dtype: str, eeq: bool) -> dict:
+    """``config`` of the JSON line: identical for the B200 arm and the reference arm."""
+    nb = wl.get("nbatch", 1)
+    return {
+        "workload": wl["name"],
+        "structures_per_gpu": nb,
+        "global_batch": nb * world,
+        "parallelism": f"structure-sharded x{world}, no data-path collective",
+        "l2": "flushed (256 MB write) between timed iterations",
+        "param": "PBE0-D4 (s8 1.20065498, a1 0.40085597, a2 5.02928789), "
+                 + ("q=None: EEQ-2019 charges solved inside every step" if eeq else "explicit charges q"),
+        "dispersion_model": wl.get("model", "d4"),
+        "precision": dtype,
+    }  # fmt: skip
 
 
 def work_counts(numbers: torch.Tensor, grad: bool):
@@ -158,7 +152,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")  # fmt: skip
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
 
     def __enter__(self):
         try:
@@ -166,7 +160,7 @@ class ClockSampler:
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read)
             self.thread.start()
         except OSError:
             self.proc = None
@@ -183,6 +177,9 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+                self.proc.wait()
+            self.thread.join()  # the pipe is closed: the reader has seen EOF
+            self.proc.stdout.close()
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
@@ -204,6 +201,11 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------
+def cpu_sample_shape(wl: dict, nbatch: int):
+    chunk = 8 if wl["grad"] else 64
+    return min(chunk * 2, nbatch), chunk
+
+
 def cpu_time_sample(wl: dict, numbers, positions, q, nsample: int, chunk: int, eeq: bool = False, keep=None):
     """Seconds the dense CPU formulation needs for ``nsample`` structures of the
     workload (model rebuilt per call like the reference, dispersion/base.py:363).
@@ -230,12 +232,21 @@ def cpu_time_sample(wl: dict, numbers, positions, q, nsample: int, chunk: int, e
     return time.perf_counter() - t0
 
 
+def cpu_sample_text(nsample: int, chunk: int) -> str:
+    return (f"first {nsample} structures of the workload per step in chunks of {chunk} (dense N^3 temporaries), "
+            f"float64, torch threads = {torch.get_num_threads()}; oracle/d4_oracle.py = the reference's dense torch "
+            "formulation (the reference itself is not installable here: tad-mctc / tad-multicharge absent)")  # fmt: skip
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
+    if wl.get("large"):
+        print(json.dumps({"impl": "reference", "unavailable": "the dense reference formulation needs "
+                          "157 GB for rc6 and 6.4e13 B per N^3 temporary at 20k atoms (BASELINE.md)"}), flush=True)
+        return
     numbers, positions, q = make_batch(wl, 0)
-    chunk = 8 if wl["grad"] else 64
-    nsample = min(chunk * 2, numbers.shape[0])
+    nsample, chunk = cpu_sample_shape(wl, numbers.shape[0])
     times = []
     for it in range(args.warmup + args.steps):
         dt = cpu_time_sample(wl, numbers, positions, q, nsample, chunk, eeq=args.eeq)
@@ -243,22 +254,19 @@ def run_reference(args, wl, rank, world):
             times.append(dt)
     sec = sum(times) / len(times)
     value = nsample / sec
-    cores = os.cpu_count() or 1
-    sample = (f"{nsample} structures of the workload per step in chunks of {chunk} "
-              f"(dense N^3 temporaries), float64, torch threads = {torch.get_num_threads()}")  # fmt: skip
     line = {
         "impl": "reference",
-        "metric": "D4 dispersion throughput (batched molecules/s)",
+        "metric": METRIC,
         "value": value, "unit": "molecules/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "parallelism": "host cores"},
-        "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": config_dict(wl, world, "f64", args.eeq),
+        "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": cpu_sample_text(nsample, chunk)},
         "e2e": {"value": value, "unit": "molecules/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "note": "reference (tad-dftd4 0.8.0) is not installable here (tad-mctc / tad-multicharge "
-                "absent); timed: oracle/d4_oracle.py, the same dense torch formulation",
+        "note": "CPU arm: the host cores of this box run the oracle port of tad-dftd4 0.8.0 (kind = port); "
+                "it does not scale with --gpus",
     }  # fmt: skip
     print(json.dumps(line), flush=True)
 
@@ -266,305 +274,391 @@ def run_reference(args, wl, rank, world):
 # --------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------
-def run_b200(args, wl, rank, world, local_rank):
-    import tad_dftd4_b200 as d4
-    from tad_dftd4_b200 import _lib
-    from tad_dftd4_b200.disp import _Engine
+class Ctx:
+    """Process-wide state of the B200 arm."""
 
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+    def __init__(self, args, rank, world, local_rank):
+        import tad_dftd4_b200 as d4
+        from tad_dftd4_b200 import _lib
 
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        self.args, self.rank, self.world = args, rank, world
+        self.d4 = d4
+        self.dev = torch.device("cuda", local_rank)
+        self.local_rank = local_rank
+        torch.cuda.set_device(self.dev)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
 
-    dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    numbers_h, positions_h, q_h = make_batch(wl, rank)
-    positions_h, q_h = positions_h.to(dtype), q_h.to(dtype)
-    nat, pairs, triples, flop = work_counts(numbers_h, wl["grad"])
-    numbers_h, positions_h, q_h = numbers_h.pin_memory(), positions_h.pin_memory(), q_h.pin_memory()
-    numbers, positions, q = numbers_h.to(dev), positions_h.to(dev), q_h.to(dev)
-    d4.set_checks(False)  # fully asynchronous steps; parity is the tests' job
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        d4.set_checks(False)  # fully asynchronous steps; parity is the tests' job (and cpu_baseline.parity)
+        self.lib = _lib.load()
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)  # > 126 MB L2
 
-    model = wl.get("model", "d4")
-    use_eeq = bool(args.eeq)  # q=None: EEQ charges computed on device inside the step (and on the tape)
+    def launches(self) -> int:
+        return int(self.lib.d4b200_total_launch_count()) + int(self.lib.d4b200_eeq_launch_count())
 
-    def call(n, p, qq):
-        return d4.dftd4(n, p, 0.0, PBE0, q=None if use_eeq else qq, model=model)
+    def barrier(self):
+        torch.cuda.synchronize(self.dev)
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
 
-    def step_resident():
-        if wl["grad"]:
-            pos = positions.detach().requires_grad_(True)
-            e = call(numbers, pos, q)
-            (g,) = torch.autograd.grad(e.sum(), pos)
-            return e, g
-        return call(numbers, positions, q), None
-
-    out_e = torch.empty(numbers_h.shape, dtype=dtype).pin_memory()
-    out_g = torch.empty(positions_h.shape, dtype=dtype).pin_memory() if wl["grad"] else None
-
-    def step_e2e_host():
-        # public host-buffer API: pinned host tensors in, pinned host tensors out; the C ABI
-        # pipelines H2D copy / kernels / D2H copy in chunks (d4b200_energy_host_*,
-        # d4b200_energy_gradient_host_* for the workloads with forces)
-        d4.dftd4_host(numbers_h, positions_h, 0.0, PBE0, q=q_h, model=model, device=dev, out=out_e,
-                      with_gradient=wl["grad"], out_gradient=out_g)
-
-    host_api = not use_eeq
-
-    def step_e2e():
-        if host_api:
-            return step_e2e_host()
-        n = numbers_h.to(dev, non_blocking=True)
-        p = positions_h.to(dev, non_blocking=True)
-        qq = None if use_eeq else q_h.to(dev, non_blocking=True)
-        if wl["grad"]:
-            p.requires_grad_(True)
-            e = call(n, p, qq)
-            (g,) = torch.autograd.grad(e.sum(), p)
-            out_g.copy_(g, non_blocking=True)
-        else:
-            e = call(n, p, qq)
-        out_e.copy_(e.detach(), non_blocking=True)
-
-    h2d = numbers_h.numel() * 8 + (positions_h.numel() + (0 if use_eeq else q_h.numel())) * positions_h.element_size()
-    d2h = out_e.numel() * out_e.element_size() + (out_g.numel() * out_g.element_size() if wl["grad"] else 0)
-
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    def timed(fn, steps, warmup, host_call=False):
+    def timed(self, fn, steps, warmup, host_call=False):
+        """Sum of the per-step device times (ms) of ``steps`` calls, L2 flushed before each."""
         for _ in range(warmup):
             fn()
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        self.barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        launches = 0
+        n0 = self.launches()
         for s in range(steps):
-            flush.fill_(float(s))  # evict inputs/tables from L2 between timed iterations
+            self.flush.fill_(float(s))  # evict inputs/tables from L2 between timed iterations
             if host_call:  # the host-buffer API runs on its own streams: let the flush finish first
-                torch.cuda.current_stream(dev).synchronize()
+                torch.cuda.current_stream(self.dev).synchronize()
             ev[s][0].record()
             fn()
             ev[s][1].record()
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        ms = [a.elapsed_time(b) for a, b in ev]
-        return sum(ms), launches
+        self.barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), self.launches() - n0
 
-    engine = _Engine.get(dev, 3.0, 2.0)
-    lib = _lib.load()
-    step_resident()  # builds tables / workspace
-    n0 = int(lib.d4b200_total_launch_count()) + int(lib.d4b200_eeq_launch_count())
-    step_resident()
-    launches_per_step = int(lib.d4b200_total_launch_count()) + int(lib.d4b200_eeq_launch_count()) - n0
+    def reduce(self, values, op="max"):
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
 
-    with ClockSampler(local_rank) as clocks:
-        total_ms, _ = timed(step_resident, args.steps, args.warmup)
-        e2e_ms, _ = timed(step_e2e, args.steps, max(args.warmup, 3), host_call=host_api)
-        # keep the same load running (untimed) until nvidia-smi has had time to sample it
-        t_end = time.perf_counter() + 1.5
-        while time.perf_counter() < t_end:
-            for _ in range(20):
-                step_resident()
-            torch.cuda.synchronize(dev)
-    clk = clocks.summary()
 
-    # ---- dominant kernel: per-launch duration measured live with CUDA events
-    lib.d4b200_profile_enable(engine.handle, 1)
-    caps = (C.c_int * NCLS)()
-    lib.d4b200_class_caps_model(engine.handle, int(dtype == torch.float32), int(wl["grad"]),
-                                int(model == "d4s"), caps)
-    per_class = [[] for _ in range(NCLS)]
-    prep_ms, call_ms = [], []
-    for s in range(max(3, min(args.steps, 10))):
-        flush.fill_(1.0)
-        step_resident()
-        ms = (C.c_float * (NCLS + 2))()
-        lib.d4b200_profile_read(engine.handle, ms)
+class BatchBench:
+    """One padded-batch workload on this rank: resident step, host-buffer step, work counts."""
+
+    def __init__(self, ctx: Ctx, key: str, dtype: str, batch, eeq: bool = False):
+        self.ctx, self.key, self.wl, self.dtype_name = ctx, key, WORKLOADS[key], dtype
+        wl, dev = self.wl, ctx.dev
+        self.dtype = torch.float64 if dtype == "f64" else torch.float32
+        numbers_h, positions_h, q_h = batch
+        positions_h, q_h = positions_h.to(self.dtype), q_h.to(self.dtype)
+        self.nat, self.pairs, self.triples, self.flop = work_counts(numbers_h, wl["grad"])
+        self.numbers_h, self.positions_h, self.q_h = numbers_h.pin_memory(), positions_h.pin_memory(), q_h.pin_memory()
+        self.numbers, self.positions, self.q = self.numbers_h.to(dev), self.positions_h.to(dev), self.q_h.to(dev)
+        self.model = wl.get("model", "d4")
+        self.eeq = eeq
+        self.out_e = torch.empty(numbers_h.shape, dtype=self.dtype).pin_memory()
+        self.out_g = torch.empty(positions_h.shape, dtype=self.dtype).pin_memory() if wl["grad"] else None
+        es = positions_h.element_size()
+        self.h2d = numbers_h.numel() * 8 + (positions_h.numel() + (0 if eeq else q_h.numel())) * es
+        self.d2h = self.out_e.numel() * es + (self.out_g.numel() * es if wl["grad"] else 0)
+
+    def call(self, n, p, qq):
+        return self.ctx.d4.dftd4(n, p, 0.0, PBE0, q=None if self.eeq else qq, model=self.model)
+
+    def step_resident(self):
+        if self.wl["grad"]:
+            pos = self.positions.detach().requires_grad_(True)
+            e = self.call(self.numbers, pos, self.q)
+            (g,) = torch.autograd.grad(e.sum(), pos)
+            return e, g
+        return self.call(self.numbers, self.positions, self.q), None
+
+    def step_e2e(self):
+        dev, wl = self.ctx.dev, self.wl
+        if not self.eeq:
+            # public host-buffer API: pinned host tensors in, pinned host tensors out; the C ABI pipelines
+            # H2D copy / kernels / D2H copy in chunks (d4b200_energy_host_*, d4b200_energy_gradient_host_*)
+            self.ctx.d4.dftd4_host(self.numbers_h, self.positions_h, 0.0, PBE0, q=self.q_h, model=self.model,
+                                   device=dev, out=self.out_e, with_gradient=wl["grad"], out_gradient=self.out_g)
+            return
+        n = self.numbers_h.to(dev, non_blocking=True)
+        p = self.positions_h.to(dev, non_blocking=True)
+        if wl["grad"]:
+            p.requires_grad_(True)
+            e = self.call(n, p, None)
+            (g,) = torch.autograd.grad(e.sum(), p)
+            self.out_g.copy_(g, non_blocking=True)
+        else:
+            e = self.call(n, p, None)
+        self.out_e.copy_(e.detach(), non_blocking=True)
+
+    # ---- measurements ---------------------------------------------------
+    def measure(self, steps, warmup):
+        """value / e2e of this workload, aggregated over the ranks (weak scaling)."""
+        ctx = self.ctx
+        total_ms, launches = ctx.timed(self.step_resident, steps, warmup)
+        e2e_ms, _ = ctx.timed(self.step_e2e, steps, max(warmup, 3), host_call=not self.eeq)
+        total_ms, e2e_ms = ctx.reduce([total_ms, e2e_ms], "max")
+        nmol, npair, ntrip, nflop = ctx.reduce([float(self.numbers.shape[0]), float(self.pairs.sum()),
+                                                float(self.triples.sum()), float(self.flop.sum())], "sum")  # fmt: skip
+        sec, e2e_sec = total_ms / steps * 1e-3, e2e_ms / steps * 1e-3
+        return {
+            "value": nmol / sec, "unit": "molecules/s", "ms_per_step": sec * 1e3, "steps": steps,
+            "pair_terms_per_s": npair / sec, "triple_terms_per_s": ntrip / sec,
+            "algorithmic_tflops": nflop / sec / 1e12,
+            "e2e": {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(self.h2d),
+                    "d2h_bytes_per_step": int(self.d2h), "ms_per_step": e2e_sec * 1e3},
+            "gpu_launches": int(launches),
+        }  # fmt: skip
+
+    def roofline(self, step_ms, nsteps=6):
+        """Dominant kernel of this workload: per-launch duration measured live with CUDA events
+        (on the streams the class kernels are launched on, inside the C library)."""
+        from tad_dftd4_b200.disp import _Engine
+
+        ctx, lib, wl = self.ctx, self.ctx.lib, self.wl
+        engine = _Engine.get(ctx.dev, 3.0, 2.0)
+        f32, d4s = int(self.dtype == torch.float32), int(self.model == "d4s")
+        lib.d4b200_profile_enable(engine.handle, 1)
+        caps = (C.c_int * NCLS)()
+        lib.d4b200_class_caps_model(engine.handle, f32, int(wl["grad"]), d4s, caps)
+        per_class = [[] for _ in range(NCLS)]
+        prep_ms, call_ms = [], []
+        for _ in range(nsteps):
+            ctx.flush.fill_(1.0)
+            self.step_resident()
+            ms = (C.c_float * (NCLS + 2))()
+            lib.d4b200_profile_read(engine.handle, ms)
+            for c in range(NCLS):
+                if ms[c] >= 0:
+                    per_class[c].append(ms[c])
+            prep_ms.append(ms[NCLS])
+            call_ms.append(ms[NCLS + 1])
+        lib.d4b200_profile_enable(engine.handle, 0)
+        class_ms = [statistics.mean(v[1:] if len(v) > 1 else v) if v else 0.0 for v in per_class]
+        lo, class_flop = 0, []
         for c in range(NCLS):
-            if ms[c] >= 0:
-                per_class[c].append(ms[c])
-        prep_ms.append(ms[NCLS])
-        call_ms.append(ms[NCLS + 1])
-    lib.d4b200_profile_enable(engine.handle, 0)
-    class_ms = [statistics.mean(v[1:] if len(v) > 1 else v) if v else 0.0 for v in per_class]
-    lo = 0
-    class_flop = []
-    for c in range(NCLS):
-        sel = (nat >= lo) & (nat <= caps[c]) if caps[c] >= lo else torch.zeros_like(nat, dtype=torch.bool)
-        class_flop.append(float(flop[sel].sum()))
-        lo = caps[c] + 1
-    dom = max(range(NCLS), key=lambda c: class_ms[c])
+            sel = (self.nat >= lo) & (self.nat <= caps[c]) if caps[c] >= lo else torch.zeros_like(self.nat, dtype=torch.bool)
+            class_flop.append(float(self.flop[sel].sum()))
+            lo = caps[c] + 1
+        dom = max(range(NCLS), key=lambda c: class_ms[c])
+        peak_tf = C.c_double(0.0)
+        scratch = torch.empty(64 * 1024 * 1024, dtype=torch.uint8, device=ctx.dev)
+        lib.d4b200_measure_fp64_peak(engine.handle, scratch.data_ptr(), scratch.numel(),
+                                     torch.cuda.current_stream(ctx.dev).cuda_stream, C.byref(peak_tf))  # fmt: skip
+        fp64 = self.dtype == torch.float64
+        nominal_tf = 37.2 if fp64 else 74.4
+        peak = peak_tf.value if fp64 else 2 * peak_tf.value
+        achieved = class_flop[dom] / (class_ms[dom] * 1e-3) / 1e12 if class_ms[dom] > 0 else 0.0
+        whole = float(self.flop.sum()) / (step_ms * 1e-3) / 1e12 if step_ms > 0 else 0.0
+        return {
+            "bound": "fp64" if fp64 else "fp32",
+            "kernel": f"small_kernel<{'double' if fp64 else 'float'},{'grad' if wl['grad'] else 'energy'},"
+                      f"{self.model}> size class <= {caps[dom]} atoms",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak else None,
+            "traffic": measured_traffic(self.key, self.dtype_name),
+            "peak_source": "measured in this run: DFMA chain microbenchmark (d4b200_measure_fp64_peak"
+                           + ("" if fp64 else ", x2 for FP32") + f"); nominal 148 SM x 64 lanes x 2 x 1.965 GHz = "
+                           f"{nominal_tf} TFLOP/s; MEASURED_PEAKS.json has no FP64 entry",
+            "nominal_peak": nominal_tf, "frac_of_nominal": achieved / nominal_tf,
+            "kernel_ms": class_ms[dom], "kernel_algorithmic_flop": class_flop[dom],
+            "all_class_ms": class_ms, "prep_ms": statistics.mean(prep_ms[1:]),
+            "serialised_call_ms": statistics.mean(call_ms[1:]),
+            "step_share": class_ms[dom] / step_ms if step_ms else None,
+            "whole_step_frac": whole / peak if peak else None,
+            "hbm_gbs_algorithmic": (self.h2d + self.d2h) / (step_ms * 1e-3) / 1e9 if step_ms else None,
+        }  # fmt: skip
 
-    peak_tf = C.c_double(0.0)
-    scratch = torch.empty(64 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    lib.d4b200_measure_fp64_peak(engine.handle, scratch.data_ptr(), scratch.numel(),
-                                 torch.cuda.current_stream(dev).cuda_stream, C.byref(peak_tf))  # fmt: skip
-    nominal_tf = 37.2 if dtype == torch.float64 else 74.4
-    peak = peak_tf.value if dtype == torch.float64 else 2 * peak_tf.value
-
-    # ---- reduce over ranks (max time, summed work)
-    stats = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
-    work = torch.tensor([float(numbers.shape[0]), float(pairs.sum()), float(triples.sum()),
-                         float(flop.sum())], dtype=torch.float64, device=dev)  # fmt: skip
-    if dist is not None:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms = stats.tolist()
-    nmol, npair, ntrip, nflop = work.tolist()
-    sec_per_step = total_ms / args.steps * 1e-3
-    e2e_sec = e2e_ms / args.steps * 1e-3
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        chunk = 8 if wl["grad"] else 64
-        nsample = min(chunk * 2, numbers_h.shape[0])
+    def cpu_baseline(self):
+        """Oracle port on the host cores (bounded sample) + parity of this run's GPU results against it."""
+        wl = self.wl
+        nsample, chunk = cpu_sample_shape(wl, self.numbers_h.shape[0])
         keep: list = []
-        sec = cpu_time_sample(wl, numbers_h, positions_h.double(), q_h.double(), nsample, chunk, eeq=use_eeq, keep=keep)
-        # the float64 oracle results of the sample double as the checker of this run's GPU results
-        e_gpu, g_gpu = step_resident()
+        sec = cpu_time_sample(wl, self.numbers_h, self.positions_h.double(), self.q_h.double(), nsample, chunk,
+                              eeq=self.eeq, keep=keep)  # fmt: skip
+        e_gpu, g_gpu = self.step_resident()
         e_ref = torch.cat([k[0] for k in keep])
         scale = e_ref.abs().amax(-1, keepdim=True)
         parity = {"against": "float64 oracle, same sample", "structures": nsample,
-                  "max_rel_energy": float(((e_gpu[:nsample].detach().double().cpu() - e_ref).abs() / scale).max())}
+                  "max_rel_energy": float(((e_gpu[:nsample].detach().double().cpu() - e_ref).abs() / scale).max())}  # fmt: skip
         if wl["grad"]:
             g_ref = torch.cat([k[1] for k in keep])
             parity["max_abs_gradient"] = float((g_gpu[:nsample].double().cpu() - g_ref).abs().max())
-        cpu = {"value": nsample / sec, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"first {nsample} structures of the workload, chunks of {chunk}, float64, "
-                         f"torch threads = {torch.get_num_threads()} (oracle/d4_oracle.py: the reference's "
-                         "dense torch formulation; the reference itself is not installable here)",
-               "parity": parity}  # fmt: skip
-
-    if rank == 0:
-        achieved = class_flop[dom] / (class_ms[dom] * 1e-3) / 1e12 if class_ms[dom] > 0 else 0.0
-        line = {
-            "metric": "D4 dispersion throughput (batched molecules/s)",
-            "value": nmol / sec_per_step, "unit": "molecules/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": wl["name"], "structures_per_gpu": int(numbers.shape[0]),
-                       "global_batch": int(nmol), "parallelism": f"structure-sharded x{world}, no collective",
-                       "l2": "flushed (256 MB write) between timed iterations",
-                       "param": "PBE0-D4 (s8 1.20065498, a1 0.40085597, a2 5.02928789), "
-                                + ("q=None: EEQ-2019 charges solved on device inside every step" if use_eeq
-                                   else "explicit charges q"),
-                       "model": model},
-            "pair_terms_per_s": npair / sec_per_step, "triple_terms_per_s": ntrip / sec_per_step,
-            "algorithmic_tflops": nflop / sec_per_step / 1e12,
-            "e2e": {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_sec * 1e3},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": {
-                "bound": "fp64" if dtype == torch.float64 else "fp32",
-                "kernel": f"small_kernel<{'double' if dtype == torch.float64 else 'float'},"
-                          f"{'grad' if wl['grad'] else 'energy'},{model}> size class <= {caps[dom]} atoms",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.workload, args.dtype),
-                "peak_source": "measured in this run: DFMA chain microbenchmark (d4b200_measure_fp64_peak); "
-                               f"nominal {nominal_tf} TFLOP/s; MEASURED_PEAKS.json has no FP64 entry",
-                "kernel_ms": class_ms[dom], "kernel_algorithmic_flop": class_flop[dom],
-                "all_class_ms": class_ms, "prep_ms": statistics.mean(prep_ms[1:]),
-                "serialised_call_ms": statistics.mean(call_ms[1:]), "step_share": class_ms[dom] / (sec_per_step * 1e3),
-                "hbm_gbs_algorithmic": (h2d + d2h) / sec_per_step / 1e9,
-            },
-            "cpu_baseline": cpu,
-            "clocks": clk,
-        }  # fmt: skip
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+        return {"value": nsample / sec, "unit": "molecules/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": cpu_sample_text(nsample, chunk), "parity": parity}  # fmt: skip
 
 
-def run_large(args, wl, rank, world, local_rank):
-    """C4: one large structure, strong scaling over the ranks (row-block + all-reduce)."""
-    if args.impl == "reference":
-        if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the dense reference formulation needs "
-                              "157 GB for rc6 and 6.4e13 B per N^3 temporary at 20k atoms (BASELINE.md); "
-                              "see cpu_baseline of the b200 arm for sub-cluster timings"}), flush=True)
-        return
-    import tad_dftd4_b200 as d4
-    from tad_dftd4_b200.large import dftd4_large
+def strong_record(ctx: Ctx, key: str, batch, steps, warmup):
+    """The FIXED global batch of the workload, sharded over the ranks through the public
+    ``parallel.dftd4_sharded`` (contiguous shards, no data-path collective)."""
+    from tad_dftd4_b200.parallel import dftd4_sharded
 
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
-    dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    numbers_h, positions_h, q_h = water_cluster(args.nmol or wl["nmol"], wl["seed"])
-    nat = numbers_h.shape[0]
-    numbers, positions, q = numbers_h.to(dev), positions_h.to(dev, dtype), q_h.to(dev, dtype)
-    d4.set_checks(False)
+    wl, dev = WORKLOADS[key], ctx.dev
+    numbers, positions, q = (t.to(dev) for t in batch)
+    if ctx.dist is not None:  # every rank evaluates shards of rank 0's batch
+        for t in (numbers, positions, q):
+            ctx.dist.broadcast(t, src=0)
 
     def step():
         if wl["grad"]:
             pos = positions.detach().requires_grad_(True)
-            e = dftd4_large(numbers, pos, PBE0, q)
+            e = dftd4_sharded(numbers, pos, 0.0, PBE0, q=q, gather=False)
+            (g,) = torch.autograd.grad(e.sum(), pos)
+            return e, g
+        return dftd4_sharded(numbers, positions, 0.0, PBE0, q=q, gather=False), None
+
+    ms, _ = ctx.timed(step, steps, warmup)
+    (ms,) = ctx.reduce([ms], "max")
+    sec = ms / steps * 1e-3
+    _, pairs, triples, flop = work_counts(batch[0], wl["grad"])
+    return {"workload": wl["name"], "global_batch": int(numbers.shape[0]), "scaling": "strong",
+            "api": "tad_dftd4_b200.parallel.dftd4_sharded(gather=False)",
+            "value": numbers.shape[0] / sec, "unit": "molecules/s", "ms_per_step": sec * 1e3, "steps": steps,
+            "pair_terms_per_s": float(pairs.sum()) / sec, "triple_terms_per_s": float(triples.sum()) / sec,
+            "algorithmic_tflops": float(flop.sum()) / sec / 1e12}  # fmt: skip
+
+
+def large_record(ctx: Ctx, key: str, cluster, steps, warmup, dtype_name="f64"):
+    """C4: one large structure, STRONG scaling over the ranks (row-block + all-reduces)."""
+    from tad_dftd4_b200 import large
+
+    wl, dev = WORKLOADS[key], ctx.dev
+    dtype = torch.float64 if dtype_name == "f64" else torch.float32
+    numbers_h, positions_h, q_h = cluster
+    nat = numbers_h.shape[0]
+    numbers, positions, q = numbers_h.to(dev), positions_h.to(dev, dtype), q_h.to(dev, dtype)
+
+    def step():
+        if wl["grad"]:
+            pos = positions.detach().requires_grad_(True)
+            e = large.dftd4_large(numbers, pos, PBE0, q)
             (g,) = torch.autograd.grad(e.sum(), pos)
             return e.detach()
-        return dftd4_large(numbers, positions, PBE0, q)
+        return large.dftd4_large(numbers, positions, PBE0, q)
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, warmup)):
         e = step()
-    torch.cuda.synchronize(dev)
-    with ClockSampler(local_rank) as clocks:
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for s in range(args.steps):
-            ev[s][0].record()
-            e = step()
-            ev[s][1].record()
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
+    ctx.barrier()
+    prof = large.profile_begin()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        ev[s][0].record()
+        e = step()
+        ev[s][1].record()
+    ctx.barrier()
+    large.profile_end()
     ms = sum(a.elapsed_time(b) for a, b in ev)
-    stat = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(stat, op=dist.ReduceOp.MAX)
-    sec = stat.item() / args.steps * 1e-3
-    # exact work counts (centre-triples: sum_j C(n_j, 2); pairs within the cutoffs)
-    nb40 = torch.zeros(nat, dtype=torch.int64, device=dev)
-    p60 = 0
-    p32 = positions.to(torch.float32)
-    for b0 in range(0, nat, 2048):
-        d = torch.cdist(p32[b0 : b0 + 2048], p32)
-        nb40[b0 : b0 + 2048] = (d <= 40.0).sum(-1) - 1
-        p60 += int((d <= 60.0).sum().item()) - d.shape[0]
-    ctrip = float((nb40 * (nb40 - 1) // 2).sum().item())
-    pairs = p60 / 2
+    parts = prof.totals_ms()  # per-section device time on this rank, summed over the steps
+    ms, ar_ms, plan_ms = ctx.reduce([ms, parts.get("all_reduce", 0.0), parts.get("plan", 0.0)], "max")
+    sec = ms / steps * 1e-3
+    # exact work counts in SURVEY 8(d)'s units: P_2 (r <= 60), T = sum_j C(n_j, 2) - 2 #closed
+    counts = large.work_counts(numbers, positions.double())
+    p2, trip, ctrip = counts["pairs_disp2"], counts["triples"], counts["centre_triples"]
+    flop = (F_PCN * counts["pairs_cn"] + (F_P2 + (F_P2_G if wl["grad"] else 0)) * p2
+            + (F_PCN_G * counts["pairs_cn"] if wl["grad"] else 0)
+            + (F_T + (F_T_G if wl["grad"] else 0)) * trip + F_W * nat)  # fmt: skip
+    peak_tf = C.c_double(0.0)
+    from tad_dftd4_b200.disp import _Engine
+
+    engine = _Engine.get(dev, 3.0, 2.0)
+    scratch = torch.empty(64 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ctx.lib.d4b200_measure_fp64_peak(engine.handle, scratch.data_ptr(), scratch.numel(),
+                                     torch.cuda.current_stream(dev).cuda_stream, C.byref(peak_tf))  # fmt: skip
+    peak = peak_tf.value * (1 if dtype == torch.float64 else 2)
+    tf = flop / sec / 1e12
+    return {
+        "workload": wl["name"], "atoms": nat, "scaling": "strong", "n_gpus": ctx.world,
+        "value": nat / sec, "unit": "atoms/s", "ms_per_step": sec * 1e3, "steps": steps,
+        "all_reduce_ms_per_step": ar_ms / steps, "plan_ms_per_step": plan_ms / steps,
+        "collectives_per_step": 3 if wl["grad"] else 1,
+        "pair_terms": p2, "triple_terms": trip, "centre_triple_terms": ctrip,
+        "pair_terms_per_s": p2 / sec, "triple_terms_per_s": trip / sec,
+        "algorithmic_tflops": tf, "per_gpu_frac_of_fp64_peak": tf / ctx.world / peak if peak else None,
+        "peak_tflops": peak, "energy_sum": float(e.sum().item()),
+        "reference": "N/A: the dense reference formulation cannot hold a 20k-atom system (BASELINE.md)",
+    }  # fmt: skip
+
+
+def run_b200(args, rank, world, local_rank):
+    key = args.workload
+    wl = WORKLOADS[key]
+    subs = not args.no_subs and not wl.get("large") and not wl.get("single")
+    # ---- all synthetic inputs first: the generator's worker pool runs before CUDA / NCCL exist
+    batches = {}
+    need = {key} | ({"c2", "c3"} if subs else set())
+    for k in sorted(need - {"c4", "c4g"}):
+        batches[k] = make_batch(WORKLOADS[k], rank)
+    strong_batches = {}
+    if subs:
+        for k in ("c3", "c2"):
+            strong_batches[k] = batches[k] if rank == 0 else tuple(torch.empty_like(t) for t in batches[k])
+    if "c5" in need:
+        batches["c5"] = batches.get("c3") or make_batch(WORKLOADS["c5"], rank)
+    cluster = None
+    if subs or wl.get("large"):
+        cluster = bench_inputs.water_cluster(args.nmol or WORKLOADS["c4g"]["nmol"], WORKLOADS["c4g"]["seed"])
+
+    ctx = Ctx(args, rank, world, local_rank)
+    if wl.get("large"):
+        rec = large_record(ctx, key, cluster, args.steps, min(args.warmup, 2), args.dtype)
+        if rank == 0:
+            line = {"metric": "D4 dispersion throughput, single large system (atoms/s)", "n_gpus": world,
+                    "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": args.dtype,
+                    "data": "synthetic", "config": {"workload": wl["name"], "atoms": rec["atoms"],
+                                                     "parallelism": f"row-block x{world}, NCCL all-reduces"},
+                    "e2e": None, "gpu_launches": None, "cpu_baseline": None, **rec}  # fmt: skip
+            print(json.dumps(line), flush=True)
+        return ctx
+
+    head = BatchBench(ctx, key, args.dtype, batches[key], eeq=args.eeq)
+    head.step_resident()  # builds tables / workspace
+    with ClockSampler(local_rank) as clocks:
+        res = head.measure(args.steps, args.warmup)
+        # keep the same load running (untimed) until nvidia-smi has had time to sample it
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                head.step_resident()
+            torch.cuda.synchronize(ctx.dev)
+    clk = clocks.summary()
+    roof = head.roofline(res["ms_per_step"] / 1.0)
+
+    sub, strong, c4 = {}, {}, None
+    if subs:
+        ksteps = max(3, min(args.steps, 10))
+        for name, k, dt in (("c2_f64", "c2", "f64"), ("c3_f64", "c3", "f64"), ("c5_f64", "c5", "f64"), ("c5_f32", "c5", "f32")):
+            if k == key and dt == args.dtype and not args.eeq:
+                continue  # that is the headline
+            bb = BatchBench(ctx, k, dt, batches.get(k) or batches["c3"])
+            bb.step_resident()
+            r = bb.measure(ksteps, 3)
+            rf = bb.roofline(r["ms_per_step"], nsteps=4)
+            r["workload"] = WORKLOADS[k]["name"]
+            r["dtype"] = dt
+            r["roofline"] = {kk: rf[kk] for kk in ("bound", "kernel", "achieved", "peak", "unit", "frac", "kernel_ms",
+                                                   "all_class_ms", "whole_step_frac")}  # fmt: skip
+            sub[name] = r
+            del bb
+        for k in ("c3", "c2"):
+            strong[k] = strong_record(ctx, k, strong_batches[k], ksteps, 3)
+        c4 = large_record(ctx, "c4g", cluster, 2, 1)
+
+    cpu = None
+    if not args.no_cpu:
+        if rank == 0:  # rank 0's host cores; the other ranks wait at the barrier below
+            cpu = head.cpu_baseline()
+        ctx.barrier()
+
     if rank == 0:
         line = {
-            "metric": "D4 dispersion throughput, single large system (atoms/s)",
-            "value": nat / sec, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": wl["name"], "atoms": nat, "parallelism": f"row-block x{world}, NCCL all-reduce of E",
-                       "l2": "working set (neighbour lists, stash) exceeds L2"},
-            "pair_terms_per_s": pairs / sec, "centre_triple_terms_per_s": ctrip / sec,
-            "pair_terms": pairs, "centre_triple_terms": ctrip,
-            "energy_sum": float(e.sum().item()),
-            "algorithmic_tflops": ((F_P2 + (F_P2_G if wl["grad"] else 0)) * pairs
-                                   + (F_T + (F_T_G if wl["grad"] else 0)) * ctrip) / sec / 1e12,
-            "e2e": None, "gpu_launches": None, "cpu_baseline": None,
-            "clocks": clocks.summary(),
+            "metric": METRIC,
+            "value": res["value"], "unit": "molecules/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": config_dict(wl, world, args.dtype, args.eeq),
+            "pair_terms_per_s": res["pair_terms_per_s"], "triple_terms_per_s": res["triple_terms_per_s"],
+            "algorithmic_tflops": res["algorithmic_tflops"],
+            "e2e": res["e2e"],
+            "gpu_launches": res["gpu_launches"],
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "clocks": clk,
+            "strong": strong or None,
+            "sub": sub or None,
+            "c4": c4,
+            "native_library": str(Path(ctx.lib._name).resolve().relative_to(ROOT)) if hasattr(ctx.lib, "_name") else None,
         }  # fmt: skip
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    return ctx
 
 
 def main():
@@ -573,9 +667,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-subs", action="store_true",
+                    help="headline workload only (no strong-scaling / C2 / C5 / C4 sub-records)")
     ap.add_argument("--eeq", action="store_true",
                     help="default q=None path: EEQ charges on device inside the step (and on the autograd tape)")
     ap.add_argument("--nmol", type=int, default=0, help="c4: number of water molecules (default 6667)")
@@ -587,20 +683,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload]
-    if wl.get("large"):
-        run_large(args, wl, rank, world, local_rank)
-    elif args.impl == "reference":
-        run_reference(args, wl, rank, world)
-    else:
-        run_b200(args, wl, rank, world, local_rank)
+    if args.impl == "reference":
+        run_reference(args, WORKLOADS[args.workload], rank, world)
+        return
+    ctx = run_b200(args, rank, world, local_rank)
+    # orderly teardown: device idle, process group destroyed, then normal interpreter exit (the
+    # driver's exit-time hook records which shared libraries this process mapped)
+    torch.cuda.synchronize(ctx.dev)
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     main()
-    # The JSON line is out: leave without interpreter / library teardown.  One run in a few dozen
-    # aborted AFTER printing its result (daemon sampler thread, fork-based generator pool, OpenMP and
-    # CUDA runtimes all unwinding at once); a benchmark has nothing to save at that point.
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)

@@ -437,94 +437,10 @@ def energy_and_gradient(numbers, positions, param, q, **kw):
 
 
 # --------------------------------------------------------------------------
-# synthetic inputs shared by tests and bench
+# synthetic inputs live in bench_inputs.py at the repo root; the
+# historical names stay importable from here for the tests and golden-vector scripts
 # --------------------------------------------------------------------------
-_ORGANIC_Z = np.array([1, 6, 7, 8, 16, 9])
-_ORGANIC_P = np.array([0.48, 0.32, 0.07, 0.10, 0.02, 0.01])
-_VALENCE = {1: 1, 6: 4, 7: 3, 8: 2, 16: 2, 9: 1}
+import sys as _sys
 
-
-def organic_blob(nat: int, rng: np.random.Generator):
-    """Generator G(N, seed) of SURVEY.md 8(d), made chemically sane: a bonded
-    tree of H/C/N/O/S/F atoms grown with valence caps (so coordination numbers
-    stay physical; unphysical CN > ~12 makes the *reference's* autograd return
-    NaN through the underflowing Gaussian weights) and a 2.8 Bohr exclusion
-    radius towards non-bonded atoms.  Bond lengths U[1.85,2.15] (with H) or
-    U[2.45,2.95] Bohr.  Charges: 0.1*N(0,1), shifted to zero sum."""
-    z = rng.choice(_ORGANIC_Z, size=nat, p=_ORGANIC_P)
-    z[0] = 6
-    free = np.array([_VALENCE[int(v)] for v in z])
-    xyz = np.zeros((nat, 3))
-    for i in range(1, nat):
-        cand_parents = np.nonzero(free[:i] > 0)[0]
-        if len(cand_parents) == 0:  # saturated: start a new fragment on a carbon
-            z[i] = 6
-            free[i] = 4
-        heavy = cand_parents[z[cand_parents] > 1]
-        best, best_d = None, -1.0
-        for _ in range(200):
-            if len(cand_parents) == 0:
-                j, r = int(rng.integers(i)), rng.uniform(3.4, 4.0)
-            else:
-                j = int(rng.choice(heavy)) if len(heavy) else int(rng.choice(cand_parents))
-                r = rng.uniform(1.85, 2.15) if (z[i] == 1 or z[j] == 1) else rng.uniform(2.45, 2.95)
-            v = rng.normal(size=3)
-            v /= np.linalg.norm(v)
-            cand = xyz[j] + r * v
-            dist = np.linalg.norm(xyz[:i] - cand, axis=1)
-            dist[j] = np.inf
-            dmin = dist.min() if i > 1 else np.inf
-            if dmin > best_d:
-                best, best_d, best_j = cand, dmin, j
-            if dmin >= 2.8:
-                break
-        xyz[i] = best
-        if len(cand_parents):
-            free[best_j] -= 1
-            free[i] -= 1
-    q = 0.1 * rng.normal(size=nat)
-    q -= q.mean()
-    return z.astype(np.int64), xyz, q
-
-
-def organic_batch(sizes, seed: int):
-    """Padded batch of organic blobs: numbers (B,N) int64, positions (B,N,3),
-    q (B,N); padding is Z=0, pos=0, q=0."""
-    rng = np.random.default_rng(seed)
-    nmax = int(max(sizes))
-    b = len(sizes)
-    numbers = np.zeros((b, nmax), dtype=np.int64)
-    pos = np.zeros((b, nmax, 3))
-    q = np.zeros((b, nmax))
-    for n, nat in enumerate(sizes):
-        z, xyz, qq = organic_blob(int(nat), rng)
-        numbers[n, :nat], pos[n, :nat], q[n, :nat] = z, xyz, qq
-    return torch.from_numpy(numbers), torch.from_numpy(pos), torch.from_numpy(q)
-
-
-def _blob_job(args):
-    nat, seedseq = args
-    return organic_blob(int(nat), np.random.default_rng(seedseq))
-
-
-def organic_batch_parallel(sizes, seed: int, workers: int | None = None):
-    """Like :func:`organic_batch` but every structure has its own spawned seed,
-    so the batch is reproducible for any worker count (used by bench.py)."""
-    import os
-    from concurrent.futures import ProcessPoolExecutor
-
-    sizes = [int(s) for s in sizes]
-    seeds = np.random.SeedSequence(seed).spawn(len(sizes))
-    workers = workers or min(32, os.cpu_count() or 1)
-    if workers > 1 and len(sizes) >= 64:
-        with ProcessPoolExecutor(workers) as ex:
-            blobs = list(ex.map(_blob_job, zip(sizes, seeds), chunksize=32))
-    else:
-        blobs = [_blob_job(a) for a in zip(sizes, seeds)]
-    nmax = max(sizes)
-    numbers = np.zeros((len(sizes), nmax), dtype=np.int64)
-    pos = np.zeros((len(sizes), nmax, 3))
-    q = np.zeros((len(sizes), nmax))
-    for n, (z, xyz, qq) in enumerate(blobs):
-        numbers[n, : len(z)], pos[n, : len(z)], q[n, : len(z)] = z, xyz, qq
-    return torch.from_numpy(numbers), torch.from_numpy(pos), torch.from_numpy(q)
+_sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from bench_inputs import organic_batch, organic_batch_parallel, organic_blob  # noqa: E402,F401

@@ -356,8 +356,11 @@ def _resolve_model(model: Any) -> tuple[int, float, float, float]:
     if name in ("D4Model", "D4SModel"):
         if getattr(model, "ref_charges", "eeq") != "eeq":
             raise NotImplementedError("only ref_charges='eeq' is accelerated")
-        wf = getattr(model, "wf", defaults.WF_DEFAULT)
-        wf = float(wf) if name == "D4Model" else defaults.WF_DEFAULT
+        wf = float(getattr(model, "wf", defaults.WF_DEFAULT))
+        if name == "D4SModel" and wf != defaults.WF_DEFAULT:
+            # the D4S kernels weight with the pair table wfpair (model/d4s.py:61-67); the reference
+            # would apply the explicit uniform wf instead (model/base.py:150): not provided
+            raise NotImplementedError("D4SModel with an explicit weighting factor wf is not accelerated")
         return (0 if name == "D4Model" else 1), float(model.ga), float(model.gc), wf
     raise NotImplementedError(f"model instance of type {name} is outside the accelerated D4 hot path")
 
@@ -395,7 +398,12 @@ def _eeq_charges(numbers: Tensor, positions: Tensor, charge, cutoff: Cutoff | No
     (dispersion/base.py:401-407) on device: ``tad_dftd4_b200.eeq``."""
     from .eeq import get_eeq_charges
 
-    cut = defaults.D4_CN_EEQ_CUTOFF if cutoff is None else cutoff.as_float("cn_eeq")
+    if cutoff is None:
+        cut = defaults.D4_CN_EEQ_CUTOFF
+    elif hasattr(cutoff, "as_float"):
+        cut = cutoff.as_float("cn_eeq")
+    else:  # a foreign Cutoff object (e.g. the reference's own): tensor attributes
+        cut = float(cutoff.cn_eeq)
     return get_eeq_charges(numbers, positions, charge, cutoff=cut)
 
 
@@ -498,7 +506,7 @@ def dftd4(
             rows: list[Tensor | None] = [None] * num2.shape[0]
             small = [b for b in range(num2.shape[0]) if b not in set(big)]
             for b in big:
-                rows[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff)
+                rows[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff, model=(ga, gc, wf))
             if small:
                 # compact the small structures to the front of the atom axis
                 sel = torch.tensor(small, device=num2.device)

@@ -17,9 +17,100 @@ from typing import Callable, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["dftd4_large", "dftd4_large_vjp", "large_energy", "morton_order", "balanced_ranges"]
+__all__ = ["dftd4_large", "dftd4_large_vjp", "large_energy", "morton_order", "balanced_ranges",
+           "work_counts", "profile_begin", "profile_end", "clear_plan_cache"]  # fmt: skip
 
 Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------
+# optional section timing (bench.py: all-reduce time split out of the step)
+# --------------------------------------------------------------------------
+class _Profile:
+    """CUDA-event pairs per named section, recorded on the caller's stream."""
+
+    def __init__(self):
+        self.events: list[tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
+
+    def section(self, name: str):
+        return _Section(self, name)
+
+    def totals_ms(self) -> dict[str, float]:
+        out: dict[str, float] = {}
+        for name, a, b in self.events:
+            b.synchronize()
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+class _Section:
+    def __init__(self, prof, name):
+        self.prof, self.name = prof, name
+
+    def __enter__(self):
+        if self.prof is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.prof is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.prof.events.append((self.name, self.a, b))
+
+
+_PROFILE: _Profile | None = None
+
+
+def profile_begin() -> _Profile:
+    """Start timing the sections ``plan`` and ``all_reduce`` of every following call."""
+    global _PROFILE
+    _PROFILE = _Profile()
+    return _PROFILE
+
+
+def profile_end() -> None:
+    global _PROFILE
+    _PROFILE = None
+
+
+def _section(name: str) -> _Section:
+    return _Section(_PROFILE, name)
+
+
+def work_counts(numbers: Tensor, positions: Tensor, *, cn_cutoff=30.0, disp2_cutoff=60.0, disp3_cutoff=40.0,
+                block: int = 2048) -> dict[str, float]:  # fmt: skip
+    """Exact work of ONE structure in SURVEY.md 8(d)'s units (device tensors, blocked):
+    ``pairs_cn`` (r <= 30), ``pairs_disp2`` (r <= 60), ``centre_triples = sum_j C(n_j, 2)`` with
+    ``n_j`` the neighbours of j within 40, and ``triples = centre_triples - 2 #closed`` -- the
+    unordered triples with at least two distances inside the ATM cutoff (the reference's
+    two-distance mask, dispersion/threebody.py:153-157), ``#closed`` those with all three."""
+    keep = numbers != 0
+    p = positions[keep].to(torch.float64)
+    n = p.shape[0]
+    adj = torch.empty((n, n), dtype=torch.float32, device=p.device)
+    pcn = p2 = 0
+    for b0 in range(0, n, block):
+        d = torch.cdist(p[b0 : b0 + block], p)
+        rows = torch.arange(b0, min(n, b0 + block), device=p.device)
+        d[torch.arange(rows.numel(), device=p.device), rows] = float("inf")  # no self pairs
+        pcn += int((d <= cn_cutoff).sum().item())
+        p2 += int((d <= disp2_cutoff).sum().item())
+        adj[b0 : b0 + block] = (d <= disp3_cutoff).to(torch.float32)
+    nb = adj.sum(-1, dtype=torch.float64)
+    ctrip = float((nb * (nb - 1) / 2).sum().item())
+    closed6 = 0.0  # trace(A^3) = 6 #closed; entries of A.A are exact integers < 2^24 in float32
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for b0 in range(0, n, block):
+            blk = adj[b0 : b0 + block]
+            closed6 += float(((blk @ adj) * blk).sum(dtype=torch.float64).item())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    closed = closed6 / 6.0
+    return {"atoms": n, "pairs_cn": pcn / 2, "pairs_disp2": p2 / 2, "centre_triples": ctrip,
+            "closed_triples": closed, "triples": ctrip - 2.0 * closed}  # fmt: skip
 
 
 def morton_order(positions: Tensor, bits: int = 10) -> Tensor:
@@ -78,6 +169,19 @@ def _kernel_compute(engine, par, numbers, positions, q, rows, groups, want_cost)
     return energy, cost
 
 
+# Topology of the most recent structures: atom order along the Morton curve and this rank's
+# row / centre-group ranges.  Any atom order is correct and the ranges only balance the load,
+# so both are reused for as long as the SAME ``numbers`` tensor comes back (a geometry
+# optimisation or MD run moves the atoms a little per step); a call with another tensor,
+# another world size or an in-place change of ``numbers`` builds a new plan.
+_PLAN_CACHE: dict[tuple, tuple] = {}
+_PLAN_CACHE_SIZE = 4
+
+
+def clear_plan_cache() -> None:
+    _PLAN_CACHE.clear()
+
+
 class _Plan:
     """Sorted/compacted view of one structure + this rank's share of the work."""
 
@@ -85,41 +189,56 @@ class _Plan:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group = group
-        keep = torch.nonzero(numbers != 0).flatten()
-        self.order = keep[morton_order(positions[keep])]
-        self.numbers = numbers[self.order].to(torch.int64).contiguous()
-        self.positions = positions[self.order].detach().contiguous()
-        self.q = q[self.order].detach().to(positions.dtype).contiguous()
-        self.nat = int(self.order.numel())
-        ng = (self.nat + gs - 1) // gs
-        if self.world > 1 and self.nat > 0:
-            # cost model: a centre group with m neighbours evaluates ~m^2/2 pairs x group size
-            cost = compute_cost(self.numbers, self.positions, self.q)
-            g0, g1 = balanced_ranges(cost.to(torch.float64) ** 2, self.world)[self.rank]
-            r0, r1 = min(self.nat, g0 * gs), min(self.nat, g1 * gs)  # rows follow the same blocks
-            if self.rank == self.world - 1:
-                r1 = self.nat
-        else:
-            g0, g1, r0, r1 = 0, ng, 0, self.nat
-        self.rows, self.groups = (r0, r1), (g0, g1)
+        key = (numbers.data_ptr(), numbers._version, tuple(numbers.shape), str(numbers.device), self.world,
+               self.rank, id(group), gs)  # fmt: skip
+        hit = _PLAN_CACHE.get(key)
+        with _section("plan"):
+            if hit is not None:
+                self.order, self.numbers, self.rows, self.groups = hit
+            else:
+                keep = torch.nonzero(numbers != 0).flatten()
+                self.order = keep[morton_order(positions[keep])]
+                self.numbers = numbers[self.order].to(torch.int64).contiguous()
+            self.positions = positions[self.order].detach().contiguous()
+            self.q = q[self.order].detach().to(positions.dtype).contiguous()
+            self.nat = int(self.order.numel())
+            if hit is None:
+                ng = (self.nat + gs - 1) // gs
+                if self.world > 1 and self.nat > 0:
+                    # cost model: a centre group with m neighbours evaluates ~m^2/2 pairs x group size
+                    cost = compute_cost(self.numbers, self.positions, self.q)
+                    g0, g1 = balanced_ranges(cost.to(torch.float64) ** 2, self.world)[self.rank]
+                    r0, r1 = min(self.nat, g0 * gs), min(self.nat, g1 * gs)  # rows follow the same blocks
+                    if self.rank == self.world - 1:
+                        r1 = self.nat
+                else:
+                    g0, g1, r0, r1 = 0, ng, 0, self.nat
+                self.rows, self.groups = (r0, r1), (g0, g1)
+                while len(_PLAN_CACHE) >= _PLAN_CACHE_SIZE:
+                    _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+                _PLAN_CACHE[key] = (self.order, self.numbers, self.rows, self.groups)
 
     def all_reduce(self, t: Tensor) -> Tensor:
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            with _section("all_reduce"):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
 
-def _kernel_backend(positions: Tensor, param, cutoff):
+def _kernel_backend(positions: Tensor, param, cutoff, model=None):
+    """``model``: (ga, gc, wf) of the caller's D4Model (defaults when None)."""
     from . import _lib, defaults
     from .disp import _Engine, _flatten_param, _param_tensors
+
+    ga, gc, wf = model if model is not None else (defaults.GA_DEFAULT, defaults.GC_DEFAULT, defaults.WF_DEFAULT)
 
     if _param_tensors(param):
         raise NotImplementedError(
             "gradients with respect to the damping parameters are provided for structures of the "
             "one-CTA-per-structure kernels only (detach the parameters for the tiled large-system path)"
         )
-    engine = _Engine.get(positions.device, defaults.GA_DEFAULT, defaults.GC_DEFAULT)
-    par = _flatten_param(param, cutoff, 0, defaults.WF_DEFAULT)
+    engine = _Engine.get(positions.device, ga, gc)
+    par = _flatten_param(param, cutoff, 0, wf)
     lib = engine.lib
     gs = int(lib.d4b200_large_group_size())
     fp32 = positions.dtype == torch.float32
@@ -168,11 +287,11 @@ def _check_single(numbers, positions, q):
         raise ValueError("expected numbers (nat,), positions (nat, 3), q (nat,)")
 
 
-def large_energy(numbers, positions, param, q, *, cutoff=None, group=None, backend=None) -> Tensor:
+def large_energy(numbers, positions, param, q, *, cutoff=None, group=None, backend=None, model=None) -> Tensor:
     """Atom-resolved D4 energy of ONE structure ``(nat,)`` with the tiled kernels
     (no autograd; see :func:`dftd4_large`)."""
     _check_single(numbers, positions, q)
-    be = backend or _kernel_backend(positions, param, cutoff)
+    be = backend or _kernel_backend(positions, param, cutoff, model)
     plan = _Plan(numbers, positions, q, group,
                  lambda n, p, qq: be["energy"](n, p, qq, (0, 0), (0, 0), True)[1], be["group_size"])  # fmt: skip
     out = torch.zeros(numbers.shape[0], dtype=positions.dtype, device=positions.device)
@@ -183,14 +302,14 @@ def large_energy(numbers, positions, param, q, *, cutoff=None, group=None, backe
     return out
 
 
-def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=None, backend=None):
+def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=None, backend=None, model=None):
     """``(dL/dpositions, dL/dq)`` for ``L = sum_i gout_i E_i`` of ONE structure.
 
     Two stages with one all-reduce each (plus the final one for the forces):
     direct two-body/ATM terms -> all-reduce(dL/dcn, dL/dq) -> CN chain rule on the
     rank's rows -> all-reduce(dL/dpositions)."""
     _check_single(numbers, positions, q)
-    be = backend or _kernel_backend(positions, param, cutoff)
+    be = backend or _kernel_backend(positions, param, cutoff, model)
     plan = _Plan(numbers, positions, q, group,
                  lambda n, p, qq: be["energy"](n, p, qq, (0, 0), (0, 0), True)[1], be["group_size"])  # fmt: skip
     gpos = torch.zeros_like(positions)
@@ -212,18 +331,18 @@ def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=No
 
 class _LargeFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, positions, q, numbers, param, cutoff, group):
+    def forward(ctx, positions, q, numbers, param, cutoff, group, model):
         ctx.save_for_backward(positions, q, numbers)
-        ctx.param, ctx.cutoff, ctx.group = param, cutoff, group
-        return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group)
+        ctx.param, ctx.cutoff, ctx.group, ctx.model = param, cutoff, group, model
+        return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group, model=model)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         positions, q, numbers = ctx.saved_tensors
         gpos, gq = dftd4_large_vjp(numbers, positions, ctx.param, q, gout.contiguous(),
-                                   cutoff=ctx.cutoff, group=ctx.group)  # fmt: skip
-        return gpos, gq, None, None, None, None
+                                   cutoff=ctx.cutoff, group=ctx.group, model=ctx.model)  # fmt: skip
+        return gpos, gq, None, None, None, None, None
 
 
 def dftd4_large(
@@ -236,6 +355,7 @@ def dftd4_large(
     group=None,
     compute: Callable | None = None,
     group_size: int | None = None,
+    model: tuple[float, float, float] | None = None,
 ) -> Tensor:
     """Atom-resolved D4 energy of ONE structure ``(nat,)`` with the tiled kernels;
     differentiable with respect to ``positions`` and ``q``.
@@ -244,10 +364,11 @@ def dftd4_large(
     (replicated) inputs, evaluates its share of two-body rows / ATM centre groups and
     the result is all-reduced, so every rank returns the full energy vector.
 
-    ``compute(numbers, positions, q, rows, groups, want_cost)`` is injectable for CPU
-    tests of this host logic (energy only).
+    ``model = (ga, gc, wf)`` carries the hyper-parameters of a caller-supplied ``D4Model``
+    (defaults otherwise).  ``compute(numbers, positions, q, rows, groups, want_cost)`` is
+    injectable for CPU tests of this host logic (energy only).
     """
     if compute is not None:
         be = dict(energy=compute, group_size=group_size or 16)
         return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group, backend=be)
-    return _LargeFunction.apply(positions, q, numbers, param, cutoff, group)
+    return _LargeFunction.apply(positions, q, numbers, param, cutoff, group, model)
