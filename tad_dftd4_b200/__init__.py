@@ -14,6 +14,7 @@ from .cutoff import Cutoff
 from .damping import MZeroDamping, OptimisedPowerDamping, Param, RationalDamping, ZeroDamping, get_params
 from .eeq import get_eeq_charges
 from .disp import dftd4, dftd4_host, get_properties, last_launch_count, set_checks, set_fused_forward
+from .install import install, uninstall
 from .model import D4Model, D4SModel
 
 __version__ = "0.1.0"
@@ -22,4 +23,5 @@ __all__ = [
     "__version__", "batch", "cutoff", "Cutoff", "damping", "defaults", "dftd4", "dftd4_host", "get_params",
     "get_properties", "pack", "Param", "RationalDamping", "set_checks", "set_fused_forward", "last_launch_count",
     "ZeroDamping", "MZeroDamping", "OptimisedPowerDamping", "dispersion", "eeq", "get_eeq_charges", "large", "model", "ncoord", "parallel", "D4Model", "D4SModel",
+    "install", "uninstall",
 ]  # fmt: skip

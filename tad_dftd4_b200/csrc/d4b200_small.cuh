@@ -424,6 +424,174 @@ __device__ __forceinline__ T reduce8x32(const T (&v)[8], bool b4, bool b3, bool 
   return y;
 }
 
+// ---------------------------------------------------------------------------
+// Register-tiled gradient sweep (closed structure, unit upstream weights).
+//
+// The owner-pair sweep above reads six stash entries (48 B) per visit for 20 FP64
+// instructions: four warps per scheduler at the FP64 rate ask the shared-memory
+// crossbar (128 B/clk/SM) for ~0.9 wavefronts per clock -- it is co-limited by LDS
+// bandwidth.  Here a thread owns the 2 x 2 block of owner pairs {i0, i1} x {k0, k1},
+//   i0 = 2I, i1 = 2I + 1, k0 = m, k1 = m + I   (0 <= m < I),
+// and sweeps the third atom j: the stash entries of (i0,j), (i1,j), (k0,j), (k1,j) are
+// loaded once and serve four visits (24 B per visit).  Consecutive lanes take
+// consecutive m, so the k loads are unit-stride across the warp (conflict free) and the
+// i loads are broadcasts.  The blocks cover every pair (i,k) with k < 2 (i >> 1) exactly
+// once; the remaining "diagonal" pairs (2I + 1, 2I) are swept by eight lanes each.
+// When the last round of blocks fills less than half of the CTA, every block is shared
+// by 2 or 4 lanes (sub-ranges of j, combined with shuffles in a fixed order).
+// ---------------------------------------------------------------------------
+
+// per-pair epilogue of the closed/unit sweep: sums over the third atom -> dL/dC6(q=0), dL/dr^2
+// and the energy shares of the fused energy + gradient call
+template <typename T, bool D4S, int CP>
+__device__ __forceinline__ void grad_pair_store(T* __restrict__ out0, T* __restrict__ out1, bool want_e, int p,
+                                                T bb, T Pjk, T ifac9, T accG, T accC, T accS) {
+  const bool pz = Pjk == T(0);  // no ATM contribution through this pair (C6(q=0) = 0)
+  T accH = accG + accG;         // both atoms of the owner pair have multiplicity 2
+  accG *= T(6);                 // unit upstream weights: W = 6 for every triple
+  accC *= T(6);
+  accS *= T(6);
+  if (pz) accG = accC = accS = accH = T(0);
+  const T accD = fma(accC, d4_rcp(bb), T(0.375) * accS);
+  if constexpr (!D4S) {
+    const T w = (Pjk * ifac9) * (bb * bb);  // C6(q=0) = (P'_jk r^5 / fac9)^2
+    accG = pz ? T(0) : accG * (T(0.5) * d4_rcp((w * w) * bb));
+  }
+  out0[p] = accG;
+  out1[p] = accD;
+  if (want_e) {
+    out0[2 * CP + p] = accH;
+    out0[3 * CP + p] = accH;
+  }
+}
+
+// loop invariants of one owner pair (see grad_visit)
+template <typename T>
+struct OwnerPair {
+  T b, b2, twob, iP, sPu, kAi;
+  __device__ __forceinline__ void load(const T* __restrict__ pa, const T* __restrict__ pP,
+                                       const T* __restrict__ pu, int p, T kA) {
+    b = fabs(pa[p]);
+    b2 = b * b;
+    twob = b + b;
+    const T Pjk = pP[p];
+    iP = Pjk == T(0) ? T(1) : d4_rcp(Pjk);
+    sPu = T(6) * pu[p] * iP;
+    kAi = kA * iP;
+  }
+};
+
+template <typename T, bool D4S, int CAP, int NT>
+__device__ __forceinline__ void grad_sweep_tiled(const T* __restrict__ pa, const T* __restrict__ pP,
+                                                 const T* __restrict__ pu, T* __restrict__ out0,
+                                                 T* __restrict__ out1, bool want_e,
+                                                 const unsigned short* __restrict__ pij, int n, int tid,
+                                                 T kA, T kB, T ifac9) {
+  constexpr int CP = CAP * (CAP - 1) / 2;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nI = (n + 1) >> 1;  // atom pairs (2I, 2I + 1); the last one may lack its second atom
+  const int nblk = nI * (nI - 1) / 2;
+  const T z = T(0);
+  for (int base = 0; base < nblk; base += NT) {
+    const int left = nblk - base;
+    // lanes per block in this round (1, 2 or 4; CTA-uniform)
+    const int parts = left * 2 > NT ? 1 : (left * 4 > NT ? 2 : 4);
+    const int per = 32 / parts;  // blocks per warp
+    if (warp * per >= left) continue;
+    const int sub = lane / per;  // which part of the j range
+    const int item = base + warp * per + (lane - sub * per);
+    const bool valid = item < nblk;
+    int I, m;
+    pair_lookup(pij, valid ? item : nblk - 1, I, m);
+    const int i0 = 2 * I, k0 = m, k1 = m + I;
+    const bool has1 = i0 + 1 < n;
+    const int i1 = has1 ? i0 + 1 : i0;  // odd n: the last row pair is a single row (evaluated twice, stored once)
+    const int ti0 = i0 * (i0 - 1) / 2, ti1 = i1 * (i1 - 1) / 2;
+    const int tk0 = k0 * (k0 - 1) / 2, tk1 = k1 * (k1 - 1) / 2;
+    const int p00 = ti0 + k0, p01 = ti0 + k1, p10 = ti1 + k0, p11 = ti1 + k1;
+    OwnerPair<T> o00, o01, o10, o11;
+    o00.load(pa, pP, pu, p00, kA);
+    o01.load(pa, pP, pu, p01, kA);
+    o10.load(pa, pP, pu, p10, kA);
+    o11.load(pa, pP, pu, p11, kA);
+    T g00 = z, c00 = z, s00 = z, g01 = z, c01 = z, s01 = z;
+    T g10 = z, c10 = z, s10 = z, g11 = z, c11 = z, s11 = z;
+    T dH = z, dL = z;  // unused outputs of grad_visit in this mode
+    const int len = (n + parts - 1) / parts;
+    const int jbeg = sub * len;
+    const int jend = min(n, jbeg + len);
+#pragma unroll 1
+    for (int j = jbeg; j < jend; ++j) {
+      const int tj = j * (j - 1) / 2;
+      // stash index of (x, j); for j == x the owner's own entry (finite values, factor zeroed below)
+      const int xi0 = j < i0 ? ti0 + j : (j > i0 ? tj + i0 : p00);
+      const int xi1 = j < i1 ? ti1 + j : (j > i1 ? tj + i1 : p10);
+      const int xk0 = j < k0 ? tk0 + j : (j > k0 ? tj + k0 : p00);
+      const int xk1 = j < k1 ? tk1 + j : (j > k1 ? tj + k1 : p01);
+      const T ai0 = pa[xi0], ui0 = pu[xi0], Pi0 = j != i0 ? pP[xi0] : z;
+      const T ai1 = pa[xi1], ui1 = pu[xi1], Pi1 = j != i1 ? pP[xi1] : z;
+      const T ak0 = pa[xk0], uk0 = pu[xk0], Pk0 = j != k0 ? pP[xk0] : z;
+      const T ak1 = pa[xk1], uk1 = pu[xk1], Pk1 = j != k1 ? pP[xk1] : z;
+      grad_visit<T, false, true>(ai0, Pi0, ui0, ak0, Pk0, uk0, o00.b, o00.b2, o00.twob, z, o00.iP, o00.sPu,
+                                 o00.kAi, kB, z, z, z, z, g00, c00, s00, dH, dL);
+      grad_visit<T, false, true>(ai0, Pi0, ui0, ak1, Pk1, uk1, o01.b, o01.b2, o01.twob, z, o01.iP, o01.sPu,
+                                 o01.kAi, kB, z, z, z, z, g01, c01, s01, dH, dL);
+      grad_visit<T, false, true>(ai1, Pi1, ui1, ak0, Pk0, uk0, o10.b, o10.b2, o10.twob, z, o10.iP, o10.sPu,
+                                 o10.kAi, kB, z, z, z, z, g10, c10, s10, dH, dL);
+      grad_visit<T, false, true>(ai1, Pi1, ui1, ak1, Pk1, uk1, o11.b, o11.b2, o11.twob, z, o11.iP, o11.sPu,
+                                 o11.kAi, kB, z, z, z, z, g11, c11, s11, dH, dL);
+    }
+    if (parts > 1) {  // combine the sub-ranges: fixed order, the first lane of a block ends up with the sum
+#define D4_COMBINE(v)                                                     \
+  if (parts == 4) v += __shfl_down_sync(0xffffffffu, v, 16);              \
+  v += __shfl_down_sync(0xffffffffu, v, per);
+      // parts == 4: per = 8, lanes l, l+8, l+16, l+24 -> (l, l+16) and (l+8, l+24), then l + (l+8)
+      D4_COMBINE(g00) D4_COMBINE(c00) D4_COMBINE(s00) D4_COMBINE(g01) D4_COMBINE(c01) D4_COMBINE(s01)
+      D4_COMBINE(g10) D4_COMBINE(c10) D4_COMBINE(s10) D4_COMBINE(g11) D4_COMBINE(c11) D4_COMBINE(s11)
+#undef D4_COMBINE
+    }
+    if (valid && sub == 0) {
+      grad_pair_store<T, D4S, CP>(out0, out1, want_e, p00, o00.b, pP[p00], ifac9, g00, c00, s00);
+      grad_pair_store<T, D4S, CP>(out0, out1, want_e, p01, o01.b, pP[p01], ifac9, g01, c01, s01);
+      if (has1) {
+        grad_pair_store<T, D4S, CP>(out0, out1, want_e, p10, o10.b, pP[p10], ifac9, g10, c10, s10);
+        grad_pair_store<T, D4S, CP>(out0, out1, want_e, p11, o11.b, pP[p11], ifac9, g11, c11, s11);
+      }
+    }
+  }
+  // diagonal pairs (2d + 1, 2d): eight lanes per pair, each an eighth of the j range
+  const int nd = n >> 1;
+  const int len8 = (n + 7) >> 3;
+  for (int d0 = 0; d0 < nd; d0 += NT / 8) {
+    if (d0 + warp * 4 >= nd) continue;
+    const int d = d0 + (tid >> 3), sub = lane & 7;
+    const bool valid = d < nd;
+    const int jj = 2 * (valid ? d : nd - 1) + 1, kk = jj - 1;
+    const int tjj = jj * (jj - 1) / 2, tkk = kk * (kk - 1) / 2;
+    const int p = tjj + kk;
+    OwnerPair<T> o;
+    o.load(pa, pP, pu, p, kA);
+    T g = z, c = z, s = z, dH = z, dL = z;
+    const int jend = min(n, (sub + 1) * len8);
+#pragma unroll 2
+    for (int j = sub * len8; j < jend; ++j) {
+      const int tj = j * (j - 1) / 2;
+      const bool ok = (j != jj) & (j != kk);
+      const int x1 = ok ? (j < jj ? tjj + j : tj + jj) : p;
+      const int x2 = ok ? (j < kk ? tkk + j : tj + kk) : p;
+      grad_visit<T, false, true>(pa[x1], ok ? pP[x1] : z, pu[x1], pa[x2], pP[x2], pu[x2], o.b, o.b2, o.twob, z,
+                                 o.iP, o.sPu, o.kAi, kB, z, z, z, z, g, c, s, dH, dL);
+    }
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      g += __shfl_down_sync(0xffffffffu, g, off);
+      c += __shfl_down_sync(0xffffffffu, c, off);
+      s += __shfl_down_sync(0xffffffffu, s, off);
+    }
+    if (valid && sub == 0) grad_pair_store<T, D4S, CP>(out0, out1, want_e, p, o.b, pP[p], ifac9, g, c, s);
+  }
+}
+
 template <typename T, bool GRAD, bool D4S, int CAP, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   using L = Lay<T, GRAD, D4S, CAP>;
@@ -1060,6 +1228,15 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         // Whole warps walk the pair list (lanes past the end repeat the last pair and skip the
         // stores) so that the sweep can use warp-uniform loop bounds.
         const T ifac9 = d4_rcp(P.fac9);
+#ifndef D4_NO_TILED_SWEEP
+        const bool tiled = !open && A.gin == nullptr && n >= 4;
+#else
+        const bool tiled = false;
+#endif
+        if (tiled)
+          grad_sweep_tiled<T, D4S, CAP, NT>(pa, pP, pu, out0, out1, A.energy != nullptr, tab.pij, n, tid,
+                                            T(0.5) * P.alp3, T(0.5) * P.alp3 - T(2.5), ifac9);
+        else
         for (int p0 = warp * 32; p0 < np; p0 += NT) {
           const bool valid = p0 + lane < np;
           const int p = valid ? p0 + lane : np - 1;

@@ -39,19 +39,69 @@ class DispTerm:
     def __hash__(self) -> int:
         return hash((type(self).__name__, self.charge_dependent))
 
+    # which part of the fused kernel this term stands for: parameters that are switched off
+    _OFF: dict[str, float] = {}
+
+    def calculate(self, numbers, positions, param, cn=None, model="d4", q=None, r4r2=None, rvdw=None,
+                  cutoff=None):  # fmt: skip
+        """Atom-resolved energy of this term: the plugin interface of the reference
+        (``DispTerm.calculate``, ``dispersion/base.py:88-101``), so that an instance can be
+        registered with the reference's own ``Disp`` (``base.py:215-219``) as well as with
+        :class:`Disp` below.
+
+        ``cn`` is accepted and ignored: the kernels evaluate the D4 coordination number of the
+        structure themselves, fused with everything that consumes it (it is the same
+        ``cn_d4`` / ``erf_count`` the reference computes at ``base.py:390``;
+        :func:`tad_dftd4_b200.ncoord.cn_d4` returns it stand-alone).  ``r4r2`` / ``rvdw`` must
+        be the defaults (the reference always passes the gathered default tables here, so they
+        are not checked); ``model`` may be a model name, this package's ``D4Model`` /
+        ``D4SModel`` or the reference's (read through ``ga``, ``gc``, ``wf``)."""
+        if type(self.damping_fn).__name__ != self._DAMPING:
+            raise NotImplementedError(f"only {self._DAMPING} is accelerated for {type(self).__name__}")
+        if self.charge_dependent != self._CHARGE_DEPENDENT:
+            raise NotImplementedError(
+                f"{type(self).__name__}(charge_dependent={self.charge_dependent}) is outside the accelerated path"
+            )
+        par = dict(param)
+        for key, val in self._OFF.items():
+            par[key] = val
+        if "s10" in self._OFF:
+            par.pop("s10")
+        if q is None:
+            if self.charge_dependent:
+                raise ValueError("a charge-dependent term needs the atomic charges q")
+            q = torch.zeros(numbers.shape, dtype=positions.dtype, device=positions.device)
+        elif not self.charge_dependent:
+            q = torch.zeros_like(q)  # the reference evaluates such a term with zeta(q = 0)
+        return dftd4(numbers, positions, 0.0, par, model=model, q=q, cutoff=cutoff)
+
 
 class TwoBodyTerm(DispTerm):
+    """Two-body term with rational damping (``dispersion/twobody.py:89-201``): the fused kernel
+    with the ATM part switched off."""
+
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "RationalDamping", True, {"s9": 0.0}
+
     def __init__(self, *, damping_fn: Any = None, charge_dependent: bool = True):
         super().__init__(damping_fn if damping_fn is not None else RationalDamping(), charge_dependent)
 
 
 class D4ATMApprox(DispTerm):
+    """ATM term with the approximate C9 (``dispersion/d4.py:29-45``, ``threebody.py:210-256``):
+    the fused kernel with the two-body part switched off."""
+
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "ZeroDamping", False, {"s6": 0.0, "s8": 0.0, "s10": 0.0}
+
     def __init__(self, *, damping_fn: Any = None, charge_dependent: bool = False):
         super().__init__(damping_fn if damping_fn is not None else ZeroDamping(), charge_dependent)
 
 
 class FusedD4Term(DispTerm):
-    """Two-body + ATM in one launch (what ``DispD4`` registers as two terms)."""
+    """Two-body + ATM in ONE launch (what ``DispD4`` registers as two terms).  Registered with
+    the reference's ``Disp`` -- ``Disp(model="d4").register(FusedD4Term())`` -- it makes the
+    reference's own class-based driver run on the kernels."""
+
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "RationalDamping", True, {}
 
     def __init__(self):
         super().__init__(RationalDamping(), True)
