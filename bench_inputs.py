@@ -119,15 +119,23 @@ def organic_batch_parallel(sizes, seed: int, workers: int | None = None):
 # --------------------------------------------------------------------------
 # C4: water cluster
 # --------------------------------------------------------------------------
-def water_cluster(nmol: int, seed: int):
+def water_cluster(nmol: int, seed: int, rod: tuple[int, int] | None = None):
     """O on a jittered simple-cubic lattice (5.86 Bohr) clipped to a
     sphere, random orientation per molecule, r_OH = 1.81 Bohr, HOH = 104.5 deg.
+    ``rod=(a, b)``: an a x b x ceil(nmol / ab) column of the same lattice instead of the sphere
+    (every cutoff is exceeded along the column; used by the large-structure parity tests).
     Returns numbers (3 nmol,), positions (3 nmol, 3), q (3 nmol,)."""
     torch = _torch()
     rng = np.random.default_rng(seed)
-    m = int(np.ceil((nmol * 6 / np.pi) ** (1 / 3))) + 2
-    grid = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) - (m - 1) / 2
-    grid = grid[np.argsort(np.linalg.norm(grid, axis=1), kind="stable")][:nmol]
+    if rod is not None:
+        a, b = rod
+        c = -(-nmol // (a * b))
+        grid = np.stack(np.meshgrid(np.arange(c), np.arange(b), np.arange(a), indexing="ij"), -1).reshape(-1, 3)
+        grid = grid[:nmol, ::-1].astype(float)
+    else:
+        m = int(np.ceil((nmol * 6 / np.pi) ** (1 / 3))) + 2
+        grid = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) - (m - 1) / 2
+        grid = grid[np.argsort(np.linalg.norm(grid, axis=1), kind="stable")][:nmol]
     o = grid * 5.86 + rng.normal(scale=0.3, size=(nmol, 3))
     a = np.deg2rad(104.5) / 2
     h1 = np.array([np.sin(a), np.cos(a), 0.0]) * 1.81

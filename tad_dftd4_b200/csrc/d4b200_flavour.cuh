@@ -12,7 +12,10 @@ struct d4b200_tables;
 // Size classes per flavour: X(class, CAP, threads, min CTAs/SM for launch bounds).
 // Caps are bounded by the 227 KB shared-memory budget (Lay<>::total, static_assert).
 #define D4_CLASSES_F64_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 3) X(3, 96, 512, 1) X(4, 120, 512, 1)
-#define D4_CLASSES_F64_G(X) X(0, 32, 128, 4) X(1, 48, 256, 2) X(2, 64, 512, 1) X(3, 80, 512, 1) X(4, 100, 512, 1)
+#ifndef D4_G100_NT
+#define D4_G100_NT 512  // threads of the largest FP64 gradient class (A/B knob)
+#endif
+#define D4_CLASSES_F64_G(X) X(0, 32, 128, 4) X(1, 48, 256, 2) X(2, 64, 512, 1) X(3, 80, 512, 1) X(4, 100, D4_G100_NT, 1)
 #define D4_CLASSES_F32_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 4) X(3, 96, 512, 2) X(4, 128, 512, 1)
 #define D4_CLASSES_F32_G(X) X(0, 32, 128, 6) X(1, 48, 256, 3) X(2, 64, 512, 2) X(3, 96, 512, 1) X(4, 128, 512, 1)
 // D4S: no per-atom polarizability vectors (pair-dependent weights are evaluated per

@@ -520,7 +520,11 @@ __device__ __forceinline__ void grad_sweep_tiled(const T* __restrict__ pa, const
     const int len = (n + parts - 1) / parts;
     const int jbeg = sub * len;
     const int jend = min(n, jbeg + len);
-#pragma unroll 1
+#ifndef D4_TILED_UNROLL
+#define D4_TILED_UNROLL 1
+#endif
+    constexpr int kUnroll = D4_TILED_UNROLL;  // j steps in flight (four visits each)
+#pragma unroll kUnroll
     for (int j = jbeg; j < jend; ++j) {
       const int tj = j * (j - 1) / 2;
       // stash index of (x, j); for j == x the owner's own entry (finite values, factor zeroed below)
@@ -1678,39 +1682,45 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
             pu[p] += (ATOM(AT_DCN)[i] + ATOM(AT_DCN)[j]) * dcn * rinv;
           }
         }
+        if (A.energy) {
+          // fused energy + gradient call: per-pair energy shares of the higher- / lower-index atom
+          // from the L2 scratch (coalesced) into the planes `pa` / `pP`, which are free by now; the
+          // force gather below sums them along the rows (no strided column reads from global memory)
+          const T e2 = T(-0.5) * out0[4 * CP + p];
+          pa[p] = P.has_atm ? fma(T(0.5), out0[2 * CP + p], e2) : e2;
+          pP[p] = P.has_atm ? fma(T(0.5), out0[3 * CP + p], e2) : e2;
+        }
       }
       __syncthreads();
       PHASE(13);
       // phase 11: gather forces (one warp per atom)
       for (int i = warp; i < n; i += NW) {
         const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
-        T fx = T(0), fy = T(0), fz = T(0);
+        T fx = T(0), fy = T(0), fz = T(0), es = T(0);
         const int ti = i * (i - 1) / 2;
+        const bool want_e = A.energy != nullptr;
         for (int j = lane; j < n; j += 32) {
           if (j == i) continue;
-          const T c = j < i ? pu[ti + j] : pu[j * (j - 1) / 2 + i];
+          const int pp = j < i ? ti + j : j * (j - 1) / 2 + i;
+          const T c = pu[pp];
           fx += c * (xi - ATOM(AT_X)[j]);
           fy += c * (yi - ATOM(AT_Y)[j]);
           fz += c * (zi - ATOM(AT_Z)[j]);
+          if (want_e) es += j < i ? pa[pp] : pP[pp];
         }
         fx = warp_sum(fx);
         fy = warp_sum(fy);
         fz = warp_sum(fz);
+        if (want_e) es = warp_sum(es);
         if (lane == 0) {
           const size_t o = (size_t)b * A.nat + idx[i];
+          if (want_e) A.energy[o] = es;
           if (A.grad) {
             A.grad[3 * o] = fx;
             A.grad[3 * o + 1] = fy;
             A.grad[3 * o + 2] = fz;
           }
           if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
-        }
-      }
-      if (A.energy) {  // fused energy + gradient call: assemble the atomic energies as well
-        D4_ROWS8(i, sub) {
-          T e = T(-0.5) * row_sum2_8(out0 + 4 * CP, out0 + 4 * CP, i, sub, n);
-          if (P.has_atm) e += T(0.5) * row_sum2_8(out0 + 2 * CP, out0 + 3 * CP, i, sub, n);
-          if (sub == 0 && i < n) A.energy[(size_t)b * A.nat + idx[i]] = e;
         }
       }
       __syncthreads();

@@ -94,3 +94,88 @@ def test_dftd4_large_gradient_through_public_api():
     e = d4.dftd4(numbers.to(dev), pd, 0.0, PBE0, q=q.to(dev))
     (g,) = torch.autograd.grad(e.sum(), pd)
     assert (g.cpu() - g_ref).abs().max() < 1e-9
+
+
+# --------------------------------------------------------------------------------------------
+# Parity at scale with the reference's DEFAULT cutoffs (60 / 40 / 30 Bohr): the blocked oracle
+# (oracle/d4_oracle_blocked.py, pinned against the dense oracle in tests/test_oracle_blocked.py)
+# live at 1.2 k atoms incl. the gradient, golden vectors (oracle/make_golden_large.py) at 5 k atoms
+# and on sampled atoms of the full 20 001-atom C4 cluster.
+# --------------------------------------------------------------------------------------------
+GOLDEN_LARGE = __import__("pathlib").Path(__file__).resolve().parent / "golden" / "large"
+
+
+def _gpu_energy_gradient(numbers, positions, q, with_gradient=True):
+    from tad_dftd4_b200.large import dftd4_large
+
+    dev = torch.device("cuda:0")
+    pos = positions.to(dev).requires_grad_(with_gradient)
+    e = dftd4_large(numbers.to(dev), pos, PBE0, q.to(dev))
+    g = torch.autograd.grad(e.sum(), pos)[0].cpu() if with_gradient else None
+    return e.detach().cpu(), g
+
+
+def test_rod_1200_energy_and_gradient_default_cutoffs():
+    """400 H2O in a 3 x 3 column (260 Bohr long): pairs beyond every cutoff, open triples at 40 Bohr."""
+    import bench_inputs
+    import d4_oracle_blocked as blk
+
+    numbers, positions, q = bench_inputs.water_cluster(400, 11, rod=(3, 3))
+    e_ref, g_ref = blk.dftd4_blocked(numbers, positions, PBE0, q, gradient=True, block3=8)
+    e, g = _gpu_energy_gradient(numbers, positions, q)
+    assert (e - e_ref).abs().max() / e_ref.abs().max() < 1e-10
+    assert abs(e.sum() - e_ref.sum()) <= 1e-10 * abs(e_ref.sum())
+    assert (g - g_ref).abs().max() < 1e-9
+
+
+def test_rod_5001_energy_golden():
+    import bench_inputs
+
+    gold = np.load(GOLDEN_LARGE / "rod5001.npz")
+    numbers, positions, q = bench_inputs.water_cluster(int(gold["nmol"]), int(gold["seed"]), rod=tuple(gold["rod"]))
+    e_ref = torch.from_numpy(gold["energy"])
+    e, g = _gpu_energy_gradient(numbers, positions, q)
+    assert (e - e_ref).abs().max() / e_ref.abs().max() < 1e-10
+    assert abs(e.sum() - e_ref.sum()) <= 1e-10 * abs(e_ref.sum())
+    # the gradient at this size: translation / rotation invariance and one finite difference of the energy
+    assert g.sum(0).abs().max() < 1e-9 and torch.linalg.cross(positions, g).sum(0).abs().max() < 1e-7
+    i, h = 2500, 1e-4
+    ep = [_gpu_energy_gradient(numbers, positions + s * h * torch.eye(3)[0] * (torch.arange(numbers.shape[0]) == i)[:, None],
+                               q, False)[0].sum().item() for s in (1.0, -1.0)]  # fmt: skip
+    assert abs((ep[0] - ep[1]) / (2 * h) - g[i, 0].item()) < 1e-8
+
+
+def test_c4_full_size_sampled_atoms_golden():
+    """BASELINE config C4 itself (20 001 atoms, default cutoffs): atom-resolved energies of 12 sampled
+    atoms against the blocked oracle; energy and gradient consistency at full size."""
+    import bench_inputs
+
+    gold = np.load(GOLDEN_LARGE / "c4_samples.npz")
+    numbers, positions, q = bench_inputs.water_cluster(int(gold["nmol"]), int(gold["seed"]))
+    rows, e_ref = torch.from_numpy(gold["rows"]), torch.from_numpy(gold["energy"])
+    e, g = _gpu_energy_gradient(numbers, positions, q)
+    assert ((e[rows] - e_ref).abs() / e_ref.abs()).max() < 1e-10
+    assert g.sum(0).abs().max() < 1e-8 and torch.isfinite(g).all()
+    i, h = int(rows[5]), 1e-4
+    ep = [_gpu_energy_gradient(numbers, positions + s * h * torch.eye(3)[1] * (torch.arange(numbers.shape[0]) == i)[:, None],
+                               q, False)[0].sum().item() for s in (1.0, -1.0)]  # fmt: skip
+    assert abs((ep[0] - ep[1]) / (2 * h) - g[i, 1].item()) < 1e-7
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs")
+def test_cross_rank_equals_single_rank():
+    """Energy and gradient of a 6 000-atom cluster partitioned over all GPUs of the box (NCCL
+    all-reduces) against the single-rank evaluation: <= 1e-12 (tools/c4_crossrank.py)."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    n = min(torch.cuda.device_count(), 8)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(root / "tools" / "c4_crossrank.py"),
+                          "2000"], capture_output=True, text=True, timeout=900, cwd=str(root))  # fmt: skip
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["ranks"] == n and res["max_rel_energy_diff"] < 1e-12 and res["max_abs_gradient_diff"] < 1e-12
