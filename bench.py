@@ -51,8 +51,14 @@ import threading
 import time
 from pathlib import Path
 
-import numpy as np
-import torch
+# torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also times the CPU baseline on all host
+# cores (the other ranks only wait for it), so give its OpenMP / MKL pools the whole box back
+# BEFORE torch initialises them
+if os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -84,6 +90,13 @@ WORKLOADS = {
                 name="C4: single 20001-atom water cluster (6667 H2O), D4 energy + analytic gradient, default "
                      "60/40/30 Bohr cutoffs, row-block split over the GPUs + all-reduces"),
 }  # fmt: skip
+
+
+_OUT = None  # the process's real stdout (see main): exactly one JSON line goes there
+
+
+def emit(line: dict) -> None:
+    print(json.dumps(line), file=_OUT or sys.stdout, flush=True)
 
 
 def oracle():
@@ -242,8 +255,8 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     if wl.get("large"):
-        print(json.dumps({"impl": "reference", "unavailable": "the dense reference formulation needs "
-                          "157 GB for rc6 and 6.4e13 B per N^3 temporary at 20k atoms (BASELINE.md)"}), flush=True)
+        emit({"impl": "reference", "unavailable": "the dense reference formulation needs "
+              "157 GB for rc6 and 6.4e13 B per N^3 temporary at 20k atoms (BASELINE.md)"})
         return
     numbers, positions, q = make_batch(wl, 0)
     nsample, chunk = cpu_sample_shape(wl, numbers.shape[0])
@@ -268,7 +281,7 @@ def run_reference(args, wl, rank, world):
         "note": "CPU arm: the host cores of this box run the oracle port of tad-dftd4 0.8.0 (kind = port); "
                 "it does not scale with --gpus",
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -340,13 +353,15 @@ class BatchBench:
         positions_h, q_h = positions_h.to(self.dtype), q_h.to(self.dtype)
         self.nat, self.pairs, self.triples, self.flop = work_counts(numbers_h, wl["grad"])
         self.numbers_h, self.positions_h, self.q_h = numbers_h.pin_memory(), positions_h.pin_memory(), q_h.pin_memory()
+        # the host-buffer API takes the atomic numbers as the caller holds them; one byte per atom is enough
+        self.numbers_h8 = numbers_h.to(torch.uint8).pin_memory()
         self.numbers, self.positions, self.q = self.numbers_h.to(dev), self.positions_h.to(dev), self.q_h.to(dev)
         self.model = wl.get("model", "d4")
         self.eeq = eeq
         self.out_e = torch.empty(numbers_h.shape, dtype=self.dtype).pin_memory()
         self.out_g = torch.empty(positions_h.shape, dtype=self.dtype).pin_memory() if wl["grad"] else None
         es = positions_h.element_size()
-        self.h2d = numbers_h.numel() * 8 + (positions_h.numel() + (0 if eeq else q_h.numel())) * es
+        self.h2d = numbers_h.numel() * (8 if eeq else 1) + (positions_h.numel() + (0 if eeq else q_h.numel())) * es
         self.d2h = self.out_e.numel() * es + (self.out_g.numel() * es if wl["grad"] else 0)
 
     def call(self, n, p, qq):
@@ -365,7 +380,7 @@ class BatchBench:
         if not self.eeq:
             # public host-buffer API: pinned host tensors in, pinned host tensors out; the C ABI pipelines
             # H2D copy / kernels / D2H copy in chunks (d4b200_energy_host_*, d4b200_energy_gradient_host_*)
-            self.ctx.d4.dftd4_host(self.numbers_h, self.positions_h, 0.0, PBE0, q=self.q_h, model=self.model,
+            self.ctx.d4.dftd4_host(self.numbers_h8, self.positions_h, 0.0, PBE0, q=self.q_h, model=self.model,
                                    device=dev, out=self.out_e, with_gradient=wl["grad"], out_gradient=self.out_g)
             return
         n = self.numbers_h.to(dev, non_blocking=True)
@@ -394,7 +409,10 @@ class BatchBench:
             "pair_terms_per_s": npair / sec, "triple_terms_per_s": ntrip / sec,
             "algorithmic_tflops": nflop / sec / 1e12,
             "e2e": {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(self.h2d),
-                    "d2h_bytes_per_step": int(self.d2h), "ms_per_step": e2e_sec * 1e3},
+                    "d2h_bytes_per_step": int(self.d2h), "ms_per_step": e2e_sec * 1e3,
+                    "api": "q=None: dftd4() on tensors copied from pinned host memory" if self.eeq else
+                           "tad_dftd4_b200.dftd4_host (C ABI d4b200_energy_host_z_*): pinned host tensors in and out, "
+                           "atomic numbers as uint8"},
             "gpu_launches": int(launches),
         }  # fmt: skip
 
@@ -595,7 +613,7 @@ def run_b200(args, rank, world, local_rank):
                     "data": "synthetic", "config": {"workload": wl["name"], "atoms": rec["atoms"],
                                                      "parallelism": f"row-block x{world}, NCCL all-reduces"},
                     "e2e": None, "gpu_launches": None, "cpu_baseline": None, **rec}  # fmt: skip
-            print(json.dumps(line), flush=True)
+            emit(line)
         return ctx
 
     head = BatchBench(ctx, key, args.dtype, batches[key], eeq=args.eeq)
@@ -657,7 +675,7 @@ def run_b200(args, rank, world, local_rank):
             "c4": c4,
             "native_library": str(Path(ctx.lib._name).resolve().relative_to(ROOT)) if hasattr(ctx.lib, "_name") else None,
         }  # fmt: skip
-        print(json.dumps(line), flush=True)
+        emit(line)
     return ctx
 
 
@@ -676,9 +694,12 @@ def main():
                     help="default q=None path: EEQ charges on device inside the step (and on the autograd tape)")
     ap.add_argument("--nmol", type=int, default=0, help="c4: number of water molecules (default 6667)")
     args = ap.parse_args()
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 (NCCL's
+    # version banner at communicator creation, ...) is routed to stderr for the whole run
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -49,6 +49,8 @@ extern "C" {
 #define D4B200_EPARAM (-3)      /* a1/a2 missing (NaN) etc. */
 #define D4B200_ETABLE (-4)      /* table blob has the wrong size */
 #define D4B200_EARCH (-5)       /* device is not sm_100 */
+#define D4B200_ENUMBER (-6)     /* host-buffer entries: atomic number outside 1..103 */
+#define D4B200_ETOOLARGE (-7)   /* host-buffer entries: structure beyond the small-family kernels */
 
 /* device-side status bits returned by d4b200_status() */
 #define D4B200_STATUS_BAD_NUMBER 1 /* atomic number outside 1..103 */
@@ -124,6 +126,23 @@ int d4b200_energy_gradient_host_f64(d4b200_tables_t tables, const d4b200_params*
                                     const int64_t* numbers_host, const double* positions_host,
                                     const double* q_host, double* energy_host, double* grad_host,
                                     double* gradq_host, int chunks);
+/* Host-buffer entry with NARROW atomic numbers: ``numbers_host`` holds ``numbers_itemsize``-byte integers
+ * (8 = int64 as everywhere else, 4 = int32, 1 = uint8 -- every element fits one byte).  The array is
+ * uploaded as it is (the caller keeps it narrow; there is no host-side conversion pass) and widened on
+ * the device behind the copy: 1 instead of 8 of the 44 / 76 compulsory bytes per atom.
+ * ``grad_host`` NULL = energy only, else the fused energy+gradient kernels as
+ * d4b200_energy_gradient_host_*.  Like the other host entries the call fails with D4B200_ENUMBER /
+ * D4B200_ETOOLARGE when a kernel flagged its input; ``status_out`` (optional) receives the raw
+ * D4B200_STATUS_* bits.  Replaces: the padded ``numbers`` tensor of ``tad_dftd4.dftd4``
+ * (disp.py:44-146 of the reference) when it lives on the host. */
+int d4b200_energy_host_z_f64(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                             const void* numbers_host, int numbers_itemsize, const double* positions_host,
+                             const double* q_host, double* energy_host, double* grad_host,
+                             double* gradq_host, int chunks, int* status_out);
+int d4b200_energy_host_z_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
+                             const void* numbers_host, int numbers_itemsize, const float* positions_host,
+                             const float* q_host, float* energy_host, float* grad_host, float* gradq_host,
+                             int chunks, int* status_out);
 int d4b200_energy_gradient_host_f32(d4b200_tables_t tables, const d4b200_params* par, int nbatch, int nat,
                                     const int64_t* numbers_host, const float* positions_host,
                                     const float* q_host, float* energy_host, float* grad_host,

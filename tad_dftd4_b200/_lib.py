@@ -42,6 +42,8 @@ _SIGS = {
     "d4b200_energy_host_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_int]),
     "d4b200_energy_gradient_host_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int]),
     "d4b200_energy_gradient_host_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int]),
+    "d4b200_energy_host_z_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, C.c_int, C.POINTER(C.c_int)]),
+    "d4b200_energy_host_z_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, C.c_int, C.POINTER(C.c_int)]),
     "d4b200_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_energy_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),

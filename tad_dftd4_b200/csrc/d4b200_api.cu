@@ -355,11 +355,24 @@ int run_small(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
 // ``energy_host`` is complete.
 // GRAD: the fused energy + gradient kernels (d(sum E)/d positions, optionally d(sum E)/dq) run
 // per chunk and the gradient planes travel back with the energies.
+// atomic numbers that travelled as 1- or 4-byte integers: widen on the device (behind the copy)
+template <typename Z>
+__global__ void k_widen(const Z* __restrict__ src, int64_t* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (int64_t)src[i];
+}
+
+// ``zsize``: bytes per atomic number in the caller's host array (8 = int64, 4 = int32, 1 = uint8).
+// Narrow arrays are uploaded as they are -- one eighth of the bytes for uint8, no host-side pass --
+// and widened by a small kernel on the chunk's stream.  ``status_out`` (optional) receives the OR of
+// the kernels' status words of all chunks (D4B200_STATUS_*).
 template <typename T, bool GRAD>
 static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatch, int nat,
-                           const int64_t* numbers, const T* pos, const T* q, T* energy, int chunks,
-                           T* grad = nullptr, T* gradq = nullptr) {
+                           const void* numbers_any, int zsize, const T* pos, const T* q, T* energy, int chunks,
+                           T* grad = nullptr, T* gradq = nullptr, int* status_out = nullptr) {
+  const unsigned char* numbers = reinterpret_cast<const unsigned char*>(numbers_any);
   if (!h || !par || !numbers || !pos || !q || !energy || nbatch < 0 || nat < 0) return D4B200_EINVAL;
+  if (zsize != 8 && zsize != 4 && zsize != 1) return D4B200_EINVAL;
   if (GRAD && !grad) return D4B200_EINVAL;
   if (nbatch == 0 || nat == 0) return 0;
   int prev_dev = 0;
@@ -367,6 +380,7 @@ static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatc
   cudaSetDevice(h->device);
   if (chunks <= 0) chunks = nbatch >= 2048 ? 4 : nbatch >= 512 ? (GRAD ? 4 : 2) : 1;
   if (chunks > nbatch) chunks = nbatch;
+  if (chunks > D4_HOST_STATUS) chunks = D4_HOST_STATUS;
   const int cb = (nbatch + chunks - 1) / chunks;  // structures per chunk
   const size_t rows = (size_t)cb * nat;
   const size_t off_pos = align_up(rows * sizeof(int64_t), 256);
@@ -374,10 +388,13 @@ static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatc
   const size_t off_e = off_q + align_up(rows * sizeof(T), 256);
   const size_t off_g = off_e + align_up(rows * sizeof(T), 256);
   const size_t off_gq = off_g + (GRAD ? align_up(rows * 3 * sizeof(T), 256) : 0);
-  const size_t off_ws = off_gq + (GRAD ? align_up(rows * sizeof(T), 256) : 0);
+  const size_t off_zn = off_gq + (GRAD ? align_up(rows * sizeof(T), 256) : 0);  // narrow numbers as uploaded
+  const size_t off_ws = off_zn + (zsize != 8 ? align_up(rows * zsize, 256) : 0);
   const size_t ws_bytes = d4b200_workspace_bytes(cb, nat);
   const size_t need = off_ws + ws_bytes;
   cudaError_t e = cudaSuccess;
+  if (!h->hstatus) e = cudaHostAlloc(&h->hstatus, sizeof(int) * D4_HOST_STATUS, cudaHostAllocDefault);
+
   if (!h->hcopy) e = cudaStreamCreateWithFlags(&h->hcopy, cudaStreamNonBlocking);
   for (int s = 0; s < D4_HOST_SLOTS && s < chunks && e == cudaSuccess; ++s) {
     if (!h->hstream[s]) {
@@ -405,18 +422,27 @@ static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatc
     // all uploads share one stream so that they reach the device in chunk order at full
     // link bandwidth; the slot's stream picks up when its chunk has landed
     if (c >= D4_HOST_SLOTS) cudaStreamWaitEvent(h->hcopy, h->hev_done[s], 0);
-    cudaMemcpyAsync(d, numbers + o, r * sizeof(int64_t), cudaMemcpyHostToDevice, h->hcopy);
+    cudaMemcpyAsync(zsize == 8 ? d : d + off_zn, numbers + o * zsize, r * zsize, cudaMemcpyHostToDevice, h->hcopy);
     cudaMemcpyAsync(d + off_pos, pos + 3 * o, r * 3 * sizeof(T), cudaMemcpyHostToDevice, h->hcopy);
     cudaMemcpyAsync(d + off_q, q + o, r * sizeof(T), cudaMemcpyHostToDevice, h->hcopy);
     cudaEventRecord(h->hev_in[s], h->hcopy);
     cudaStreamWaitEvent(st, h->hev_in[s], 0);
+    if (zsize != 8) {
+      const unsigned wg = (unsigned)((r + 255) / 256 < 1184 ? (r + 255) / 256 : 1184);
+      if (zsize == 4)
+        k_widen<int32_t><<<wg, 256, 0, st>>>(reinterpret_cast<const int32_t*>(d + off_zn), reinterpret_cast<int64_t*>(d), r);
+      else
+        k_widen<uint8_t><<<wg, 256, 0, st>>>(d + off_zn, reinterpret_cast<int64_t*>(d), r);
+    }
     rc = run_small<T, GRAD>(h, par, nb, nat, reinterpret_cast<const int64_t*>(d),
                             reinterpret_cast<const T*>(d + off_pos), reinterpret_cast<const T*>(d + off_q),
                             nullptr, reinterpret_cast<T*>(d + off_e), nullptr,
                             GRAD ? reinterpret_cast<T*>(d + off_g) : nullptr,
                             GRAD && gradq ? reinterpret_cast<T*>(d + off_gq) : nullptr, d + off_ws, ws_bytes,
                             st, nullptr, nullptr, 1 + s);
-    launches += g_launches;
+    launches += g_launches + (zsize != 8 ? 1 : 0);
+    // status word of the chunk (first int of its workspace, see d4b200_status) -> pinned host slot
+    cudaMemcpyAsync(h->hstatus + c, d + off_ws, sizeof(int), cudaMemcpyDeviceToHost, st);
     e = cudaMemcpyAsync(energy + o, d + off_e, r * sizeof(T), cudaMemcpyDeviceToHost, st);
     if (GRAD) {
       cudaMemcpyAsync(grad + 3 * o, d + off_g, r * 3 * sizeof(T), cudaMemcpyDeviceToHost, st);
@@ -430,8 +456,19 @@ static int run_energy_host(d4b200_tables* h, const d4b200_params* par, int nbatc
       if (e == cudaSuccess) e = es;
     }
   g_launches = (int)launches;
+  g_total_launches += (zsize != 8 ? chunks : 0);
+  int bits = 0;
+  if (rc == 0 && e == cudaSuccess)
+    for (int c = 0; c < chunks; ++c) bits |= h->hstatus[c];
+  if (status_out) *status_out = bits;
   cudaSetDevice(prev_dev);
-  return rc != 0 ? rc : (e == cudaSuccess ? 0 : (int)e);
+  if (rc != 0) return rc;
+  if (e != cudaSuccess) return (int)e;
+  // an atomic number outside 1..103 / a structure beyond the kernels' limit is an error of the call
+  // (the device entry points report it through d4b200_status)
+  if (bits & D4B200_STATUS_BAD_NUMBER) return D4B200_ENUMBER;
+  if (bits & D4B200_STATUS_TOO_LARGE) return D4B200_ETOOLARGE;
+  return 0;
 }
 
 // (cn, C6, alpha) of tad_dftd4.get_properties (disp.py:149-197); the energy kernel stops
@@ -459,6 +496,8 @@ const char* d4b200_error_string(int code) {
     case D4B200_EPARAM: return "damping parameters a1/a2 missing";
     case D4B200_ETABLE: return "table blob has the wrong size";
     case D4B200_EARCH: return "device is not sm_100 (B200)";
+    case D4B200_ENUMBER: return "numbers contains an atomic number outside 1..103 (0 = padding)";
+    case D4B200_ETOOLARGE: return "a structure is larger than the one-CTA-per-structure kernels support";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
   }
 }
@@ -543,6 +582,7 @@ int d4b200_tables_destroy(d4b200_tables_t h) {
   }
   cudaFree(h->phase_dev);
   cudaFree(h->pij);
+  if (h->hstatus) cudaFreeHost(h->hstatus);
   if (h->hcopy) cudaStreamDestroy(h->hcopy);
   for (int s = 0; s < D4_HOST_SLOTS; ++s) {
     if (h->hbuf[s]) cudaFree(h->hbuf[s]);
@@ -583,25 +623,45 @@ int d4b200_energy_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, i
 int d4b200_energy_host_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                            const int64_t* numbers_host, const double* pos_host,
                            const double* q_host, double* energy_host, int chunks) {
-  return run_energy_host<double, false>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
+  return run_energy_host<double, false>(t, par, nbatch, nat, numbers_host, 8, pos_host, q_host, energy_host, chunks);
 }
 int d4b200_energy_host_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                            const int64_t* numbers_host, const float* pos_host, const float* q_host,
                            float* energy_host, int chunks) {
-  return run_energy_host<float, false>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks);
+  return run_energy_host<float, false>(t, par, nbatch, nat, numbers_host, 8, pos_host, q_host, energy_host, chunks);
 }
 int d4b200_energy_gradient_host_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                                     const int64_t* numbers_host, const double* pos_host,
                                     const double* q_host, double* energy_host, double* grad_host,
                                     double* gradq_host, int chunks) {
-  return run_energy_host<double, true>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks,
+  return run_energy_host<double, true>(t, par, nbatch, nat, numbers_host, 8, pos_host, q_host, energy_host, chunks,
                                        grad_host, gradq_host);
 }
 int d4b200_energy_gradient_host_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                                     const int64_t* numbers_host, const float* pos_host, const float* q_host,
                                     float* energy_host, float* grad_host, float* gradq_host, int chunks) {
-  return run_energy_host<float, true>(t, par, nbatch, nat, numbers_host, pos_host, q_host, energy_host, chunks,
+  return run_energy_host<float, true>(t, par, nbatch, nat, numbers_host, 8, pos_host, q_host, energy_host, chunks,
                                       grad_host, gradq_host);
+}
+int d4b200_energy_host_z_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                             const void* numbers_host, int numbers_itemsize, const double* pos_host,
+                             const double* q_host, double* energy_host, double* grad_host, double* gradq_host,
+                             int chunks, int* status_out) {
+  if (grad_host)
+    return run_energy_host<double, true>(t, par, nbatch, nat, numbers_host, numbers_itemsize, pos_host, q_host,
+                                         energy_host, chunks, grad_host, gradq_host, status_out);
+  return run_energy_host<double, false>(t, par, nbatch, nat, numbers_host, numbers_itemsize, pos_host, q_host,
+                                        energy_host, chunks, nullptr, nullptr, status_out);
+}
+int d4b200_energy_host_z_f32(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
+                             const void* numbers_host, int numbers_itemsize, const float* pos_host,
+                             const float* q_host, float* energy_host, float* grad_host, float* gradq_host,
+                             int chunks, int* status_out) {
+  if (grad_host)
+    return run_energy_host<float, true>(t, par, nbatch, nat, numbers_host, numbers_itemsize, pos_host, q_host,
+                                        energy_host, chunks, grad_host, gradq_host, status_out);
+  return run_energy_host<float, false>(t, par, nbatch, nat, numbers_host, numbers_itemsize, pos_host, q_host,
+                                       energy_host, chunks, nullptr, nullptr, status_out);
 }
 int d4b200_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nbatch, int nat,
                         const int64_t* numbers, const double* pos, const double* q,

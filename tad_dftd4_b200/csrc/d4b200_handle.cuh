@@ -9,6 +9,7 @@
 using namespace d4b200;
 
 #define D4_HOST_SLOTS 4
+#define D4_HOST_STATUS 64  // chunks per host-buffer call whose status words are read back
 
 struct d4b200_tables {
   int device;
@@ -43,6 +44,7 @@ struct d4b200_tables {
   size_t hbuf_bytes[D4_HOST_SLOTS];
   cudaStream_t hcopy;  // all H2D copies, in chunk order
   cudaEvent_t hev_in[D4_HOST_SLOTS], hev_done[D4_HOST_SLOTS];
+  int* hstatus;  // pinned host: status word of every chunk of the last host-buffer call
 };
 
 // upper bound of resident CTAs per SM we ever launch for a class

@@ -207,10 +207,25 @@ class _D4Function(torch.autograd.Function):
         return energy
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, gout: Tensor):
         positions, q, numbers = ctx.saved_tensors
         need_pos, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if torch.is_grad_enabled() and (need_pos or need_q):
+            # backward under create_graph=True (Hessians, gradgradcheck, force matching): the VJP
+            # itself has to stay on the tape -> second-order node, see _D4Vjp
+            if ctx.ptens and any(ctx.needs_input_grad[5 + k] for k in range(len(ctx.ptens))):
+                raise NotImplementedError(
+                    "second derivatives are provided with respect to positions and charges; detach the "
+                    "damping parameters (or differentiate them to first order only)"
+                )
+            gpos, gq = _D4Vjp.apply(gout, positions, q, numbers, ctx.par, ctx.engine)
+            return (gpos if need_pos else None, gq if need_q else None, None, None, None,
+                    *((None,) * len(ctx.ptens)))  # fmt: skip
+        with torch.no_grad():
+            return _D4Function._first_order(ctx, gout, positions, q, numbers, need_pos, need_q)
+
+    @staticmethod
+    def _first_order(ctx, gout, positions, q, numbers, need_pos, need_q):
         gpar: tuple = ()
         if ctx.ptens:
             want = [ctx.needs_input_grad[5 + k] for k in range(len(ctx.ptens))]
@@ -232,6 +247,66 @@ class _D4Function(torch.autograd.Function):
             ctx.par, numbers, positions, q, gout.contiguous(), need_pos, need_q
         )
         return (gpos, gq, None, None, None, *gpar)
+
+
+# Central-difference step of the second-order path (Bohr for positions, e for charges; applied to
+# the direction normalised to unit maximum component) and its fourth-order stencil
+_FD_STEP = 2.0e-3
+_FD_STENCIL = ((1.0, 8.0 / 12.0), (-1.0, -8.0 / 12.0), (2.0, -1.0 / 12.0), (-2.0, 1.0 / 12.0))
+
+
+def _fd_direction(*parts: Tensor | None) -> Tensor:
+    """Per-structure step ``t`` (shape [B]) such that the largest component of ``t * direction`` is
+    ``_FD_STEP``; structures whose direction vanishes get ``t = 1`` (their derivative is zero)."""
+    amax = None
+    for w in parts:
+        if w is None:
+            continue
+        a = w.detach().abs().reshape(w.shape[0], -1).amax(-1)
+        amax = a if amax is None else torch.maximum(amax, a)
+    return torch.where(amax > 0, _FD_STEP / amax.clamp_min(1e-300), torch.ones_like(amax))
+
+
+class _D4Vjp(torch.autograd.Function):
+    """``(dL/dpositions, dL/dq)`` for ``L = sum gout * E`` -- the analytic VJP kernels -- as a node that
+    can be differentiated once more.
+
+    Second derivatives are SEMI-NUMERICAL, the standard route for dispersion Hessians: with the
+    upstream direction ``w = (w_pos, w_q)`` the node needs ``d/dx (g . w) = D_w g`` (the Hessian is
+    symmetric), the directional derivative of the ANALYTIC gradient, and ``d/dgout (g . w) = D_w E``.
+    Both are fourth-order central differences of the kernels along ``w`` (four gradient and four
+    energy launches, step 2e-3 Bohr on the largest component: truncation ~1e-11 relative,
+    round-off ~1e-13), far inside the 1e-7 the reference's Hessian tests ask for
+    (``test/test_grad/test_hessian.py:47``).  Everything stays on the CUDA kernels."""
+
+    @staticmethod
+    def forward(ctx, gout, positions, q, numbers, par, engine):
+        gpos, gq = engine.gradient(par, numbers, positions.detach(), q.detach(), gout.detach().contiguous(), True, True)
+        ctx.save_for_backward(gout, positions, q, numbers)
+        ctx.par, ctx.engine = par, engine
+        return gpos, gq
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, wpos, wq):
+        gout, positions, q, numbers = ctx.saved_tensors
+        par, engine = ctx.par, ctx.engine
+        t = _fd_direction(wpos, wq)
+        dpos = wpos * t[:, None, None] if wpos is not None else None
+        dq = wq * t[:, None] if wq is not None else None
+        g = gout.contiguous()
+        hpos = torch.zeros_like(positions)
+        hq = torch.zeros_like(q)
+        de = torch.zeros_like(q)
+        for mult, coef in _FD_STENCIL:
+            x = positions + mult * dpos if dpos is not None else positions
+            y = q + mult * dq if dq is not None else q
+            gp, gqq = engine.gradient(par, numbers, x.contiguous(), y.contiguous(), g, True, True)
+            hpos += coef * gp
+            hq += coef * gqq
+            if ctx.needs_input_grad[0]:
+                de += coef * engine.energy(par, numbers, x.contiguous(), y.contiguous())[0]
+        return de / t[:, None], hpos / t[:, None, None], hq / t[:, None], None, None, None
 
 
 _PARAM_ORDER = ("s6", "s8", "s9", "s10", "a1", "a2", "alp")
@@ -566,28 +641,40 @@ def dftd4_host(
     nat = numbers.shape[-1]
     if nat > _small_limit(engine, positions.dtype, bool(with_gradient), model_id):
         raise NotImplementedError("dftd4_host handles batches of small structures; use dftd4 for large ones")
-    num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
+    # atomic numbers travel as the caller holds them: uint8 / int32 tensors are uploaded narrow and
+    # widened on the device (d4b200_energy_host_z_*); anything else goes as int64
+    if numbers.dtype in (torch.uint8, torch.int32, torch.int64):
+        num2 = numbers.reshape(-1, nat).contiguous()
+    else:
+        num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
     pos2 = positions.reshape(-1, nat, 3).contiguous()
     q2 = q.to(positions.dtype).reshape(-1, nat).contiguous()
-    if out is None:
-        out = torch.empty(num2.shape, dtype=positions.dtype, pin_memory=True)
-    f64 = positions.dtype == torch.float64
+
+    def _buffer(t, shape, what):
+        if t is None:
+            return torch.empty(shape, dtype=positions.dtype, pin_memory=True)
+        if (t.device.type != "cpu" or t.dtype != positions.dtype or t.numel() != int(np.prod(shape))
+                or not t.is_contiguous()):  # fmt: skip
+            raise ValueError(f"{what} must be a contiguous CPU tensor of dtype {positions.dtype} with "
+                             f"{int(np.prod(shape))} elements (got {tuple(t.shape)}, {t.dtype}, {t.device})")  # fmt: skip
+        return t
+
+    out = _buffer(out, num2.shape, "out")
     if with_gradient:
-        if out_gradient is None:
-            out_gradient = torch.empty(pos2.shape, dtype=positions.dtype, pin_memory=True)
-        fn = engine.lib.d4b200_energy_gradient_host_f64 if f64 else engine.lib.d4b200_energy_gradient_host_f32
-        _lib.check(
-            fn(engine.handle, C.byref(par), num2.shape[0], nat, num2.data_ptr(), pos2.data_ptr(),
-               q2.data_ptr(), out.data_ptr(), out_gradient.data_ptr(), None, int(chunks)),
-            "d4b200_energy_gradient_host",
-        )  # fmt: skip
+        out_gradient = _buffer(out_gradient, pos2.shape, "out_gradient")
+    f64 = positions.dtype == torch.float64
+    fn = engine.lib.d4b200_energy_host_z_f64 if f64 else engine.lib.d4b200_energy_host_z_f32
+    bits = C.c_int(0)
+    code = fn(engine.handle, C.byref(par), num2.shape[0], nat, num2.data_ptr(), num2.element_size(),
+              pos2.data_ptr(), q2.data_ptr(), out.data_ptr(),
+              out_gradient.data_ptr() if with_gradient else None, None, int(chunks), C.byref(bits))  # fmt: skip
+    if bits.value & 1:
+        raise ValueError("numbers contains an atomic number outside 1..103 (0 = padding).")
+    if bits.value & 2:
+        raise NotImplementedError("a structure is larger than the one-CTA-per-structure kernels support")
+    _lib.check(code, "d4b200_energy_host_z")
+    if with_gradient:
         return out.reshape(numbers.shape), out_gradient.reshape(positions.shape)
-    fn = engine.lib.d4b200_energy_host_f64 if f64 else engine.lib.d4b200_energy_host_f32
-    _lib.check(
-        fn(engine.handle, C.byref(par), num2.shape[0], nat, num2.data_ptr(), pos2.data_ptr(),
-           q2.data_ptr(), out.data_ptr(), int(chunks)),
-        "d4b200_energy_host",
-    )  # fmt: skip
     return out.reshape(numbers.shape)
 
 

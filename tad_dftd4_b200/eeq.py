@@ -105,14 +105,49 @@ class _EeqFunction(torch.autograd.Function):
         ctx.save_for_backward(positions, numbers, q)
         ctx.cutoff = cutoff
         ctx.engine = engine
+        ctx.charge = charge
         return q
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, gq: Tensor):
         positions, numbers, q = ctx.saved_tensors
-        gpos = ctx.engine.vjp(numbers, positions, ctx.cutoff, q, gq.contiguous())
+        if torch.is_grad_enabled():  # create_graph=True: keep the VJP on the tape (second derivatives)
+            return _EeqVjp.apply(gq, positions, numbers, q, ctx.charge, ctx.cutoff, ctx.engine), None, None, None, None
+        with torch.no_grad():
+            gpos = ctx.engine.vjp(numbers, positions, ctx.cutoff, q, gq.contiguous())
         return gpos, None, None, None, None
+
+
+class _EeqVjp(torch.autograd.Function):
+    """``dL/dpositions = J^T gq`` of the EEQ charges (analytic VJP kernel) as a node that can be
+    differentiated once more, semi-numerically like ``disp._D4Vjp``: along the upstream direction
+    ``w``, ``d/dx (gq^T J w) = D_w (J^T gq)`` and ``d/dgq (gq^T J w) = J w = D_w q`` are fourth-order
+    central differences of the VJP / charge kernels."""
+
+    @staticmethod
+    def forward(ctx, gq, positions, numbers, q, charge, cutoff, engine):
+        ctx.save_for_backward(gq, positions, numbers, charge)
+        ctx.cutoff, ctx.engine = cutoff, engine
+        return engine.vjp(numbers, positions.detach(), cutoff, q.detach(), gq.detach().contiguous())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, w):
+        from .disp import _FD_STENCIL, _fd_direction
+
+        gq, positions, numbers, charge = ctx.saved_tensors
+        engine, cutoff = ctx.engine, ctx.cutoff
+        t = _fd_direction(w)
+        d = w * t[:, None, None]
+        g = gq.contiguous()
+        hpos = torch.zeros_like(positions)
+        dq = torch.zeros_like(gq)
+        for mult, coef in _FD_STENCIL:
+            x = (positions + mult * d).contiguous()
+            qx = engine.charges(numbers, x, charge, cutoff)
+            dq += coef * qx
+            hpos += coef * engine.vjp(numbers, x, cutoff, qx, g)
+        return dq / t[:, None], hpos / t[:, None, None], None, None, None, None, None
 
 
 _TABLES: dict[tuple[str, torch.dtype], Tensor] = {}

@@ -259,3 +259,29 @@ def test_host_buffer_forces_entry_matches_device_entry(dtype, chunks, model):
         ref, gref = np.tile(case[f"energy_{key}"], (rep, 1)), np.tile(case[f"grad_{key}"], (rep, 1, 1))
         assert np.abs(e_host.numpy() - ref).max() / np.abs(ref).max() < E_RTOL64
         assert np.abs(g_host.numpy() - gref).max() < G_ATOL64
+
+
+def test_host_entry_narrow_numbers_and_status():
+    """dftd4_host: uint8 / int32 atomic numbers are uploaded narrow and give bitwise the int64 result;
+    a bad atomic number or a wrong output buffer raises (the host entries read the kernels' status)."""
+    import tad_dftd4_b200 as d4
+
+    numbers, positions, q = orc.organic_batch([12, 33, 7, 50, 20], seed=5)
+    param = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)
+    ref_e, ref_g = d4.dftd4_host(numbers, positions, 0.0, param, q=q, with_gradient=True)
+    for dt in (torch.uint8, torch.int32):
+        e, g = d4.dftd4_host(numbers.to(dt), positions, 0.0, param, q=q, with_gradient=True)
+        assert torch.equal(e, ref_e) and torch.equal(g, ref_g)
+        assert torch.equal(d4.dftd4_host(numbers.to(dt), positions, 0.0, param, q=q), d4.dftd4_host(numbers, positions, 0.0, param, q=q))
+    dev_e = d4.dftd4(numbers.cuda(), positions.cuda(), 0.0, param, q=q.cuda()).cpu()
+    assert torch.allclose(ref_e, dev_e, rtol=1e-13, atol=0)
+    bad = numbers.clone()
+    bad[1, 3] = 110
+    with pytest.raises(ValueError):
+        d4.dftd4_host(bad, positions, 0.0, param, q=q)
+    with pytest.raises(ValueError):
+        d4.dftd4_host(bad.to(torch.uint8), positions, 0.0, param, q=q, with_gradient=True)
+    with pytest.raises(ValueError):
+        d4.dftd4_host(numbers, positions, 0.0, param, q=q, out=torch.empty(3, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        d4.dftd4_host(numbers, positions, 0.0, param, q=q, out=torch.empty(numbers.shape, dtype=torch.float32))
