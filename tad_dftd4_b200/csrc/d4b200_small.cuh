@@ -25,6 +25,37 @@
 namespace d4b200 {
 
 
+// ---------------------------------------------------------------- bulk-async (TMA) staging
+// The inputs of a structure are three contiguous rows of the padded batch (numbers, positions,
+// charges).  A persistent CTA claims its NEXT structure one iteration early and has the TMA unit
+// copy the three rows into a region of shared memory that is dead at that point
+// (cp.async.bulk.shared::cluster.global, completion on an mbarrier), so that the compaction phase of
+// the next iteration reads shared memory instead of waiting on global loads.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ unsigned r16(size_t b) { return (unsigned)((b + 15) & ~size_t(15)); }
 
 // ---------------------------------------------------------------- math shims
 __device__ __forceinline__ double d4_erfc(double x) { return erfc(x); }
@@ -825,14 +856,87 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     tlast = now;                                                        \
   }
 
+  // ---- bulk-async staging of the next structure's input rows (see the helpers above) ----------
+  // misc[24] = next work item (-1: not claimed yet), misc[25] = its rows are being staged,
+  // misc[26] = the current item's rows are staged, misc[28..29] = the mbarrier
+  unsigned long long* const bar = reinterpret_cast<unsigned long long*>(misc + 28);
+  constexpr size_t abuf_used = GRAD ? 2 * NFREQ * AS : ((E2S ? CP : 0) + size_t(NW) * CAP + 3) / 4 * 4;
+  unsigned char* const stage = reinterpret_cast<unsigned char*>(Aq + abuf_used);  // gradient: Bq, B0
+  constexpr size_t stage_avail = D4S ? 0 : (size_t(GRAD ? 4 : 2) * NFREQ * AS - abuf_used) * sizeof(T);
+  const unsigned seg_p = r16((size_t)A.nat * 8 + 16);
+  const unsigned seg_q = seg_p + r16((size_t)A.nat * 3 * sizeof(T) + 16);
+  const unsigned seg_end = seg_q + r16((size_t)A.nat * sizeof(T) + 16);
+#ifdef D4_NO_STAGE  // A/B knob: plain global loads in the compaction phase
+  const bool use_stage = false;
+#else
+  const bool use_stage = !D4S && seg_end <= stage_avail;
+#endif
+  unsigned bar_parity = 0;
+  if (tid == 0) {
+    misc[24] = -1;
+    misc[25] = 0;
+    if (use_stage) mbar_init(bar, 1);
+  }
+  // claim the next work item and start the copy of its rows; called by thread 0 after a block barrier
+  // behind which the staging region is dead
+  auto prefetch_next = [&]() {
+    const int nxt = atomicAdd(&A.wk.queue[A.cls], 1);
+    int staged = 0;
+    if (use_stage && range_begin + nxt < range_end) {
+      const size_t o2 = (size_t)A.wk.order[range_begin + nxt] * A.nat, tot = (size_t)A.nbatch * A.nat;
+      const char* z0 = reinterpret_cast<const char*>(A.numbers + o2);
+      const char* p0 = reinterpret_cast<const char*>(A.pos + 3 * o2);
+      const char* q0 = reinterpret_cast<const char*>(A.q + o2);
+      const unsigned lz = (unsigned)((size_t)z0 & 15), lp = (unsigned)((size_t)p0 & 15), lq = (unsigned)((size_t)q0 & 15);
+      const unsigned bz = r16(lz + (size_t)A.nat * 8), bp = r16(lp + (size_t)A.nat * 3 * sizeof(T)),
+                     bq = r16(lq + (size_t)A.nat * sizeof(T));
+      // the 16-byte aligned windows must stay inside the arrays (first / last rows of unaligned views)
+      const bool inside = z0 - lz >= reinterpret_cast<const char*>(A.numbers) &&
+                          z0 - lz + bz <= reinterpret_cast<const char*>(A.numbers + tot) &&
+                          p0 - lp >= reinterpret_cast<const char*>(A.pos) &&
+                          p0 - lp + bp <= reinterpret_cast<const char*>(A.pos + 3 * tot) &&
+                          q0 - lq >= reinterpret_cast<const char*>(A.q) &&
+                          q0 - lq + bq <= reinterpret_cast<const char*>(A.q + tot);
+      if (inside) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy accesses of the region are done
+        mbar_expect_tx(bar, bz + bp + bq);
+        bulk_g2s(stage, z0 - lz, bz, bar);
+        bulk_g2s(stage + seg_p, p0 - lp, bp, bar);
+        bulk_g2s(stage + seg_q, q0 - lq, bq, bar);
+        staged = 1;
+      }
+    }
+    misc[24] = nxt;
+    misc[25] = staged;
+  };
+
   while (true) {
     __syncthreads();  // previous structure fully written, misc[] reusable
-    if (tid == 0) misc[0] = atomicAdd(&A.wk.queue[A.cls], 1);
+    if (tid == 0) {
+      if (misc[24] < 0) {  // nothing claimed ahead (first iteration, properties mode)
+        misc[24] = atomicAdd(&A.wk.queue[A.cls], 1);
+        misc[25] = 0;
+      }
+      misc[0] = misc[24];
+      misc[26] = misc[25];
+      misc[24] = -1;
+      misc[25] = 0;
+    }
     __syncthreads();
     const int item = range_begin + misc[0];
     if (item >= range_end) break;
     const int b = A.wk.order[item];
-    const int64_t* zrow = A.numbers + (size_t)b * A.nat;
+    const bool staged = misc[26] != 0;
+    if (staged) {  // the rows of this structure were copied into shared memory during the previous iteration
+      mbar_wait(bar, bar_parity);
+      bar_parity ^= 1u;
+    }
+    const int64_t* const zrow_g = A.numbers + (size_t)b * A.nat;
+    const T* const prow_g = A.pos + (size_t)b * A.nat * 3;
+    const T* const qrow_g = A.q + (size_t)b * A.nat;
+    const int64_t* const zrow = staged ? reinterpret_cast<const int64_t*>(stage + ((size_t)zrow_g & 15)) : zrow_g;
+    const T* const prow = staged ? reinterpret_cast<const T*>(stage + seg_p + ((size_t)prow_g & 15)) : prow_g;
+    const T* const qrow = staged ? reinterpret_cast<const T*>(stage + seg_q + ((size_t)qrow_g & 15)) : qrow_g;
 
     // ---- phase 0: compact real atoms (numbers != 0), zero padded outputs ----
     if (tid < 32) {
@@ -891,10 +995,10 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     for (int i = tid; i < n; i += NT) {
       const size_t o = (size_t)b * A.nat + idx[i];
       const int z = zs[i];
-      ATOM(AT_X)[i] = A.pos[3 * o];
-      ATOM(AT_Y)[i] = A.pos[3 * o + 1];
-      ATOM(AT_Z)[i] = A.pos[3 * o + 2];
-      if constexpr (GRAD || D4S) ATOM(AT_Q)[i] = A.q[o];
+      ATOM(AT_X)[i] = prow[3 * idx[i]];
+      ATOM(AT_Y)[i] = prow[3 * idx[i] + 1];
+      ATOM(AT_Z)[i] = prow[3 * idx[i] + 2];
+      if constexpr (GRAD || D4S) ATOM(AT_Q)[i] = qrow[idx[i]];
       ATOM(AT_RCOV)[i] = tab.rcov[z];
       ATOM(AT_SQ)[i] = tab.sqrt_r4r2[z];
       if (GRAD) ATOM(AT_G)[i] = A.gin ? A.gin[o] : T(1);
@@ -977,7 +1081,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           z0[h] = tab.zeta0[za[h]];
         }
         const double gam = tab.gamgc[z], zeff = tab.zeff[z];
-        const double qat = row ? (double)A.q[(size_t)b * A.nat + idx[i]] : 0.0;
+        const double qat = row ? (double)qrow[idx[i]] : 0.0;
         T c0 = T(0), c1 = T(0);
         if (row) {
           const T* r = pu + i * (i - 1) / 2;
@@ -1095,7 +1199,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       double qat = 0.0;
       if (i < n) {
         if constexpr (GRAD || D4S) qat = (double)ATOM(AT_Q)[i];
-        else qat = (double)A.q[(size_t)b * A.nat + idx[i]];
+        else qat = (double)qrow[idx[i]];
       }
       const double d = (double)cn_row - rcn;
       const double arg = (rc > 0 && !D4S) ? P.wf * d * d : 1e300;
@@ -1371,6 +1475,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       __syncthreads();
       PHASE(5);
       open = misc[2] != 0;
+      if (tid == 0) prefetch_next();  // the A vectors are dead: their tail receives the next structure's rows
     } else {
     // ---- phase 5 (gradient kernel): ATM pair stash --------------------------
     if constexpr (sizeof(T) == 8) {  // C6(q = 0) of all pairs on the tensor path -> plane `pP`
@@ -1847,6 +1952,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
       __syncthreads();
       PHASE(12);
+      if (tid == 0) prefetch_next();  // the B vectors are dead: they receive the next structure's rows
       }  // D4 / D4S
       // phase 10: CN chain rule, d cn/d r = -den kcn/(r0 sqrt(pi)) exp(-x^2)
       for (int p = tid; p < np; p += NT) {
