@@ -1876,31 +1876,45 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         //   A[r][c] = coef(i0 + r, j0 + c), B[c][r] = A_{j0 + c}[w0 + r], r = lane / 4, c = lane % 4
         const int nrb = (n + 7) >> 3;
         const int r = lane >> 2, c = lane & 3;
-        for (int tile = warp; tile < nrb * 6; tile += NW) {
-          const int fl = tile & 1, rest = tile >> 1;
-          const int wb = rest % 3, rb = rest / 3;
-          const T* const coef = fl ? pP : pa;
-          const T* const Av = fl ? A0 : Aq;
+        // both flavours of a tile in the same warp: two independent accumulator chains share the index
+        // arithmetic (the chain of dependent DMMAs is latency bound on its own)
+        for (int tile = warp; tile < nrb * 3; tile += NW) {
+          const int wb = tile % 3, rb = tile / 3;
           const int i = rb * 8 + r, ti = i * (i - 1) / 2;
           const int w = wb * 8 + r;
           const bool iok = i < n, wok = w < NFREQ;
-          double d0 = 0.0, d1 = 0.0;
+          double q0 = 0.0, q1 = 0.0, z0 = 0.0, z1 = 0.0;
           for (int j0 = 0; j0 < n; j0 += 4) {
             const int j = j0 + c;
             const bool jok = j < n;
-            double av = 0.0, bv = 0.0;
-            if (iok && jok && j != i) av = coef[j < i ? ti + j : j * (j - 1) / 2 + i];
-            if (wok && jok) bv = Av[w * AS + j];
+            double aq = 0.0, a0 = 0.0, bq = 0.0, b0 = 0.0;
+            if (iok && jok && j != i) {
+              const int pp = j < i ? ti + j : j * (j - 1) / 2 + i;
+              aq = pa[pp];
+              a0 = pP[pp];
+            }
+            if (wok && jok) {
+              bq = Aq[w * AS + j];
+              b0 = A0[w * AS + j];
+            }
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(d0), "+d"(d1)
-                         : "d"(av), "d"(bv));
+                         : "+d"(q0), "+d"(q1)
+                         : "d"(aq), "d"(bq));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(z0), "+d"(z1)
+                         : "d"(a0), "d"(b0));
           }
           // accumulator fragment: row r (atom), columns 2c, 2c+1 (frequency)
-          T* const Bv = fl ? B0 : Bq;
           const int wo = wb * 8 + 2 * c;
           if (iok) {
-            if (wo < NFREQ) Bv[wo * AS + i] = d0;
-            if (wo + 1 < NFREQ) Bv[(wo + 1) * AS + i] = d1;
+            if (wo < NFREQ) {
+              Bq[wo * AS + i] = q0;
+              B0[wo * AS + i] = z0;
+            }
+            if (wo + 1 < NFREQ) {
+              Bq[(wo + 1) * AS + i] = q1;
+              B0[(wo + 1) * AS + i] = z1;
+            }
           }
         }
       } else {
@@ -1984,34 +1998,42 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       }
       __syncthreads();
       PHASE(13);
-      // phase 11: gather forces (one warp per atom)
-      for (int i = warp; i < n; i += NW) {
-        const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
-        T fx = T(0), fy = T(0), fz = T(0), es = T(0);
-        const int ti = i * (i - 1) / 2;
+      // phase 11: gather forces, eight lanes per atom (four atoms per warp: all warps busy for a few
+      // short passes instead of a long chain per atom), fixed summation order
+      {
         const bool want_e = A.energy != nullptr;
-        for (int j = lane; j < n; j += 32) {
-          if (j == i) continue;
-          const int pp = j < i ? ti + j : j * (j - 1) / 2 + i;
-          const T c = pu[pp];
-          fx += c * (xi - ATOM(AT_X)[j]);
-          fy += c * (yi - ATOM(AT_Y)[j]);
-          fz += c * (zi - ATOM(AT_Z)[j]);
-          if (want_e) es += j < i ? pa[pp] : pP[pp];
-        }
-        fx = warp_sum(fx);
-        fy = warp_sum(fy);
-        fz = warp_sum(fz);
-        if (want_e) es = warp_sum(es);
-        if (lane == 0) {
-          const size_t o = (size_t)b * A.nat + idx[i];
-          if (want_e) A.energy[o] = es;
-          if (A.grad) {
-            A.grad[3 * o] = fx;
-            A.grad[3 * o + 1] = fy;
-            A.grad[3 * o + 2] = fz;
+        D4_ROWS8(i, sub) {
+          T fx = T(0), fy = T(0), fz = T(0), es = T(0);
+          if (i < n) {
+            const T xi = ATOM(AT_X)[i], yi = ATOM(AT_Y)[i], zi = ATOM(AT_Z)[i];
+            const int ti = i * (i - 1) / 2;
+            for (int j = sub; j < n; j += 8) {
+              if (j == i) continue;
+              const int pp = j < i ? ti + j : j * (j - 1) / 2 + i;
+              const T c = pu[pp];
+              fx += c * (xi - ATOM(AT_X)[j]);
+              fy += c * (yi - ATOM(AT_Y)[j]);
+              fz += c * (zi - ATOM(AT_Z)[j]);
+              if (want_e) es += j < i ? pa[pp] : pP[pp];
+            }
           }
-          if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            es += __shfl_xor_sync(0xffffffffu, es, o);
+          }
+          if (sub == 0 && i < n) {
+            const size_t o = (size_t)b * A.nat + idx[i];
+            if (want_e) A.energy[o] = es;
+            if (A.grad) {
+              A.grad[3 * o] = fx;
+              A.grad[3 * o + 1] = fy;
+              A.grad[3 * o + 2] = fz;
+            }
+            if (A.gradq) A.gradq[o] = ATOM(AT_DQ)[i];
+          }
         }
       }
       __syncthreads();

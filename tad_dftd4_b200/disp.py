@@ -74,7 +74,7 @@ class _Engine:
         self.ga, self.gc = float(ga), float(gc)
         self.limits: dict[tuple[bool, bool, int], int] = {}
         self.device = torch.device("cuda", index)
-        self._ws: Tensor | None = None
+        self._ws_by_stream: dict[int, Tensor] = {}
 
     @classmethod
     def get(cls, device: torch.device, ga: float, gc: float) -> "_Engine":
@@ -86,16 +86,24 @@ class _Engine:
         return eng
 
     def large_workspace(self, need: int) -> Tensor:
-        ws = getattr(self, "_ws_large", None)
+        key = ("large", torch.cuda.current_stream(self.device).cuda_stream)
+        ws = self._ws_by_stream.get(key)
         if ws is None or ws.numel() < need:
-            self._ws_large = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            ws = self._ws_by_stream[key] = torch.empty(need, dtype=torch.uint8, device=self.device)
         return ws
 
     def workspace(self, nbatch: int, nat: int) -> Tensor:
+        """Workspace of the CURRENT CUDA stream: calls issued on different streams (or from different
+        host threads on their own streams) never share the planning arrays, work queues and scratch
+        planes a running call still reads."""
         need = int(self.lib.d4b200_workspace_bytes(nbatch, nat))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws_by_stream.get(key)
+        if ws is None or ws.numel() < need:
+            if len(self._ws_by_stream) > 16:  # streams come and go: do not grow without bound
+                self._ws_by_stream.clear()
+            ws = self._ws_by_stream[key] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
 
     def _status(self, ws: Tensor, stream: int) -> None:
         bits = C.c_int(0)
@@ -697,6 +705,13 @@ def get_properties(
         )
     if positions.device.type != "cuda":
         raise RuntimeError("tad_dftd4_b200 runs on B200 GPUs only (no CPU fallback).")
+    if torch.is_grad_enabled() and (positions.requires_grad or (q is not None and q.requires_grad)):
+        # the reference's get_properties stays on the autograd tape (disp.py:149-197); these kernels
+        # return plain values: refuse rather than hand back silently detached tensors
+        raise NotImplementedError(
+            "get_properties returns non-differentiable values (cn, C6, alpha); call it under "
+            "torch.no_grad() or with detached inputs, and differentiate dftd4() instead"
+        )
     if q is None:
         q = _eeq_charges(numbers, positions, 0.0 if charge is None else charge, cutoff)
     if numbers.shape != q.shape:

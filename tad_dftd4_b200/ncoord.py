@@ -21,5 +21,7 @@ def cn_d4(numbers: torch.Tensor, positions: torch.Tensor, **kwargs) -> torch.Ten
         raise NotImplementedError("only the default cn_d4 (erf_count, default radii) is accelerated")
     from .disp import get_properties
 
+    # plain values (not on the autograd tape): the fused kernels differentiate the coordination number
+    # themselves; a term that receives this tensor through Disp.calculate ignores it (dispersion.py)
     q = torch.zeros(numbers.shape, dtype=positions.dtype, device=positions.device)
-    return get_properties(numbers, positions, q=q)[0]
+    return get_properties(numbers, positions.detach(), q=q)[0]

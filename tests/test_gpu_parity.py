@@ -285,3 +285,31 @@ def test_host_entry_narrow_numbers_and_status():
         d4.dftd4_host(numbers, positions, 0.0, param, q=q, out=torch.empty(3, dtype=torch.float64))
     with pytest.raises(ValueError):
         d4.dftd4_host(numbers, positions, 0.0, param, q=q, out=torch.empty(numbers.shape, dtype=torch.float32))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_unaligned_views_and_odd_width_are_bitwise_consistent(dtype):
+    """Odd padded width (rows of odd structures are only 8-byte aligned) and views that start inside an
+    allocation: the bulk-async staging windows of the persistent kernels must not change a single bit,
+    whichever structures a CTA happens to stage or to load directly."""
+    import tad_dftd4_b200 as d4
+
+    dev = torch.device("cuda:0")
+    numbers, positions, q = orc.organic_batch([12, 33, 7, 21, 5, 30, 33, 2, 19] * 30, seed=6)
+    n, p, qq = numbers.to(dev), positions.to(dev, dtype), q.to(dev, dtype)
+    param = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)
+
+    def run(sl):
+        pos = p[sl].clone().requires_grad_(True)
+        e = d4.dftd4(n[sl], pos, 0.0, param, q=qq[sl])
+        (g,) = torch.autograd.grad(e.sum(), pos)
+        return d4.dftd4(n[sl], p[sl], 0.0, param, q=qq[sl]), e.detach(), g
+
+    full = run(slice(None))
+    if dtype == torch.float64:
+        ref = orc.dftd4(numbers[:9], positions[:9], param, q[:9])
+        assert ((full[0][:9].cpu() - ref).abs().max() / ref.abs().max()) < 1e-10
+    for sl in (slice(1, None), slice(3, -2), slice(0, 1), slice(-1, None)):
+        part = run(sl)
+        for a, b in zip(part, full):
+            assert torch.equal(a, b[sl])
