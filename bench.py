@@ -112,7 +112,9 @@ def make_batch(wl: dict, rank: int):
         return bench_inputs.single_molecule()
     rng = np.random.default_rng(wl["seed"] + 1000 * rank)
     sizes = rng.integers(wl["lo"], wl["hi"] + 1, size=wl["nbatch"])
-    numbers, positions, q = bench_inputs.organic_batch_parallel(sizes, seed=wl["seed"] + 1000 * rank)
+    world = int(os.environ.get("WORLD_SIZE", "1"))  # the ranks of one box share its host cores
+    numbers, positions, q = bench_inputs.organic_batch_parallel(
+        sizes, seed=wl["seed"] + 1000 * rank, workers=max(2, min(32, (os.cpu_count() or 8) // world)))
     pad = wl["hi"] - numbers.shape[1]  # every rank's batch has the workload's padded width
     if pad > 0:
         numbers = torch.nn.functional.pad(numbers, (0, pad))

@@ -1,4 +1,4 @@
-# Energy of one molecule through the drop-in API (mirrors the reference's examples/single.py,
+# Energy of one molecule through the drop-in API (mirrors the reference's examples/single.py;
 # with explicit charges: EEQ charges are outside the accelerated hot path).
 import sys
 from pathlib import Path
