@@ -401,7 +401,9 @@ class BatchBench:
         """value / e2e of this workload, aggregated over the ranks (weak scaling)."""
         ctx = self.ctx
         total_ms, launches = ctx.timed(self.step_resident, steps, warmup)
-        e2e_ms, _ = ctx.timed(self.step_e2e, steps, max(warmup, 3), host_call=not self.eeq)
+        e2e_ms = 1.0
+        if not ctx.args.no_e2e:
+            e2e_ms, _ = ctx.timed(self.step_e2e, steps, max(warmup, 3), host_call=not self.eeq)
         total_ms, e2e_ms = ctx.reduce([total_ms, e2e_ms], "max")
         nmol, npair, ntrip, nflop = ctx.reduce([float(self.numbers.shape[0]), float(self.pairs.sum()),
                                                 float(self.triples.sum()), float(self.flop.sum())], "sum")  # fmt: skip
@@ -410,7 +412,7 @@ class BatchBench:
             "value": nmol / sec, "unit": "molecules/s", "ms_per_step": sec * 1e3, "steps": steps,
             "pair_terms_per_s": npair / sec, "triple_terms_per_s": ntrip / sec,
             "algorithmic_tflops": nflop / sec / 1e12,
-            "e2e": {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(self.h2d),
+            "e2e": None if ctx.args.no_e2e else {"value": nmol / e2e_sec, "unit": "molecules/s", "h2d_bytes_per_step": int(self.h2d),
                     "d2h_bytes_per_step": int(self.d2h), "ms_per_step": e2e_sec * 1e3,
                     "api": "q=None: dftd4() on tensors copied from pinned host memory" if self.eeq else
                            "tad_dftd4_b200.dftd4_host (C ABI d4b200_energy_host_z_*): pinned host tensors in and out, "
@@ -690,6 +692,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer leg (A/B of older library builds)")
     ap.add_argument("--no-subs", action="store_true",
                     help="headline workload only (no strong-scaling / C2 / C5 / C4 sub-records)")
     ap.add_argument("--eeq", action="store_true",

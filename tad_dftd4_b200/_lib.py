@@ -102,7 +102,11 @@ def load() -> C.CDLL:
         )
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in _SIGS.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:
+            if os.environ.get("D4B200_LIBRARY"):  # an older build of the ABI, loaded on purpose for A/B timing
+                continue
+            raise D4B200Error(f"{LIB_PATH} does not export {name}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         fn.restype = res
         fn.argtypes = args
     _lib = lib

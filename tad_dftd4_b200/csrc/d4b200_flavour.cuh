@@ -11,11 +11,7 @@ struct d4b200_tables;
 
 // Size classes per flavour: X(class, CAP, threads, min CTAs/SM for launch bounds).
 // Caps are bounded by the 227 KB shared-memory budget (Lay<>::total, static_assert).
-#ifdef D4_E_LOWOCC  // A/B knob: fewer resident CTAs, more registers per thread for the tiled triple loop
-#define D4_CLASSES_F64_E(X) X(0, 32, 128, 4) X(1, 48, 192, 3) X(2, 64, 256, 2) X(3, 96, 512, 1) X(4, 120, 512, 1)
-#else
 #define D4_CLASSES_F64_E(X) X(0, 32, 128, 6) X(1, 48, 192, 4) X(2, 64, 256, 3) X(3, 96, 512, 1) X(4, 120, 512, 1)
-#endif
 #ifndef D4_G100_NT
 #define D4_G100_NT 512  // threads of the largest FP64 gradient class (A/B knob)
 #endif

@@ -456,185 +456,6 @@ __device__ __forceinline__ T reduce8x32(const T (&v)[8], bool b4, bool b3, bool 
 }
 
 // ---------------------------------------------------------------------------
-// Register-tiled energy triple loop (closed structures: every pair inside the ATM cutoff).
-//
-// Every unordered triple i > j > k is evaluated once.  A lane owns the 2 x 2 block of bottom pairs
-// {j0, j1} x {k0, k1}, j0 = 2J, j1 = 2J + 1, k0 = m, k1 = m + J (0 <= m < J), and sweeps the top atom
-// i > j1: the stash entries of (i,j0), (i,j1), (i,k0), (i,k1) are loaded once for four triples
-// (12 loads per four visits instead of 24; lanes of a warp take consecutive m, so the k loads are
-// unit stride and the j loads broadcasts), index arithmetic and the transposed shuffle reduction of
-// the top atom's share are amortised over four triples.  Left over: the triples (j1, j0, k) (two
-// per block, after the sweep) and the "diagonal" bottom pairs (2d + 1, 2d) (one lane per pair).
-// A warp takes chunks of 32 consecutive blocks (similar J, i.e. similar sweep length); chunks are
-// dealt to the warps statically in boustrophedon order, so every sum has a fixed order.
-// ---------------------------------------------------------------------------
-
-// one visit with the bottom pair's invariants folded into the damping denominator
-// (fp = P'_jk / (1 + 6 u_ij u_ik u_jk) = 1 / (iP + sPu u_ij u_ik)); 16 FP64 operations
-template <typename T>
-__device__ __forceinline__ T energy_visit(T a, T Pij, T uij, T c, T Pik, T uik, T b, T b2, T iP, T sPu) {
-  const T t1 = a - c, t2 = a + c;
-  const T s = fma(-t1, t1, b2) * (t2 - b);
-  const T abc = (a * c) * b;
-  const T fp = d4_rcp(fma(sPu, uij * uik, iP));
-  return ((Pij * Pik) * fp) * fma(T(0.375), s, abc);
-}
-
-// transposed reduction: 4 values x 32 lanes -> every lane of the group (lane >> 3) holds the sum of v[lane >> 3]
-template <typename T>
-__device__ __forceinline__ T reduce4x32(const T (&v)[4], bool b4, bool b3) {
-  const T w0 = (b4 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16);
-  const T w1 = (b4 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16);
-  T y = (b3 ? w1 : w0) + __shfl_xor_sync(0xffffffffu, b3 ? w0 : w1, 8);
-  y += __shfl_xor_sync(0xffffffffu, y, 4);
-  y += __shfl_xor_sync(0xffffffffu, y, 2);
-  y += __shfl_xor_sync(0xffffffffu, y, 1);
-  return y;
-}
-
-template <typename T>
-struct BottomPair {
-  T b, b2, iP, sPu;
-  __device__ __forceinline__ void load(const T* __restrict__ pa, const T* __restrict__ pP,
-                                       const T* __restrict__ pu, int p) {
-    b = fabs(pa[p]);
-    b2 = b * b;
-    const T Pjk = pP[p];
-    // C6(q=0) = 0 for this pair: a huge 1/P' makes every term of the pair underflow to zero
-    iP = Pjk == T(0) ? T(1e30) : d4_rcp(Pjk);
-    sPu = T(6) * pu[p] * iP;
-  }
-};
-
-// `Tw`: this warp's partial atomic energies [CAP] (zeroed by the caller)
-template <typename T, int CAP, int NT>
-__device__ __forceinline__ void energy_triples_tiled(const T* __restrict__ pa, const T* __restrict__ pP,
-                                                     const T* __restrict__ pu, T* __restrict__ Tw,
-                                                     const unsigned short* __restrict__ pij, int n, int warp,
-                                                     int lane) {
-  constexpr int NW = NT / 32;
-  const int nI = n >> 1;  // complete atom pairs (2J, 2J + 1): an unpaired last atom is never a bottom atom
-  const int nblk = nI * (nI - 1) / 2;
-  const int nchunks = (nblk + 31) >> 5;
-  const bool b4 = lane & 16, b3 = lane & 8;
-  const T z = T(0);
-  for (int round = 0; round * NW < nchunks; ++round) {
-    const int chunk = round * NW + ((round & 1) ? NW - 1 - warp : warp);
-    if (chunk >= nchunks) continue;
-    const int item = chunk * 32 + lane;
-    const bool valid = item < nblk;
-    int J, m;
-    pair_lookup(pij, valid ? item : nblk - 1, J, m);
-    const int jfirst = __shfl_sync(0xffffffffu, J, 0);  // items ascend in J: the longest sweep of the chunk
-    const int j0 = 2 * J, j1 = j0 + 1, k0 = m, k1 = m + J;
-    const int tj0 = j0 * (j0 - 1) / 2, tj1 = tj0 + j0;
-    BottomPair<T> o00, o01, o10, o11;
-    o00.load(pa, pP, pu, tj0 + k0);
-    o01.load(pa, pP, pu, tj0 + k1);
-    o10.load(pa, pP, pu, tj1 + k0);
-    o11.load(pa, pP, pu, tj1 + k1);
-    T a00 = z, a01 = z, a10 = z, a11 = z;
-    T v[4];
-    for (int i0 = 2 * jfirst + 2; i0 < n; i0 += 4) {
-      int ti = i0 * (i0 - 1) / 2;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u;
-        T ei = z;
-        if (i < n) {  // warp uniform
-          const bool act = valid && i > j1;
-          // inactive lanes read in-bounds entries of the packed planes and get a zero pair factor
-          const int xj = act ? ti + j0 : 0, xk0 = act ? ti + k0 : 0, xk1 = act ? ti + k1 : 0;
-          const T aj0 = pa[xj], uj0 = pu[xj], Pj0 = act ? pP[xj] : z;
-          const T aj1 = pa[xj + 1], uj1 = pu[xj + 1], Pj1 = act ? pP[xj + 1] : z;
-          const T ak0 = pa[xk0], uk0 = pu[xk0], Pk0 = pP[xk0];
-          const T ak1 = pa[xk1], uk1 = pu[xk1], Pk1 = pP[xk1];
-          const T e00 = energy_visit(aj0, Pj0, uj0, ak0, Pk0, uk0, o00.b, o00.b2, o00.iP, o00.sPu);
-          const T e01 = energy_visit(aj0, Pj0, uj0, ak1, Pk1, uk1, o01.b, o01.b2, o01.iP, o01.sPu);
-          const T e10 = energy_visit(aj1, Pj1, uj1, ak0, Pk0, uk0, o10.b, o10.b2, o10.iP, o10.sPu);
-          const T e11 = energy_visit(aj1, Pj1, uj1, ak1, Pk1, uk1, o11.b, o11.b2, o11.iP, o11.sPu);
-          a00 += e00;
-          a01 += e01;
-          a10 += e10;
-          a11 += e11;
-          ei = (e00 + e01) + (e10 + e11);
-        }
-        v[u] = ei;
-        ti += i;
-      }
-      const T y = reduce4x32(v, b4, b3);
-      const int iw = i0 + (lane >> 3);
-      if ((lane & 7) == 0 && iw < n) Tw[iw] += y;
-    }
-    // triples (j1, j0, k): top atom j1 over the bottom pairs (j0, k0), (j0, k1)
-    T top1 = z;
-    if (valid) {
-      const int xj = tj1 + j0;
-      const T aj = pa[xj], uj = pu[xj], Pj = pP[xj];
-      const T e0 = energy_visit(aj, Pj, uj, pa[tj1 + k0], pP[tj1 + k0], pu[tj1 + k0], o00.b, o00.b2, o00.iP, o00.sPu);
-      const T e1 = energy_visit(aj, Pj, uj, pa[tj1 + k1], pP[tj1 + k1], pu[tj1 + k1], o01.b, o01.b2, o01.iP, o01.sPu);
-      a00 += e0;
-      a01 += e1;
-      top1 = e0 + e1;
-    }
-    // shares of the bottom atoms -> per-warp partials, row pair by row pair of the chunk (the lanes of
-    // one J have distinct k0 and distinct k1, and k0 < J <= k1)
-    __syncwarp();
-    const int jlast = __shfl_sync(0xffffffffu, J, 31);
-    for (int JJ = jfirst; JJ <= jlast; ++JJ) {
-      const bool mine = valid && J == JJ;
-      const T s0 = warp_sum(mine ? a00 + a01 : z);
-      const T s1 = warp_sum(mine ? (a10 + a11) + top1 : z);
-      if (mine) {
-        Tw[k0] += a00 + a10;
-        Tw[k1] += a01 + a11;
-      }
-      if (lane == 0) {
-        Tw[2 * JJ] += s0;
-        Tw[2 * JJ + 1] += s1;
-      }
-      __syncwarp();
-    }
-  }
-  // diagonal bottom pairs (2d + 1, 2d): one lane per pair, one visit per step
-  const int nd = n >> 1;
-  for (int c = warp; c * 32 < nd; c += NW) {
-    const int d = c * 32 + lane;
-    const bool valid = d < nd;
-    const int j = 2 * (valid ? d : nd - 1) + 1, k = j - 1;
-    BottomPair<T> o;
-    o.load(pa, pP, pu, j * (j - 1) / 2 + k);
-    T acc = z;
-    T v[4];
-    for (int i0 = 64 * c + 2; i0 < n; i0 += 4) {
-      int ti = i0 * (i0 - 1) / 2;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u;
-        T ei = z;
-        if (i < n) {
-          const bool act = valid && i > j;
-          const int x = act ? ti + k : 0;
-          ei = energy_visit(pa[x + 1], act ? pP[x + 1] : z, pu[x + 1], pa[x], pP[x], pu[x], o.b, o.b2, o.iP, o.sPu);
-          acc += ei;
-        }
-        v[u] = ei;
-        ti += i;
-      }
-      const T y = reduce4x32(v, b4, b3);
-      const int iw = i0 + (lane >> 3);
-      if ((lane & 7) == 0 && iw < n) Tw[iw] += y;
-    }
-    __syncwarp();
-    if (valid) {
-      Tw[j] += acc;
-      Tw[k] += acc;
-    }
-    __syncwarp();
-  }
-}
-
-// ---------------------------------------------------------------------------
 // Register-tiled gradient sweep (closed structure, unit upstream weights).
 //
 // The owner-pair sweep above reads six stash entries (48 B) per visit for 20 FP64
@@ -866,11 +687,15 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
   const unsigned seg_p = r16((size_t)A.nat * 8 + 16);
   const unsigned seg_q = seg_p + r16((size_t)A.nat * 3 * sizeof(T) + 16);
   const unsigned seg_end = seg_q + r16((size_t)A.nat * sizeof(T) + 16);
+  // Gradient kernels only: in the energy kernels (80 registers per thread at three or more CTAs per SM)
+  // the extra live pointers cost spills and 3 % of the C2 step, while their compaction phase is already
+  // overlapped by the other resident CTAs (measured)
 #ifdef D4_NO_STAGE  // A/B knob: plain global loads in the compaction phase
-  const bool use_stage = false;
+  constexpr bool STAGE_ON = false;
 #else
-  const bool use_stage = !D4S && seg_end <= stage_avail;
+  constexpr bool STAGE_ON = GRAD && !D4S;
 #endif
+  const bool use_stage = STAGE_ON && seg_end <= stage_avail;
   unsigned bar_parity = 0;
   if (tid == 0) {
     misc[24] = -1;
@@ -926,7 +751,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     const int item = range_begin + misc[0];
     if (item >= range_end) break;
     const int b = A.wk.order[item];
-    const bool staged = misc[26] != 0;
+    const bool staged = STAGE_ON && misc[26] != 0;
     if (staged) {  // the rows of this structure were copied into shared memory during the previous iteration
       mbar_wait(bar, bar_parity);
       bar_parity ^= 1u;
@@ -1081,7 +906,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           z0[h] = tab.zeta0[za[h]];
         }
         const double gam = tab.gamgc[z], zeff = tab.zeff[z];
-        const double qat = row ? (double)qrow[idx[i]] : 0.0;
+        const double qat = row ? (double)A.q[(size_t)b * A.nat + idx[i]] : 0.0;  // energy kernel: never staged
         T c0 = T(0), c1 = T(0);
         if (row) {
           const T* r = pu + i * (i - 1) / 2;
@@ -1199,7 +1024,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       double qat = 0.0;
       if (i < n) {
         if constexpr (GRAD || D4S) qat = (double)ATOM(AT_Q)[i];
-        else qat = (double)qrow[idx[i]];
+        else qat = (double)A.q[(size_t)b * A.nat + idx[i]];
       }
       const double d = (double)cn_row - rcn;
       const double arg = (rc > 0 && !D4S) ? P.wf * d * d : 1e300;
@@ -1475,7 +1300,6 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
       __syncthreads();
       PHASE(5);
       open = misc[2] != 0;
-      if (tid == 0) prefetch_next();  // the A vectors are dead: their tail receives the next structure's rows
     } else {
     // ---- phase 5 (gradient kernel): ATM pair stash --------------------------
     if constexpr (sizeof(T) == 8) {  // C6(q = 0) of all pairs on the tensor path -> plane `pP`
@@ -1637,13 +1461,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         T* const Tw = Aq + (E2S ? CP : 0) + warp * CAP;  // A vectors are dead: per-warp E_i partials
         for (int i = lane; i < n; i += 32) Tw[i] = T(0);
         __syncwarp();
-#ifndef D4_NO_TILED_ENERGY
-        const bool tiled_e = !open && n >= 4;
-#else
-        const bool tiled_e = false;
-#endif
-        if (tiled_e) energy_triples_tiled<T, CAP, NT>(pa, pP, pu, Tw, tab.pij, n, warp, lane);
-        const int nchunks = tiled_e ? 0 : (np + 31) >> 5;
+        const int nchunks = (np + 31) >> 5;
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
         // static assignment of the chunks (sorted by decreasing sweep length): the
         // order of every floating-point sum is fixed, so results are bitwise reproducible

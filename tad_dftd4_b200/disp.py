@@ -259,7 +259,7 @@ class _D4Function(torch.autograd.Function):
 
 # Central-difference step of the second-order path (Bohr for positions, e for charges; applied to
 # the direction normalised to unit maximum component) and its fourth-order stencil
-_FD_STEP = 2.0e-3
+_FD_STEP = 5.0e-4
 _FD_STENCIL = ((1.0, 8.0 / 12.0), (-1.0, -8.0 / 12.0), (2.0, -1.0 / 12.0), (-2.0, 1.0 / 12.0))
 
 
@@ -283,7 +283,7 @@ class _D4Vjp(torch.autograd.Function):
     upstream direction ``w = (w_pos, w_q)`` the node needs ``d/dx (g . w) = D_w g`` (the Hessian is
     symmetric), the directional derivative of the ANALYTIC gradient, and ``d/dgout (g . w) = D_w E``.
     Both are fourth-order central differences of the kernels along ``w`` (four gradient and four
-    energy launches, step 2e-3 Bohr on the largest component: truncation ~1e-11 relative,
+    energy launches, step 5e-4 Bohr on the largest component: truncation ~1e-11 relative,
     round-off ~1e-13), far inside the 1e-7 the reference's Hessian tests ask for
     (``test/test_grad/test_hessian.py:47``).  Everything stays on the CUDA kernels."""
 

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+import d4_oracle as orc
 from helpers import GOLDEN_CASES, as_torch, load_golden
 
 pytestmark = pytest.mark.gpu

@@ -4,6 +4,6 @@
 args="$1"; shift
 for r in 1 2; do
   for lib in "$@"; do
-    D4B200_LIBRARY=$lib python bench.py $args --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$lib', 'step %.4f ms' % d['ms_per_step'], 'e2e %.4f' % d['e2e']['ms_per_step'], 'classes', [round(x,4) for x in d['roofline']['all_class_ms']])"
+    D4B200_LIBRARY=$lib python bench.py $args --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$lib', 'step %.4f ms' % d['ms_per_step'], 'e2e %.4f' % (d['e2e']['ms_per_step'] if d['e2e'] else 0), 'classes', [round(x,4) for x in d['roofline']['all_class_ms']])"
   done
 done
