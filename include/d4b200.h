@@ -240,6 +240,22 @@ int d4b200_large_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, 
                               int row_end, int group_begin, int group_end, float* force_dev,
                               float* dcn_dev, float* dq_dev, void* workspace_dev,
                               size_t workspace_bytes, void* stream);
+/* Stage 1 with the atomic energies from the same launches (fused energy + gradient call of the tiled
+ * family; what ``energy = dftd4(...); autograd.grad(energy.sum(), positions)`` asks for,
+ * examples/forces.py:47-50 of the reference): additionally ACCUMULATES into energy_dev [nat] the
+ * two-body rows and ATM centre groups of this rank (zero it first; all-reduce over the ranks). */
+int d4b200_large_energy_gradient_f64(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                                     const int64_t* numbers_dev, const double* positions_dev,
+                                     const double* q_dev, const double* grad_energy_dev, int row_begin,
+                                     int row_end, int group_begin, int group_end, double* energy_dev,
+                                     double* force_dev, double* dcn_dev, double* dq_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream);
+int d4b200_large_energy_gradient_f32(d4b200_tables_t tables, const d4b200_params* par, int nat,
+                                     const int64_t* numbers_dev, const float* positions_dev,
+                                     const float* q_dev, const float* grad_energy_dev, int row_begin,
+                                     int row_end, int group_begin, int group_end, float* energy_dev,
+                                     float* force_dev, float* dcn_dev, float* dq_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream);
 int d4b200_large_cn_chain_f64(d4b200_tables_t tables, const d4b200_params* par, int nat,
                               const int64_t* numbers_dev, const double* positions_dev,
                               const double* dcn_total_dev, int row_begin, int row_end,

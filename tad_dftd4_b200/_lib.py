@@ -56,6 +56,8 @@ _SIGS = {
     "d4b200_large_energy_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_large_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_large_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_large_energy_gradient_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
+    "d4b200_large_energy_gradient_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, C.c_size_t, _VP]),
     "d4b200_large_cn_chain_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "d4b200_large_cn_chain_f32": (C.c_int, [_VP, C.POINTER(Params), C.c_int, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "d4b200_weight_references_f64": (C.c_int, [_VP, C.POINTER(Params), C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

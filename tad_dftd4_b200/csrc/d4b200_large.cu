@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(128) large_twobody_grad(LargeArgs<T> A, int nc
   const Par<T>& P = A.par;
   const int chunk = (A.nat + ncolchunks - 1) / ncolchunks;
   const int c0 = blockIdx.y * chunk, c1 = min(A.nat, c0 + chunk);
-  T fx = T(0), fy = T(0), fz = T(0), dcn = T(0), dq = T(0);
+  T fx = T(0), fy = T(0), fz = T(0), dcn = T(0), dq = T(0), e2 = T(0);
   for (int base = c0; base < c1; base += 64) {
     __syncthreads();
     for (int t = tid; t < 64 * AVEC; t += 128) {
@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(128) large_twobody_grad(LargeArgs<T> A, int nc
           dF -= T(10) * P.s10k * qq * qq * r8 * t10 * t10;
         }
         const T G2 = T(-0.5) * (gi + sg[t]);
+        e2 += c6 * F;  // fused energy + gradient call: the row's two-body energy
         const T fc = G2 * c6 * dF;
         fx += fc * dx;
         fy += fc * dy;
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(128) large_twobody_grad(LargeArgs<T> A, int nc
     atomicAdd(&A.force[3 * i + 2], fz);
     atomicAdd(&A.dcn[i], dcn);
     atomicAdd(&A.dq[i], dq);
+    if (A.energy && e2 != T(0)) atomicAdd(&A.energy[i], T(-0.5) * e2);
   }
 }
 
@@ -795,6 +797,7 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
         }
         T kfx = T(0), kfy = T(0), kfz = T(0), kdc = T(0);         // column atom k
         T ifx[2] = {T(0), T(0)}, ify[2] = {T(0), T(0)}, ifz[2] = {T(0), T(0)}, idc[2] = {T(0), T(0)};
+        T ie[2] = {T(0), T(0)}, ke = T(0);  // fused energy + gradient call: E_i += e, E_k += e per centre (large_atm)
         for (int j = 0; j < GROUP; ++j) {
           T jfx = T(0), jfy = T(0), jfz = T(0), jdc = T(0);       // centre j
           const T b = TST(1, j, 0, lane), Pb = TST(1, j, 1, lane), ub = TST(1, j, 2, lane);
@@ -831,6 +834,8 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
               kfx += vbx - vcx, kfy += vby - vcy, kfz += vbz - vcz;
               jfx -= vax + vbx, jfy -= vay + vby, jfz -= vaz + vbz;
               const T We = W * e;
+              ie[rr] += e;
+              ke += e;
               idc[rr] += We * (TST(0, j, 4, row) + fDi[rr]);   // D^(i)_ij + D^(i)_ik
               kdc += We * (Dkj + fDk[rr]);                      // D^(k)_kj + D^(k)_ki
               jdc += We * (TST(0, j, 3, row) + Djk);           // D^(j)_ji + D^(j)_jk
@@ -855,7 +860,12 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
             atomicAdd(&A.force[3 * ii + 2], sz_);
             atomicAdd(&A.dcn[ii], sc_);
           }
+          if (A.energy) {
+            const T se_ = warp_sum(ie[rr]);
+            if (lane == 0 && ii >= 0 && se_ != T(0)) atomicAdd(&A.energy[ii], se_);
+          }
         }
+        if (A.energy && kk >= 0 && ke != T(0)) atomicAdd(&A.energy[kk], ke);
         if (kk >= 0 && (kfx != T(0) || kfy != T(0) || kfz != T(0) || kdc != T(0))) {
           atomicAdd(&A.force[3 * kk], kfx);
           atomicAdd(&A.force[3 * kk + 1], kfy);
@@ -1063,7 +1073,7 @@ template <typename T>
 int run_large_grad(d4b200_tables* h, const d4b200_params* par, int nat, const int64_t* numbers,
                    const T* pos, const T* q, const T* gin, int row_begin, int row_end,
                    int group_begin, int group_end, T* force, T* dcn, T* dq, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
+                   size_t ws_bytes, cudaStream_t st, T* energy = nullptr) {
   if (!h || !par || !numbers || !pos || !q || !ws || !force || !dcn || !dq || nat <= 0) return D4B200_EINVAL;
   if (par->model != D4B200_MODEL_D4) return D4B200_EPARAM;
   const int nctas = large_grad_ctas(h);
@@ -1074,6 +1084,7 @@ int run_large_grad(d4b200_tables* h, const d4b200_params* par, int nat, const in
   fill_common<T>(A, h, par, c, w, nat, numbers, pos, q);
   const int ng = A.ngroups;
   A.gin = gin;
+  A.energy = energy;  // optional: partial atomic energies of this rank's ranges from the same launches
   A.force = force;
   A.dcn = dcn;
   A.dq = dq;
@@ -1154,6 +1165,22 @@ int d4b200_large_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int n
                               size_t ws_bytes, void* stream) {
   return run_large_grad<double>(t, par, nat, numbers, pos, q, gin, row_begin, row_end, group_begin,
                                 group_end, force, dcn, dq, ws, ws_bytes, (cudaStream_t)stream);
+}
+int d4b200_large_energy_gradient_f64(d4b200_tables_t t, const d4b200_params* par, int nat,
+                                     const int64_t* numbers, const double* pos, const double* q,
+                                     const double* gin, int row_begin, int row_end, int group_begin,
+                                     int group_end, double* energy, double* force, double* dcn, double* dq,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  return run_large_grad<double>(t, par, nat, numbers, pos, q, gin, row_begin, row_end, group_begin,
+                                group_end, force, dcn, dq, ws, ws_bytes, (cudaStream_t)stream, energy);
+}
+int d4b200_large_energy_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nat,
+                                     const int64_t* numbers, const float* pos, const float* q,
+                                     const float* gin, int row_begin, int row_end, int group_begin,
+                                     int group_end, float* energy, float* force, float* dcn, float* dq,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  return run_large_grad<float>(t, par, nat, numbers, pos, q, gin, row_begin, row_end, group_begin,
+                               group_end, force, dcn, dq, ws, ws_bytes, (cudaStream_t)stream, energy);
 }
 int d4b200_large_gradient_f32(d4b200_tables_t t, const d4b200_params* par, int nat,
                               const int64_t* numbers, const float* pos, const float* q,

@@ -253,20 +253,27 @@ def _kernel_backend(positions: Tensor, param, cutoff, model=None):
         with torch.cuda.device(p.device):
             return _kernel_compute(engine, par, n, p, qq, rows, groups, want_cost)
 
-    def grad1(n, p, qq, g, rows, groups):
+    def grad1(n, p, qq, g, rows, groups, energy=None):
+        """Stage 1 of the gradient; ``energy`` (zeroed tensor [nat]) additionally receives this rank's
+        partial atomic energies from the same launches (fused energy + gradient call)."""
         nat = n.shape[0]
         force = torch.zeros((nat, 3), dtype=p.dtype, device=p.device)
         dcn = torch.zeros(nat, dtype=p.dtype, device=p.device)
         dq = torch.zeros(nat, dtype=p.dtype, device=p.device)
         ws = ws_for(nat)
-        fn = lib.d4b200_large_gradient_f32 if fp32 else lib.d4b200_large_gradient_f64
         with torch.cuda.device(p.device):
-            _lib.check(
-                fn(engine.handle, C.byref(par), nat, n.data_ptr(), p.data_ptr(), qq.data_ptr(),
-                   g.data_ptr() if g is not None else None, rows[0], rows[1], groups[0], groups[1],
-                   force.data_ptr(), dcn.data_ptr(), dq.data_ptr(), ws.data_ptr(), ws.numel(), stream()),
-                "d4b200_large_gradient",
-            )  # fmt: skip
+            if energy is None:
+                fn = lib.d4b200_large_gradient_f32 if fp32 else lib.d4b200_large_gradient_f64
+                code = fn(engine.handle, C.byref(par), nat, n.data_ptr(), p.data_ptr(), qq.data_ptr(),
+                          g.data_ptr() if g is not None else None, rows[0], rows[1], groups[0], groups[1],
+                          force.data_ptr(), dcn.data_ptr(), dq.data_ptr(), ws.data_ptr(), ws.numel(), stream())  # fmt: skip
+            else:
+                fn = lib.d4b200_large_energy_gradient_f32 if fp32 else lib.d4b200_large_energy_gradient_f64
+                code = fn(engine.handle, C.byref(par), nat, n.data_ptr(), p.data_ptr(), qq.data_ptr(),
+                          g.data_ptr() if g is not None else None, rows[0], rows[1], groups[0], groups[1],
+                          energy.data_ptr(), force.data_ptr(), dcn.data_ptr(), dq.data_ptr(), ws.data_ptr(),
+                          ws.numel(), stream())  # fmt: skip
+            _lib.check(code, "d4b200_large_gradient")
         return force, dcn, dq
 
     def grad2(n, p, dcn_total, rows, force):
@@ -302,30 +309,42 @@ def large_energy(numbers, positions, param, q, *, cutoff=None, group=None, backe
     return out
 
 
-def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=None, backend=None, model=None):
-    """``(dL/dpositions, dL/dq)`` for ``L = sum_i gout_i E_i`` of ONE structure.
+def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=None, backend=None, model=None,
+                    with_energy: bool = False):
+    """``(dL/dpositions, dL/dq)`` for ``L = sum_i gout_i E_i`` of ONE structure (``gout=None``: ones).
 
     Two stages with one all-reduce each (plus the final one for the forces):
     direct two-body/ATM terms -> all-reduce(dL/dcn, dL/dq) -> CN chain rule on the
-    rank's rows -> all-reduce(dL/dpositions)."""
+    rank's rows -> all-reduce(dL/dpositions).  ``with_energy=True`` additionally returns the
+    atom-resolved energies, accumulated by the same kernel launches (one more all-reduce)."""
     _check_single(numbers, positions, q)
     be = backend or _kernel_backend(positions, param, cutoff, model)
     plan = _Plan(numbers, positions, q, group,
                  lambda n, p, qq: be["energy"](n, p, qq, (0, 0), (0, 0), True)[1], be["group_size"])  # fmt: skip
     gpos = torch.zeros_like(positions)
     gq = torch.zeros(numbers.shape[0], dtype=positions.dtype, device=positions.device)
+    energy = torch.zeros(numbers.shape[0], dtype=positions.dtype, device=positions.device) if with_energy else None
     if plan.nat == 0:
-        return gpos, gq
+        return (gpos, gq, energy) if with_energy else (gpos, gq)
     g_s = None if gout is None else gout[plan.order].to(positions.dtype).contiguous()
-    force, dcn, dq = be["grad1"](plan.numbers, plan.positions, plan.q, g_s, plan.rows, plan.groups)
+    e_s = torch.zeros(plan.nat, dtype=positions.dtype, device=positions.device) if with_energy else None
+    if with_energy:
+        force, dcn, dq = be["grad1"](plan.numbers, plan.positions, plan.q, g_s, plan.rows, plan.groups, energy=e_s)
+    else:
+        force, dcn, dq = be["grad1"](plan.numbers, plan.positions, plan.q, g_s, plan.rows, plan.groups)
     if plan.world > 1:
         both = torch.stack([dcn, dq])
         plan.all_reduce(both)
         dcn, dq = both[0].contiguous(), both[1].contiguous()
+        if with_energy:
+            plan.all_reduce(e_s)
     force = be["grad2"](plan.numbers, plan.positions, dcn, plan.rows, force)
     plan.all_reduce(force)
     gpos[plan.order] = force
     gq[plan.order] = dq
+    if with_energy:
+        energy[plan.order] = e_s
+        return gpos, gq, energy
     return gpos, gq
 
 
@@ -334,12 +353,24 @@ class _LargeFunction(torch.autograd.Function):
     def forward(ctx, positions, q, numbers, param, cutoff, group, model):
         ctx.save_for_backward(positions, q, numbers)
         ctx.param, ctx.cutoff, ctx.group, ctx.model = param, cutoff, group, model
+        ctx.cached = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            # inputs on the tape: energies AND the gradient of sum(E) from one set of launches (the
+            # gradient kernels evaluate every term anyway); backward only scales the cached gradient
+            # when the upstream gradient is a broadcast scalar (energy.sum().backward(), forces)
+            gpos, gq, energy = dftd4_large_vjp(numbers, positions, param, q, None, cutoff=cutoff, group=group,
+                                               model=model, with_energy=True)  # fmt: skip
+            ctx.cached = (gpos, gq)
+            return energy
         return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group, model=model)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         positions, q, numbers = ctx.saved_tensors
+        if ctx.cached is not None and all(s == 0 for s in gout.stride()):
+            c = gout.reshape(-1)[0]
+            return ctx.cached[0] * c, ctx.cached[1] * c, None, None, None, None, None
         gpos, gq = dftd4_large_vjp(numbers, positions, ctx.param, q, gout.contiguous(),
                                    cutoff=ctx.cutoff, group=ctx.group, model=ctx.model)  # fmt: skip
         return gpos, gq, None, None, None, None, None

@@ -50,7 +50,9 @@ def _oracle_backend(orc):
         e = torch.where(rowmask, e2, torch.zeros_like(e2)) + e3
         return e if g is None else (e * g)
 
-    def grad1(n, p, q, g, rows, groups):
+    def grad1(n, p, q, g, rows, groups, energy=None):
+        if energy is not None:  # fused energy + gradient call: this rank's partial atomic energies
+            energy += partial(n, p, q, None, rows, groups).detach()
         pp = p.clone().requires_grad_(True)
         qq = q.clone().requires_grad_(True)
         cn = orc.cn_d4(n, p).requires_grad_(True)  # independent variable: direct terms only
@@ -142,6 +144,12 @@ def _worker(rank, world, port, out_dir):
         gp, gq = dftd4_large_vjp(numbers, positions, PARAM, qq, g, backend=_oracle_backend(orc))
         assert (gp - gp_ref).abs().max() < 1e-14, (gp - gp_ref).abs().max()
         assert (gq - gq_ref).abs().max() < 1e-14, (gq - gq_ref).abs().max()
+        # fused energy + gradient (what the autograd function's forward runs when inputs are on the tape)
+        gp1, gq1, e1 = dftd4_large_vjp(numbers, positions, PARAM, qq, None, backend=_oracle_backend(orc),
+                                       with_energy=True)  # fmt: skip
+        gp1_ref, gq1_ref = torch.autograd.grad(orc.dftd4(numbers, pos, PARAM, qv).sum(), (pos, qv))
+        assert (e1 - ref).abs().max() < 1e-15 and (gp1 - gp1_ref).abs().max() < 1e-14
+        assert (gq1 - gq1_ref).abs().max() < 1e-14
         Path(out_dir, f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
