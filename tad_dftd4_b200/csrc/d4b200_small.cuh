@@ -97,7 +97,13 @@ __device__ __forceinline__ double d4_rcp(double x) {
   const double e = fma(-x, y, 1.0);
   return fma(y, fma(e, e, e), y);
 }
-__device__ __forceinline__ float d4_rcp(float x) { return __frcp_rn(x); }
+// float: MUFU.RCP seed (~1 ulp) + one Newton step; __frcp_rn is a ~16-instruction IEEE-rounding
+// sequence that made up a third of the instructions of the FP32 gradient kernel (ncu source view)
+__device__ __forceinline__ float d4_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
 // Damping reciprocal of the gradient triple sweep: MUFU seed + ONE Newton step (two FMAs).
 // Relative error ~ e^2 < 1e-12 on the three-body terms only, which are ~1e-2 of the energy
 // and ~1e-5 Eh/Bohr in the gradient: four orders of magnitude inside the 1e-10 / 1e-9 bars.
@@ -110,7 +116,11 @@ __device__ __forceinline__ double d4_rcp_sweep(double x) {
   return fma(y, fma(-x, y, 1.0), y);
 #endif
 }
-__device__ __forceinline__ float d4_rcp_sweep(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float d4_rcp_sweep(float x) {  // three-body terms only: the MUFU result as it is
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <typename T>
 __device__ __forceinline__ T d4_eps();

@@ -4,7 +4,9 @@ Aggregate an ncu source-page CSV (SASS view) by CUDA source line.
 
     ncu -i prof.ncu-rep --page source --csv > prof_src.csv
     cuobjdump -xelf all libd4b200.so ; nvdisasm -g -c *.cubin > dis.txt
-    python tools/ncu_by_line.py prof_src.csv dis.txt 'small_kernelIdLb0' [min_pct]
+    python tools/ncu_by_line.py prof_src.csv dis.txt 'small_kernelIdLb0' [min_pct [source_dir]]
+
+(source_dir: directory holding the .cuh/.cu files of the profiled build, default tad_dftd4_b200/csrc)
 
 ncu's CSV source page carries per-SASS-instruction samples but no line numbers;
 nvdisasm -g carries the line table.  Both list the kernel's instructions in
@@ -40,6 +42,7 @@ def parse_dis(path, func_pat):
 def main():
     src_csv, dis, pat = sys.argv[1:4]
     min_pct = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+    src_dir = sys.argv[5] if len(sys.argv) > 5 else "/root/repo/tad_dftd4_b200/csrc"
     rows = list(csv.reader(open(src_csv)))
     hdr = rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
@@ -72,7 +75,7 @@ def main():
             continue
         if f not in srcs:
             try:
-                srcs[f] = open(f"/root/repo/tad_dftd4_b200/csrc/{f}").read().splitlines()
+                srcs[f] = open(f"{src_dir}/{f}").read().splitlines()
             except OSError:
                 srcs[f] = []
         code = srcs[f][line - 1].strip()[:70] if 0 < line <= len(srcs[f]) else ""
