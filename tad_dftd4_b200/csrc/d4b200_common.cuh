@@ -16,6 +16,7 @@ constexpr int NCLASS = 5;       // size classes of the small family
 constexpr int HIST_BINS = SMALL_MAX + 2;
 constexpr int D4S_ECAP = 8;         // D4S weight table: distinct elements per structure it can hold
 constexpr int D4S_WSTR = 2 * NREF;  // table entry: gw[7], d gw/d cn [7]
+constexpr int D4S_RCAP = 7;         // D4S gradient: distinct elements whose reference-C6 blocks are staged in shared memory
 
 // Per-element tables in device memory (layout: tad_dftd4_b200/tables.py).
 // Weight-related tables are always double (the reference evaluates the

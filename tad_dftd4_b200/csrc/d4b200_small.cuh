@@ -188,7 +188,12 @@ struct Lay {
   static constexpr size_t wts = atoms + al16(size_t(n_atom) * CAP * sizeof(T));
   static constexpr size_t ints = wts + al16(size_t(n_wt) * NREF * CAP * sizeof(T));
   // zs[CAP], idx[CAP], (D4S: element index per atom [CAP]), misc[32]
-  static constexpr size_t total = ints + al16(((D4S ? 3 : 2) * CAP + 32) * sizeof(int));
+  // D4S gradient kernels: the reference-C6 blocks rc6[Z, Z', 7, 7] of the structure's distinct element
+  // pairs, staged once per structure (the per-pair 7 x 7 contractions otherwise gather 49 values per
+  // pair from the global table with lane-varying (Z, Z'): ncu shows them stalled on those loads)
+  static constexpr size_t rs_elems = (D4S && GRAD) ? size_t(D4S_RCAP) * D4S_RCAP * NREF * NREF : 0;
+  static constexpr size_t rs = ints + al16(((D4S ? 3 : 2) * CAP + 32) * sizeof(int));
+  static constexpr size_t total = rs + al16(rs_elems * sizeof(T));
   static constexpr int scratch_planes = GRAD ? 5 : 3;  // gradient: Gamma, D, E3 shares (2), E2; energy: E3 shares (2), E2
   // per-CTA stride of the L2 scratch: the planes, then (D4S) the weight table [CAP][D4S_ECAP][D4S_WSTR]
   static constexpr size_t scratch_stride = size_t(scratch_planes) * CP + (D4S ? size_t(CAP) * D4S_ECAP * D4S_WSTR : 0);
@@ -1144,6 +1149,7 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     bool open = false;
     int nel = 0;           // D4S: distinct elements of the structure
     bool use_tab = false;  // D4S: weights come from the per-(atom, element) table
+    T* const Rs = reinterpret_cast<T*>(smem + L::rs);  // D4S gradient: staged reference-C6 blocks
     if constexpr (D4S) {
       for (int i = tid; i < n; i += NT) atomicOr(&misc[8 + (zs[i] >> 5)], (int)(1u << (zs[i] & 31)));
       __syncthreads();
@@ -1158,6 +1164,15 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           misc[12 + e] = z;  // every atom of the element writes the same value
         }
         __syncthreads();
+        if constexpr (GRAD) {
+          if (nel <= D4S_RCAP) {
+            for (int t = tid; t < nel * nel * (NREF * NREF); t += NT) {
+              const int blk = t / (NREF * NREF), ab = t - blk * (NREF * NREF);
+              const int e1 = blk / nel, e2 = blk - e1 * nel;
+              Rs[t] = tab.rc6[((size_t)misc[12 + e1] * NELEM + misc[12 + e2]) * (NREF * NREF) + ab];
+            }
+          }
+        }
         for (int t = tid; t < n * nel; t += NT) {
           const int i = t / nel, e = t - i * nel;
           const int zi = zs[i];
@@ -1202,7 +1217,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           v[bq] = WT(WT_Q)[j * NREF + bq] * gj[bq];
           v0[bq] = WT(WT_0)[j * NREF + bq] * gj[bq];
         }
-        const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
+        const T* R = (GRAD && use_tab && nel <= D4S_RCAP) ? Rs + (ei[i] * nel + ei[j]) * (NREF * NREF)
+                                                          : tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
         T c6q = T(0), c60 = T(0);
 #pragma unroll
         for (int a = 0; a < NREF; ++a) {
@@ -1567,52 +1583,68 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           pair_lookup(tab.pij, p, i, j);
           const T r2 = fabs(pa[p]);  // stash: signed squared distance
           const int zi = zs[i], zj = zs[j];
-          const T* R = tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
-          T gi[NREF], dgi[NREF], gj[NREF], dgj[NREF];
+          const T* R = (use_tab && nel <= D4S_RCAP) ? Rs + (ei[i] * nel + ei[j]) * (NREF * NREF)
+                                                    : tab.rc6 + ((size_t)zi * NELEM + zj) * (NREF * NREF);
+          // weights (gw[7], d gw/d cn[7]) of i as seen by j's element and vice versa: from the per-(atom,
+          // element) table, or evaluated here when the structure has more distinct elements than it holds
+          T wloc[2][2 * NREF];
+          const T* wi = wloc[0];
+          const T* wj = wloc[1];
           if (use_tab) {
-            const T* wi = wtab + (size_t)(i * nel + ei[j]) * D4S_WSTR;
-            const T* wj = wtab + (size_t)(j * nel + ei[i]) * D4S_WSTR;
-#pragma unroll
-            for (int a = 0; a < NREF; ++a) {
-              gi[a] = wi[a];
-              dgi[a] = wi[NREF + a];
-              gj[a] = wj[a];
-              dgj[a] = wj[NREF + a];
-            }
+            wi = wtab + (size_t)(i * nel + ei[j]) * D4S_WSTR;
+            wj = wtab + (size_t)(j * nel + ei[i]) * D4S_WSTR;
           } else {
-            d4s_weights<T, true>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], gi, dgi);
-            d4s_weights<T, true>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], gj, dgj);
+            T g[NREF], dg[NREF];
+            d4s_weights<T, true>(tab.refcn, tab.refc, zi, (double)ATOM(AT_CN)[i], tab.wfpair[zi * NELEM + zj], g, dg);
+#pragma unroll
+            for (int a = 0; a < NREF; ++a) wloc[0][a] = g[a], wloc[0][NREF + a] = dg[a];
+            d4s_weights<T, true>(tab.refcn, tab.refc, zj, (double)ATOM(AT_CN)[j], tab.wfpair[zj * NELEM + zi], g, dg);
+#pragma unroll
+            for (int a = 0; a < NREF; ++a) wloc[1][a] = g[a], wloc[1][NREF + a] = dg[a];
           }
-          // t = R v, s = R^T u for both flavours
+          // One SIDE at a time (x = i with partner j, then x = j with partner i, R transposed): t = R_xy v_y
+          // with v_y = zeta_y o gw_y|Zx, then everything that differentiates x's weights.  Two passes over
+          // the 7 x 7 block with ~30 live values each instead of one pass with ~60 (which spilled).
+          const T* Rji = (use_tab && nel <= D4S_RCAP) ? Rs + (ei[j] * nel + ei[i]) * (NREF * NREF)
+                                                      : tab.rc6 + ((size_t)zj * NELEM + zi) * (NREF * NREF);
           T c6q = T(0), c60 = T(0), dq_cni = T(0), d0_cni = T(0), dq_qi = T(0);
-          T sq[NREF], s0[NREF];
-#pragma unroll
-          for (int bq = 0; bq < NREF; ++bq) sq[bq] = s0[bq] = T(0);
-#pragma unroll
-          for (int a = 0; a < NREF; ++a) {
-            const T zq = WT(WT_Q)[i * NREF + a], z0 = WT(WT_0)[i * NREF + a];
-            const T u = zq * gi[a], u0 = z0 * gi[a];
-            T t = T(0), t0 = T(0);
-#pragma unroll
-            for (int bq = 0; bq < NREF; ++bq) {
-              const T rab = R[a * NREF + bq];
-              t += rab * (WT(WT_Q)[j * NREF + bq] * gj[bq]);
-              t0 += rab * (WT(WT_0)[j * NREF + bq] * gj[bq]);
-              sq[bq] += rab * u;
-              s0[bq] += rab * u0;
-            }
-            c6q += u * t;
-            c60 += u0 * t0;
-            dq_cni += zq * dgi[a] * t;
-            d0_cni += z0 * dgi[a] * t0;
-            dq_qi += WT(WT_ZGD)[i * NREF + a] * gi[a] * t;
-          }
           T dq_cnj = T(0), d0_cnj = T(0), dq_qj = T(0);
 #pragma unroll
-          for (int bq = 0; bq < NREF; ++bq) {
-            dq_cnj += WT(WT_Q)[j * NREF + bq] * dgj[bq] * sq[bq];
-            d0_cnj += WT(WT_0)[j * NREF + bq] * dgj[bq] * s0[bq];
-            dq_qj += WT(WT_ZGD)[j * NREF + bq] * gj[bq] * sq[bq];
+          for (int side = 0; side < 2; ++side) {
+            const int x = side ? j : i, y = side ? i : j;
+            const T* Rxy = side ? Rji : R;
+            const T* wx = side ? wj : wi;
+            const T* wy = side ? wi : wj;
+            T vq[NREF], v0[NREF];
+#pragma unroll
+            for (int bq = 0; bq < NREF; ++bq) {
+              const T g = wy[bq];
+              vq[bq] = WT(WT_Q)[y * NREF + bq] * g;
+              v0[bq] = WT(WT_0)[y * NREF + bq] * g;
+            }
+            T cq = T(0), c0 = T(0), dcq = T(0), dc0 = T(0), dqq = T(0);
+#pragma unroll
+            for (int a = 0; a < NREF; ++a) {
+              T t = T(0), t0 = T(0);
+#pragma unroll
+              for (int bq = 0; bq < NREF; ++bq) {
+                const T rab = Rxy[a * NREF + bq];
+                t += rab * vq[bq];
+                t0 += rab * v0[bq];
+              }
+              const T gx = wx[a], dgx = wx[NREF + a];
+              const T zq = WT(WT_Q)[x * NREF + a], z0 = WT(WT_0)[x * NREF + a];
+              cq += zq * gx * t;
+              c0 += z0 * gx * t0;
+              dcq += zq * dgx * t;
+              dc0 += z0 * dgx * t0;
+              dqq += WT(WT_ZGD)[x * NREF + a] * gx * t;
+            }
+            if (side == 0) {
+              c6q = cq, c60 = c0, dq_cni = dcq, d0_cni = dc0, dq_qi = dqq;
+            } else {
+              dq_cnj = dcq, d0_cnj = dc0, dq_qj = dqq;
+            }
           }
           const T G2 = T(-0.5) * (ATOM(AT_G)[i] + ATOM(AT_G)[j]);
           T coefq = T(0), fc = T(2) * pu[p], e2 = T(0);

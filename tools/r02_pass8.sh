@@ -4,9 +4,10 @@ out=gpurun_out
 mkdir -p $out
 timeout 1500 python -m pytest tests -m gpu -q > $out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/r02_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/r02_smoke.log 2>&1; tail -2 $out/r02_smoke.log
+D4B200_LIBRARY=build_ab/final3.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_param.py tests/test_gpu_hessian.py -m gpu -q > $out/r02_pytest_final3.log 2>&1; echo "pytest final3 rc=$?"; tail -3 $out/r02_pytest_final3.log
 rm -f $out/r02_ab_r01_final.txt
 for w in "c3" "c2" "c5" "c5 --dtype f32" "c3 --dtype f32" "c2 --dtype f32"; do
-  bash tools/ab.sh "--workload $w --steps 30 --warmup 5 --no-subs --no-e2e" build_ab/r01.so build_ab/final.so build_ab/final2.so 2>&1 | tee -a $out/r02_ab_r01_final.txt
+  bash tools/ab.sh "--workload $w --steps 30 --warmup 5 --no-subs --no-e2e" build_ab/r01.so build_ab/final.so build_ab/final2.so build_ab/final3.so 2>&1 | tee -a $out/r02_ab_r01_final.txt
 done
 b() { name=$1; shift; timeout 600 python bench.py "$@" > $out/r02_bench_$name.json 2> $out/r02_bench_$name.err; cut -c1-200 $out/r02_bench_$name.json; }
 b default --steps 20 --warmup 3
