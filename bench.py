@@ -307,6 +307,8 @@ class Ctx:
 
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
+            # the other ranks WAIT (blocking sockets, no spinning on the host cores) while rank 0 times the CPU baseline
+            self.wait_group = dist.new_group(backend="gloo")
         d4.set_checks(False)  # fully asynchronous steps; parity is the tests' job (and cpu_baseline.parity)
         self.lib = _lib.load()
         self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)  # > 126 MB L2
@@ -655,9 +657,11 @@ def run_b200(args, rank, world, local_rank):
 
     cpu = None
     if not args.no_cpu:
-        if rank == 0:  # rank 0's host cores; the other ranks wait at the barrier below
+        torch.cuda.synchronize(ctx.dev)
+        if rank == 0:  # rank 0 has the host cores to itself; the other ranks sleep in the gloo barrier below
             cpu = head.cpu_baseline()
-        ctx.barrier()
+        if ctx.dist is not None:
+            ctx.dist.barrier(group=ctx.wait_group)
 
     if rank == 0:
         line = {
