@@ -897,8 +897,8 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
     // exponent) and the normalisation are 8-lane shuffle reductions; the weights stay in
     // registers for the weighted polarizability vectors (three frequencies per lane).
 #ifndef D4_WEIGHTS_LANES8
-    if constexpr (!GRAD && !D4S) {
-      // D4 energy kernel: FOUR lanes per atom (references a and a + 4 per lane, frequencies
+    if constexpr (!D4S) {
+      // D4 kernels: FOUR lanes per atom (references a and a + 4 per lane, frequencies
       // a, a + 4, ..., a + 20), so that the whole structure is one pass of the CTA for every
       // size class (CAP atoms x 4 lanes = NT threads): the phase is a single latency chain
       // (row sum -> shift -> exponentials -> normalisation -> vectors), two passes of eight
@@ -921,7 +921,11 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           z0[h] = tab.zeta0[za[h]];
         }
         const double gam = tab.gamgc[z], zeff = tab.zeff[z];
-        const double qat = row ? (double)A.q[(size_t)b * A.nat + idx[i]] : 0.0;  // energy kernel: never staged
+        double qat = 0.0;
+        if (row) {
+          if constexpr (GRAD) qat = (double)ATOM(AT_Q)[i];
+          else qat = (double)A.q[(size_t)b * A.nat + idx[i]];  // energy kernel: never staged
+        }
         T c0 = T(0), c1 = T(0);
         if (row) {
           const T* r = pu + i * (i - 1) / 2;
@@ -941,35 +945,48 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
         T cn_row = c0 + c1;
         cn_row += __shfl_xor_sync(0xffffffffu, cn_row, 2);
         cn_row += __shfl_xor_sync(0xffffffffu, cn_row, 1);
-        if (a == 0 && row && A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = cn_row;
-        double arg[2];
+        if (a == 0 && row) {
+          if constexpr (GRAD) ATOM(AT_CN)[i] = cn_row;
+          else if (A.cn_out) A.cn_out[(size_t)b * A.nat + idx[i]] = cn_row;
+        }
+        double arg[2], dd[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const double d = (double)cn_row - rcn[h];
+          dd[h] = d;
           arg[h] = rc[h] > 0 ? P.wf * d * d : 1e300;
         }
         double shift = fmin(arg[0], arg[1]);
         shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, 2));
         shift = fmin(shift, __shfl_xor_sync(0xffffffffu, shift, 1));
-        double S[2];
+        double S[2], dS[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const double t1 = exp(shift - arg[h]), x = exp(-arg[h]);
-          double pw = 1.0, acc = 0.0;
+          double pw = 1.0, acc = 0.0, dacc = 0.0;
 #pragma unroll
           for (int k = 1; k <= 3; ++k) {
             acc += k <= rc[h] ? pw : 0.0;
+            if (GRAD) dacc += k <= rc[h] ? (double)k * pw : 0.0;
             pw *= x;
           }
           for (int k = 4; k <= rc[h]; ++k) {
             acc += pw;
+            if (GRAD) dacc += (double)k * pw;
             pw *= x;
           }
           S[h] = rc[h] > 0 ? t1 * acc : 0.0;
+          dS[h] = (GRAD && rc[h] > 0) ? -2.0 * P.wf * dd[h] * t1 * dacc : 0.0;
         }
         double norm = S[0] + S[1];
         norm += __shfl_xor_sync(0xffffffffu, norm, 2);
         norm += __shfl_xor_sync(0xffffffffu, norm, 1);
+        double dnorm = 0.0;
+        if constexpr (GRAD) {
+          dnorm = dS[0] + dS[1];
+          dnorm += __shfl_xor_sync(0xffffffffu, dnorm, 2);
+          dnorm += __shfl_xor_sync(0xffffffffu, dnorm, 1);
+        }
         const double qmod = qat + zeff;
         const bool qpos = qmod > 0.0;
         const double qinv = 1.0 / (qpos ? qmod - (double)d4_eps<T>() : 1.0);
@@ -983,8 +1000,21 @@ __global__ void __launch_bounds__(NT, MINB) small_kernel(SmallArgs<T> A) {
           const double gw = nz ? S[h] * inv : 0.0;
           wq[h] = (T)(zeta * gw);
           w0[h] = (T)(z0[h] * gw);
+          if constexpr (GRAD) {  // weights and their derivatives for the projection on the references
+            const int ar = a + 4 * h;
+            if (row && ar < NREF) {
+              const double dgw = nz ? (dS[h] - gw * dnorm) * inv : 0.0;
+              const double dzeta = -P.ga * gam * scale * zeta * qref[h] * qinv * qinv;
+              const int o = i * NREF + ar;
+              WT(WT_Q)[o] = wq[h];
+              WT(WT_0)[o] = w0[h];
+              WT(WT_ZGD)[o] = (T)(zeta * dgw);
+              WT(WT_Z0GD)[o] = (T)(z0[h] * dgw);
+              WT(WT_DZG)[o] = (T)(dzeta * gw);
+            }
+          }
         }
-        if (A.alpha_out) {  // properties mode: alpha_i = sum_a zeta gw alpha_a(0)
+        if (!GRAD && A.alpha_out) {  // properties mode: alpha_i = sum_a zeta gw alpha_a(0)
           T al = wq[0] * tab.alpha0[za[0]] + (a + 4 < NREF ? wq[1] * tab.alpha0[za[1]] : T(0));
           al += __shfl_xor_sync(0xffffffffu, al, 2);
           al += __shfl_xor_sync(0xffffffffu, al, 1);
