@@ -1,5 +1,6 @@
 #!/bin/bash
-# multi-GPU pass: bench under torchrun (the driver's launch line), reference arm under torchrun, cross-rank test
+# Multi-GPU pass (gpurun --gpus N -- 'bash tools/round_multi.sh N'): bench under torchrun (the driver's launch
+# line), reference arm under torchrun, cross-rank consistency of the large-system path
 N=${1:-2}
 out=gpurun_out
 mkdir -p $out
