@@ -148,14 +148,25 @@ def zeta(gam: Tensor, qref: Tensor, qmod: Tensor, ga: float, dtype) -> Tensor:
     )
 
 
-def reference_alpha(numbers: Tensor, ga=GA_DEFAULT, gc=GC_DEFAULT, dtype=F64) -> Tensor:
+def _ref_charge_tables(ref_charges: str):
+    """(refq, refh): EEQ (``reference/d4/charge_eeq.py``: clsq, clsh) or GFN2-xTB reference charges
+    (``reference/d4/charge_gfn2.py``: refq, refh), selected at model/d4.py:142-149 and model/base.py:388-399."""
+    t = _tables()
+    if ref_charges == "eeq":
+        return t["clsq"], t["clsh"]
+    if ref_charges == "gfn2":
+        return t["gfn2_refq"], t["gfn2_refh"]
+    raise ValueError(f"Unknown reference charges: {ref_charges}")
+
+
+def reference_alpha(numbers: Tensor, ga=GA_DEFAULT, gc=GC_DEFAULT, dtype=F64, ref_charges="eeq") -> Tensor:
     """model/base.py:367-418 -> (..., nat, 7, 23), clamped at 0."""
     t = _tables()
     refsys = t["refsys"][numbers]
     ascale = t["refascale"].to(dtype)[numbers]
     alpha0 = t["refalpha"].to(dtype)[numbers]
     scount = t["refscount"].to(dtype)[numbers]
-    clsh = t["clsh"].to(dtype)[numbers]
+    clsh = _ref_charge_tables(ref_charges)[1].to(dtype)[numbers]
     zs = t["zeff"][refsys]
     gs = t["gam"].to(dtype)[refsys] * gc
     z = torch.where(
@@ -166,9 +177,9 @@ def reference_alpha(numbers: Tensor, ga=GA_DEFAULT, gc=GC_DEFAULT, dtype=F64) ->
     return torch.where(a > 0.0, a, torch.zeros((), dtype=dtype))
 
 
-def reference_c6(numbers: Tensor, ga=GA_DEFAULT, gc=GC_DEFAULT, dtype=F64) -> Tensor:
+def reference_c6(numbers: Tensor, ga=GA_DEFAULT, gc=GC_DEFAULT, dtype=F64, ref_charges="eeq") -> Tensor:
     """model/base.py:420-431 + utils.py:33-94 -> (..., nat, nat, 7, 7)."""
-    a = reference_alpha(numbers, ga, gc, dtype)
+    a = reference_alpha(numbers, ga, gc, dtype, ref_charges)
     w = torch.tensor(_CP_WEIGHTS, dtype=dtype)
     thopi = 3.0 / 3.141592653589793238462643383279502884197
     return thopi * torch.einsum("w,...iaw,...jbw->...ijab", w, a, a)
@@ -195,11 +206,11 @@ def _gauss_weights(dcn: Tensor, wf: Tensor, refc: Tensor, refcn: Tensor, dtype) 
     return torch.where(bad, onehot, gw)
 
 
-def _zeta_atoms(numbers: Tensor, q: Tensor, ga: float, gc: float, dtype) -> Tensor:
+def _zeta_atoms(numbers: Tensor, q: Tensor, ga: float, gc: float, dtype, ref_charges="eeq") -> Tensor:
     """model/d4.py:219-225: zeta(gam*gc, refq + zeff, q + zeff) masked by refc>0."""
     t = _tables()
     refc = t["refc"][numbers]
-    refq = t["clsq"].to(dtype)[numbers]
+    refq = _ref_charge_tables(ref_charges)[0].to(dtype)[numbers]
     zeff = t["zeff"][numbers].unsqueeze(-1)
     gam = t["gam"].to(dtype)[numbers].unsqueeze(-1) * gc
     z = zeta(gam, refq + zeff, q.unsqueeze(-1) + zeff, ga, dtype)
@@ -207,7 +218,7 @@ def _zeta_atoms(numbers: Tensor, q: Tensor, ga: float, gc: float, dtype) -> Tens
 
 
 def weight_references_d4(
-    numbers: Tensor, cn: Tensor, q: Tensor | None, ga=GA_DEFAULT, gc=GC_DEFAULT, wf=WF_DEFAULT
+    numbers: Tensor, cn: Tensor, q: Tensor | None, ga=GA_DEFAULT, gc=GC_DEFAULT, wf=WF_DEFAULT, ref_charges="eeq"
 ) -> Tensor:
     """model/d4.py:103-228 -> zeta * gw, shape (..., nat, 7)."""
     t = _tables()
@@ -232,11 +243,11 @@ def weight_references_d4(
         refcn == maxcn, torch.ones((), dtype=dtype), torch.zeros((), dtype=dtype)
     )
     gw = torch.where(bad, onehot, gw)
-    return _zeta_atoms(numbers, q, ga, gc, dtype) * gw
+    return _zeta_atoms(numbers, q, ga, gc, dtype, ref_charges) * gw
 
 
 def weight_references_d4s(
-    numbers: Tensor, cn: Tensor, q: Tensor | None, ga=GA_DEFAULT, gc=GC_DEFAULT
+    numbers: Tensor, cn: Tensor, q: Tensor | None, ga=GA_DEFAULT, gc=GC_DEFAULT, ref_charges="eeq"
 ) -> Tensor:
     """model/d4s.py:109-248 -> (..., nat_m, nat_n, 7): weights of atom n as seen
     by partner m; ``arg[m,n,a] = -(cn_n - refcn_{n,a})^2 * wf[n,m]`` (:191-198)."""
@@ -251,7 +262,7 @@ def weight_references_d4s(
     dcn = cn.to(F64).unsqueeze(-1).unsqueeze(-3) - refcn  # [m, n, a]
     wf_mn = wf.transpose(-1, -2).unsqueeze(-1)  # wf[n, m] placed at [m, n]
     gw = _gauss_weights(dcn, wf_mn.to(F64), refc, refcn, dtype)
-    z = _zeta_atoms(numbers, q, ga, gc, dtype).unsqueeze(-3)
+    z = _zeta_atoms(numbers, q, ga, gc, dtype, ref_charges).unsqueeze(-3)
     return z * gw
 
 
@@ -365,6 +376,7 @@ def dftd4(
     parts: bool = False,
     centres: Tensor | None = None,
     cn: Tensor | None = None,
+    ref_charges: str = "eeq",
 ):
     """``tad_dftd4.dftd4`` (disp.py:44-146 -> dispersion/base.py:285-431) with
     explicit charges: TwoBodyTerm(Rational, q-dependent) + D4ATMApprox(Zero,
@@ -376,16 +388,16 @@ def dftd4(
     if q.shape != numbers.shape:
         raise ValueError("Shape of atomic charges is not consistent with atomic numbers.")
     r4r2 = t["r4r2"].to(dtype)[numbers]
-    rc6 = reference_c6(numbers, ga, gc, dtype)
+    rc6 = reference_c6(numbers, ga, gc, dtype, ref_charges)
     if cn is None:  # test helper: coordination numbers as an independent variable
         cn = cn_d4(numbers, positions)
 
     if model == "d4":
-        c6q = atomic_c6_d4(rc6, weight_references_d4(numbers, cn, q, ga, gc, wf))
-        c60 = atomic_c6_d4(rc6, weight_references_d4(numbers, cn, None, ga, gc, wf))
+        c6q = atomic_c6_d4(rc6, weight_references_d4(numbers, cn, q, ga, gc, wf, ref_charges))
+        c60 = atomic_c6_d4(rc6, weight_references_d4(numbers, cn, None, ga, gc, wf, ref_charges))
     elif model == "d4s":
-        c6q = atomic_c6_d4s(rc6, weight_references_d4s(numbers, cn, q, ga, gc))
-        c60 = atomic_c6_d4s(rc6, weight_references_d4s(numbers, cn, None, ga, gc))
+        c6q = atomic_c6_d4s(rc6, weight_references_d4s(numbers, cn, q, ga, gc, ref_charges))
+        c60 = atomic_c6_d4s(rc6, weight_references_d4s(numbers, cn, None, ga, gc, ref_charges))
     else:
         raise ValueError(f"Unknown model '{model}'.")
 

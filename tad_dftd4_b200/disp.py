@@ -54,11 +54,11 @@ def last_launch_count() -> int:
 # per-device engine: tables handle + workspace cache
 # ---------------------------------------------------------------------------
 class _Engine:
-    _cache: dict[tuple[int, float, float], "_Engine"] = {}
+    _cache: dict[tuple[int, float, float, str], "_Engine"] = {}
 
-    def __init__(self, device: torch.device, ga: float, gc: float):
+    def __init__(self, device: torch.device, ga: float, gc: float, ref_charges: str = "eeq"):
         lib = _lib.load()
-        tab = build_tables(ga, gc)
+        tab = build_tables(ga, gc, ref_charges)
         f64 = np.ascontiguousarray(tab.f64_blob())
         i32 = np.ascontiguousarray(tab.i32_blob())
         handle = C.c_void_p()
@@ -77,12 +77,12 @@ class _Engine:
         self._ws_by_stream: dict[int, Tensor] = {}
 
     @classmethod
-    def get(cls, device: torch.device, ga: float, gc: float) -> "_Engine":
+    def get(cls, device: torch.device, ga: float, gc: float, ref_charges: str = "eeq") -> "_Engine":
         index = device.index if device.index is not None else torch.cuda.current_device()
-        key = (index, float(ga), float(gc))
+        key = (index, float(ga), float(gc), ref_charges)
         eng = cls._cache.get(key)
         if eng is None:
-            eng = cls._cache[key] = cls(device, ga, gc)
+            eng = cls._cache[key] = cls(device, ga, gc, ref_charges)
         return eng
 
     def large_workspace(self, need: int) -> Tensor:
@@ -424,8 +424,23 @@ def _flatten_param(param: Param, cutoff: Cutoff | None, model_id: int, wf: float
     return par
 
 
-def _resolve_model(model: Any) -> tuple[int, float, float, float]:
-    """-> (model id, ga, gc, wf)"""
+class _ModelSpec(tuple):
+    """(model id, ga, gc, wf) -- unpacks like the plain tuple -- plus ``ref_charges``."""
+
+    ref_charges = "eeq"
+
+
+def _resolve_model(model: Any) -> "_ModelSpec":
+    """-> (model id, ga, gc, wf), with ``.ref_charges`` ("eeq" | "gfn2")"""
+    spec = _ModelSpec(_resolve_model_tuple(model))
+    ref = getattr(model, "ref_charges", "eeq") if not isinstance(model, str) else "eeq"
+    if ref not in ("eeq", "gfn2"):
+        raise ValueError(f"Unknown reference charges: {ref}")
+    spec.ref_charges = ref
+    return spec
+
+
+def _resolve_model_tuple(model: Any) -> tuple[int, float, float, float]:
     if isinstance(model, str):
         key = model.casefold()
         if key not in _ALLOWED_MODELS:
@@ -437,8 +452,6 @@ def _resolve_model(model: Any) -> tuple[int, float, float, float]:
         raise NotImplementedError(f"model '{key}' is outside the accelerated D4 hot path")
     name = type(model).__name__
     if name in ("D4Model", "D4SModel"):
-        if getattr(model, "ref_charges", "eeq") != "eeq":
-            raise NotImplementedError("only ref_charges='eeq' is accelerated")
         wf = float(getattr(model, "wf", defaults.WF_DEFAULT))
         if name == "D4SModel" and wf != defaults.WF_DEFAULT:
             # the D4S kernels weight with the pair table wfpair (model/d4s.py:61-67); the reference
@@ -519,7 +532,8 @@ def dftd4(
             f"Shape of positions ({positions.shape}) is not consistent "
             f"with atomic numbers ({numbers.shape}).",
         )
-    model_id, ga, gc, wf = _resolve_model(model)
+    spec = _resolve_model(model)
+    model_id, ga, gc, wf = spec
     for name, val in (("covalent radii", rcov), ("expectation values r4r2", r4r2)):
         if val is not None and numbers.shape != val.shape:
             raise ValueError(
@@ -563,7 +577,10 @@ def dftd4(
     par = _flatten_param(param, cutoff, model_id, wf)
     ptens = _param_tensors(param)
 
-    engine = _Engine.get(positions.device, ga, gc)
+    if spec.ref_charges == "gfn2" and _CHECKS and numbers.numel() and int(numbers.max()) > 86:
+        # the reference indexes its (87, 7) GFN2 tables with the atomic numbers (model/d4.py:154)
+        raise IndexError("ref_charges='gfn2' is tabulated for Z <= 86")
+    engine = _Engine.get(positions.device, ga, gc, spec.ref_charges)
     nat = numbers.shape[-1]
     batch_shape = numbers.shape[:-1]
     num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
@@ -589,7 +606,8 @@ def dftd4(
             rows: list[Tensor | None] = [None] * num2.shape[0]
             small = [b for b in range(num2.shape[0]) if b not in set(big)]
             for b in big:
-                rows[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff, model=(ga, gc, wf))
+                rows[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff,
+                                      model=(ga, gc, wf, spec.ref_charges))
             if small:
                 # compact the small structures to the front of the atom axis
                 sel = torch.tensor(small, device=num2.device)
@@ -642,10 +660,11 @@ def dftd4_host(
         )
     if positions.device.type != "cpu" or positions.dtype not in (torch.float64, torch.float32):
         raise ValueError("dftd4_host expects float32/float64 CPU tensors")
-    model_id, ga, gc, wf = _resolve_model(model)
+    spec = _resolve_model(model)
+    model_id, ga, gc, wf = spec
     par = _flatten_param(param, cutoff, model_id, wf)
     dev = torch.device("cuda", device) if isinstance(device, int) else device
-    engine = _Engine.get(dev, ga, gc)
+    engine = _Engine.get(dev, ga, gc, spec.ref_charges)
     nat = numbers.shape[-1]
     if nat > _small_limit(engine, positions.dtype, bool(with_gradient), model_id):
         raise NotImplementedError("dftd4_host handles batches of small structures; use dftd4 for large ones")

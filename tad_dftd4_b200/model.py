@@ -26,8 +26,6 @@ class _Model:
                  wf=None, ref_charges: str = "eeq", rc6=None, device=None, dtype=None) -> None:  # fmt: skip
         if ref_charges not in ("eeq", "gfn2"):
             raise ValueError(f"Unknown reference charges: {ref_charges}")
-        if ref_charges != "eeq":
-            raise NotImplementedError("only ref_charges='eeq' is accelerated")
         if rc6 is not None:
             raise NotImplementedError("user-supplied rc6 tensors are outside the accelerated hot path")
         self.numbers = numbers
@@ -84,7 +82,7 @@ class _Model:
                 "tad_dftd4_b200 runs on B200 GPUs only (no CPU fallback): construct the model with "
                 f"numbers on a CUDA device (got {numbers.device})."
             )
-        engine = _Engine.get(numbers.device, self.ga, self.gc)
+        engine = _Engine.get(numbers.device, self.ga, self.gc, self.ref_charges)
         par = _lib.Params()
         par.wf = self.wf
         par.model = 1 if self._key == "d4s" else 0

@@ -92,9 +92,18 @@ class ElementTables:
         ("maxcn_ref", NELEM),  # index of the largest reference CN (NaN fallback)
     )
 
-    def __init__(self, ga: float, gc: float):
+    def __init__(self, ga: float, gc: float, ref_charges: str = "eeq"):
         raw = _raw()
         self.ga, self.gc = float(ga), float(gc)
+        # reference charges of the model (model/base.py:388-399, model/d4.py:142-149): EEQ (default) or GFN2-xTB
+        if ref_charges not in ("eeq", "gfn2"):
+            raise ValueError(f"Unknown reference charges: {ref_charges}")
+        self.ref_charges = ref_charges
+        ref_q, ref_h = raw["clsq"], raw["clsh"]
+        if ref_charges == "gfn2":  # tabulated for Z <= 86 (reference/d4/charge_gfn2.py); zero rows beyond
+            ref_q, ref_h = np.zeros_like(ref_q), np.zeros_like(ref_h)
+            ref_q[: raw["gfn2_refq"].shape[0]] = raw["gfn2_refq"]
+            ref_h[: raw["gfn2_refh"].shape[0]] = raw["gfn2_refh"]
         z = np.arange(NELEM)
         gam = np.asarray(_el.GAM, dtype=np.float64)
         zeff = np.asarray(_el.ZEFF, dtype=np.float64)
@@ -107,7 +116,7 @@ class ElementTables:
         self.zeff = zeff[:NELEM].copy()
         self.refcn = raw["refcovcn"].copy()
         self.refc = raw["refc"].astype(np.int32)
-        self.refq = raw["clsq"] + self.zeff[:, None]
+        self.refq = ref_q + self.zeff[:, None]
         mask = self.refc > 0
         self.zeta0 = np.where(
             mask, _zeta(self.gamgc[:, None], self.refq, self.zeff[:, None], ga), 0.0
@@ -121,7 +130,7 @@ class ElementTables:
         refsys = raw["refsys"].astype(np.int64)
         zs = zeff[refsys]
         gs = gam[refsys] * gc
-        zsec = np.where(refsys > 0, _zeta(gs, zs, raw["clsh"] + zs, ga), 0.0)
+        zsec = np.where(refsys > 0, _zeta(gs, zs, ref_h + zs, ga), 0.0)
         sec = raw["secscale"][refsys] * raw["secalpha"][refsys] * zsec[..., None]
         alpha = raw["refascale"][..., None] * (raw["refalpha"] - raw["refscount"][..., None] * sec)
         self.alpha = np.where(alpha > 0.0, alpha, 0.0)  # (104, 7, 23)
@@ -150,5 +159,5 @@ class ElementTables:
 
 
 @lru_cache(maxsize=8)
-def build_tables(ga: float = 3.0, gc: float = 2.0) -> ElementTables:
-    return ElementTables(ga, gc)
+def build_tables(ga: float = 3.0, gc: float = 2.0, ref_charges: str = "eeq") -> ElementTables:
+    return ElementTables(ga, gc, ref_charges)

@@ -6,7 +6,8 @@ into the two data files the package ships:
 * ``tad_dftd4_b200/data/d4_reference.npz`` -- literal parameter arrays of
   ``/root/reference/src/tad_dftd4/reference/d4/params.py`` (refcovcn, refalpha,
   refascale, refscount, refsys, refc, secscale, secalpha),
-  ``reference/d4/charge_eeq.py`` (clsq, clsh), ``data/r4r2.py`` (already
+  ``reference/d4/charge_eeq.py`` (clsq, clsh), ``reference/d4/charge_gfn2.py`` (refq, refh),
+  ``data/r4r2.py`` (already
   transformed, ``r4r2.py:83-88``) and ``data/wfpair.py`` (119x119, D4S).
 * ``tad_dftd4_b200/data/d4_damping.json`` -- the rational-damping parameter
   blocks of ``damping/parameters/d4.toml``.
@@ -49,6 +50,7 @@ def main() -> None:
 
     params = _load("_ref_params", REF / "reference/d4/params.py")
     ceeq = _load("_ref_charge_eeq", REF / "reference/d4/charge_eeq.py")
+    cgfn = _load("_ref_charge_gfn2", REF / "reference/d4/charge_gfn2.py")
     r4r2 = _load("_ref_r4r2", REF / "data/r4r2.py")
     wfp = _load("_ref_wfpair", REF / "data/wfpair.py")
 
@@ -63,6 +65,9 @@ def main() -> None:
         "secalpha": params.secalpha.numpy().astype(np.float64),
         "clsq": ceeq.clsq.numpy().astype(np.float64),
         "clsh": ceeq.clsh.numpy().astype(np.float64),
+        # ref_charges="gfn2" (model/base.py:393-397, model/d4.py:145-147)
+        "gfn2_refq": cgfn.refq.numpy().astype(np.float64),
+        "gfn2_refh": cgfn.refh.numpy().astype(np.float64),
         # r4r2.py:83-88 evaluated in float64
         "r4r2": r4r2.R4R2(dtype=torch.float64).numpy(),
         "wfpair": wfp.WFPAIR(dtype=torch.float64).numpy(),
