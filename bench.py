@@ -726,23 +726,37 @@ def main():
 
 
 def leave() -> None:
-    """End the process after the JSON line is out.
+    """Let the autograd worker threads go idle, then exit the interpreter normally.
 
-    A plain interpreter exit intermittently aborts here ("terminate called without an active
-    exception", SIGABRT from the C++ runtime during the teardown of the loaded libraries, roughly one
-    default run in three on the GPU boxes) -- after the result has been printed, but with exit code 134.
-    So the exit-time work of the INTERPRETER is done explicitly while it is still healthy -- non-daemon
-    threads joined, every registered ``atexit`` hook run (including any the harness installed to record
-    the shared libraries this process mapped), streams flushed -- and the process then ends without the
-    static destruction phase.  ``D4_BENCH_EXIT=normal`` restores the plain exit (diagnosis)."""
+    A plain exit right after the last backward pass aborted now and then ("terminate called without an
+    active exception", exit code 134 after the JSON line was out; 2 of 22 runs in
+    ``profiles/r02_exit_probe.txt``).  The C++ stack of the aborting thread
+    (``tools/probes/abort_trace.c``) names the cause: an autograd ENGINE worker thread
+    (``torch::autograd::Engine::thread_main``) is still releasing the buffers of the last graph task --
+    tensors created in a Python ``autograd.Function.backward`` carry a Python object, so dropping them
+    needs the GIL (``TensorImpl::decref_pyobject`` -> ``PyEval_RestoreThread``) -- while the main thread,
+    which was woken as soon as the last task completed, runs on to ``Py_Finalize`` holding the GIL.  A
+    thread that asks for the GIL of a finalizing interpreter is ended with ``pthread_exit``; its forced
+    unwind crosses a ``noexcept`` C++ frame, hence ``std::terminate``.  Giving the GIL away for a moment
+    after the last backward lets the worker finish and park on its (C++) ready queue, where finalization
+    does not touch it.  No ``os._exit``: every exit-time hook, static destructor and library finalizer
+    runs (``D4_BENCH_EXIT=hard`` keeps the old behaviour for diagnosis)."""
+    import gc
+    import time
+
     sys.stdout.flush()
     sys.stderr.flush()
-    if os.environ.get("D4_BENCH_EXIT", "hooks") == "normal":
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available():
+        torch.cuda.synchronize()
+    gc.collect()
+    time.sleep(0.25)  # sleeping releases the GIL
+    if os.environ.get("D4_BENCH_EXIT", "normal") != "hard":
         return
     import atexit
 
     try:
-        threading._shutdown()  # what Py_FinalizeEx does first: join non-daemon threads, threading's exit hooks
+        threading._shutdown()
     except Exception:  # noqa: BLE001
         pass
     atexit._run_exitfuncs()
@@ -755,5 +769,9 @@ if __name__ == "__main__":
     import faulthandler
 
     faulthandler.enable()  # a fatal signal during teardown leaves the Python stacks on stderr
+    if os.environ.get("D4_BENCH_ABORT_TRACE"):  # diagnosis: tools/probes/abort_trace.c (C++ stack on SIGABRT)
+        import ctypes
+
+        ctypes.CDLL(os.environ["D4_BENCH_ABORT_TRACE"]).abort_trace_install()
     main()
     leave()

@@ -7,7 +7,9 @@ is not a B200 the import / first call fails loudly.
 from __future__ import annotations
 
 import ctypes as C
+import atexit
 import os
+import time
 from pathlib import Path
 
 # D4B200_LIBRARY points at an alternative build of the same C ABI (A/B timing of kernel variants)
@@ -112,7 +114,21 @@ def load() -> C.CDLL:
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    atexit.register(_let_autograd_workers_finish)
     return lib
+
+
+def _let_autograd_workers_finish() -> None:
+    """Exit hook: give the GIL away for a moment before the interpreter finalizes.
+
+    The gradients come out of Python ``autograd.Function.backward`` methods, so the tensors the autograd
+    engine's worker thread drops after the last task of a backward pass carry Python objects, and
+    dropping them needs the GIL.  The caller of ``backward`` is woken before that; if it goes straight
+    on to interpreter exit, the worker asks for the GIL of a finalizing interpreter, is ended with
+    ``pthread_exit`` and the forced unwind through a ``noexcept`` frame calls ``std::terminate``
+    (exit code 134 after all work is done; stack in ``profiles/r02_exit_probe.txt``).  ``atexit`` hooks run
+    before the interpreter is marked as finalizing, and sleeping releases the GIL."""
+    time.sleep(0.05)
 
 
 def check(code: int, what: str) -> None:
