@@ -352,6 +352,31 @@ int d4b200_eeq_vjp_f32(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* num
                        const float* grad_q_dev, float* grad_positions_dev, int* status_dev,
                        void* stream);
 
+/* The same two calls with the factor of the bordered EEQ matrix kept between them: the charges call
+ * leaves the eliminated upper triangle, the reciprocal pivots and the raw coordination numbers of every
+ * structure in ``factor_dev`` (nbatch * d4b200_eeq_factor_doubles(nat) doubles, float64 for both I/O
+ * types), and a VJP call for the SAME numbers/positions only substitutes its right-hand side -- the
+ * backward pass of ``get_eeq_charges`` (tad_multicharge, call site
+ * /root/reference/src/tad_dftd4/dispersion/base.py:401-407) then costs no second elimination.
+ * ``factor_dev`` may be NULL (plain call). */
+size_t d4b200_eeq_factor_doubles(int nat);
+int d4b200_eeq_charges_factor_f64(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                                  const double* positions_dev, const double* charge_dev,
+                                  double cn_cutoff, double* q_dev, double* factor_dev,
+                                  int* status_dev, void* stream);
+int d4b200_eeq_charges_factor_f32(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                                  const float* positions_dev, const float* charge_dev,
+                                  double cn_cutoff, float* q_dev, double* factor_dev, int* status_dev,
+                                  void* stream);
+int d4b200_eeq_vjp_factor_f64(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                              const double* positions_dev, double cn_cutoff, const double* q_dev,
+                              const double* grad_q_dev, const double* factor_dev,
+                              double* grad_positions_dev, int* status_dev, void* stream);
+int d4b200_eeq_vjp_factor_f32(d4b200_eeq_t eeq, int nbatch, int nat, const int64_t* numbers_dev,
+                              const float* positions_dev, double cn_cutoff, const float* q_dev,
+                              const float* grad_q_dev, const double* factor_dev,
+                              float* grad_positions_dev, int* status_dev, void* stream);
+
 /* Synchronises ``stream`` and returns the device status bits recorded by the
  * last energy/gradient call that used ``workspace_dev``. */
 int d4b200_status(void* workspace_dev, void* stream, int* status_bits_out);

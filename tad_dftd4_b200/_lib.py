@@ -79,6 +79,11 @@ _SIGS = {
     "d4b200_eeq_charges_f32": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP]),
     "d4b200_eeq_vjp_f64": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),
     "d4b200_eeq_vjp_f32": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "d4b200_eeq_factor_doubles": (C.c_size_t, [C.c_int]),
+    "d4b200_eeq_charges_factor_f64": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP]),
+    "d4b200_eeq_charges_factor_f32": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP]),
+    "d4b200_eeq_vjp_factor_f64": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "d4b200_eeq_vjp_factor_f32": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
     "d4b200_status": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
     "d4b200_last_launch_count": (C.c_int, []),
     "d4b200_total_launch_count": (C.c_longlong, []),

@@ -44,6 +44,8 @@ struct EeqTables {
 };
 
 __host__ __device__ inline int eeq_ld(int nat) { return (nat + 2) | 1; }
+// doubles per structure of the saved factor: matrix rows, reciprocal pivots, raw coordination numbers
+__host__ inline size_t eeq_factor_doubles(int nat) { return (size_t)(nat + 1) * eeq_ld(nat) + 2 * (size_t)(nat + 1); }
 __host__ inline size_t eeq_smem(int nat) {
   return sizeof(double) * ((size_t)EEQ_NARR * (nat + 1) + (size_t)(nat + 1) * eeq_ld(nat));
 }
@@ -66,7 +68,8 @@ template <typename T, bool VJP, int EEQ_NT>
 __global__ void __launch_bounds__(EEQ_NT)
 eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* __restrict__ pos,
            const T* __restrict__ charge, double cutoff2, const T* __restrict__ q_in,
-           const T* __restrict__ gq, T* __restrict__ out, int* __restrict__ status) {
+           const T* __restrict__ gq, T* __restrict__ out, int* __restrict__ status,
+           double* __restrict__ fac, size_t fac_stride) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   constexpr int NW = EEQ_NT / 32, EEQ_NW = NW;
@@ -136,6 +139,14 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
   }
   __syncthreads();
 
+  // The factor of the bordered matrix does not depend on the right-hand side: the charges kernel can
+  // leave it (upper triangle after the elimination, reciprocal pivots, raw coordination numbers) in
+  // global memory, and the VJP kernel of the same geometry then only substitutes its own right-hand side.
+  double* const fb = fac ? fac + (size_t)b * fac_stride : nullptr;
+  const size_t fac_dinv = (size_t)(nat + 1) * eeq_ld(nat), fac_cn = fac_dinv + (nat + 1);
+  const bool reuse = VJP && fb != nullptr;
+  const int npair = n * (n - 1) / 2;
+  if (!reuse) {
   // ---- coordination number: ordered rows; the few near pairs of a row (r < 1.8 r0, beyond
   // which erfc/2 < 1e-17) are first compacted into a per-warp list (in the not yet used matrix
   // area) so that the expensive erfc runs once per 32 near pairs, not once per 32 pairs.
@@ -175,7 +186,6 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
   for (int c = tid; c < n; c += EEQ_NT) cnc[c] = LOG1P_EXP_CN_MAX - log1p(exp(CN_MAX - cnr[c]));
 
   // ---- Coulomb block, once per unordered pair --------------------------------------------
-  const int npair = n * (n - 1) / 2;
   for (int p = tid; p < npair; p += EEQ_NT) {
     int i, j;
     pair_of(p, i, j);
@@ -236,6 +246,25 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
     }
     __syncthreads();
   }
+  if (!VJP && fb) {
+    for (int i = warp; i < m; i += EEQ_NW)
+      for (int j = i + lane; j < m; j += 32) fb[(size_t)i * ld + j] = M[i * ld + j];
+    for (int c = tid; c < m; c += EEQ_NT) fb[fac_dinv + c] = dinv[c];
+    for (int c = tid; c < n; c += EEQ_NT) fb[fac_cn + c] = cnr[c];
+  }
+  } else {
+    for (int i = warp; i < m; i += EEQ_NW)
+      for (int j = i + lane; j < m; j += 32) M[i * ld + j] = fb[(size_t)i * ld + j];
+    for (int c = tid; c < m; c += EEQ_NT) dinv[c] = fb[fac_dinv + c];
+    for (int c = tid; c < n; c += EEQ_NT) {
+      const double cn = fb[fac_cn + c];
+      cnr[c] = cn;
+      cnc[c] = LOG1P_EXP_CN_MAX - log1p(exp(CN_MAX - cn));
+      M[c * ld + m] = (double)gq[(size_t)b * nat + idx[c]];
+    }
+    if (tid == 0) M[n * ld + m] = 0.0;
+    __syncthreads();
+  }
   // ---- back substitution: warp 0, right-hand side in registers, no block barriers -----------
   if (warp == 0) {
     constexpr int MAXC = (EEQ_MAX_NAT + 1 + 31) / 32;
@@ -244,6 +273,22 @@ eeq_kernel(EeqTables tb, int nat, const int64_t* __restrict__ numbers, const T* 
     for (int c = 0; c < MAXC; ++c) {
       const int i = lane + 32 * c;
       bb[c] = i < m ? M[i * ld + m] : 0.0;
+    }
+    if (reuse) {  // the elimination steps applied to this right-hand side: b_i -= (u_ki / u_kk) b_k, i > k
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (32 * c < m) {
+          for (int kk = 0; kk <= min(31, m - 1 - 32 * c); ++kk) {
+            const int k = 32 * c + kk;
+            const double xk = __shfl_sync(0xffffffffu, bb[c], kk) * dinv[k];
+#pragma unroll
+            for (int cc = c; cc < MAXC; ++cc) {
+              const int i = lane + 32 * cc;
+              if (i > k && i < m) bb[cc] = fma(-M[k * ld + i], xk, bb[cc]);
+            }
+          }
+        }
+      }
     }
 #pragma unroll
     for (int c = MAXC - 1; c >= 0; --c) {
@@ -405,7 +450,7 @@ int d4b200_eeq_destroy(d4b200_eeq_t h) {
 template <typename T, bool VJP>
 static int eeq_launch(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers, const T* pos,
                       const T* charge, double cutoff, const T* q, const T* gq, T* out, int* status,
-                      void* stream) {
+                      void* stream, double* factor = nullptr) {
   if (!h || nbatch < 0 || nat < 0) return D4B200_EINVAL;
   if (nbatch == 0 || nat == 0) return 0;
   if (!numbers || !pos || !out || (VJP ? (!q || !gq) : !charge)) return D4B200_EINVAL;
@@ -413,10 +458,10 @@ static int eeq_launch(d4b200_eeq_t h, int nbatch, int nat, const int64_t* number
   if (!(cutoff > 0.0)) return D4B200_EPARAM;
   if (nat <= 64)
     eeq_kernel<T, VJP, EEQ_NT_SMALL><<<nbatch, EEQ_NT_SMALL, eeq_smem(nat), (cudaStream_t)stream>>>(
-        h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status);
+        h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status, factor, eeq_factor_doubles(nat));
   else
     eeq_kernel<T, VJP, EEQ_NT_LARGE><<<nbatch, EEQ_NT_LARGE, eeq_smem(nat), (cudaStream_t)stream>>>(
-        h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status);
+        h->t, nat, numbers, pos, charge, cutoff * cutoff, q, gq, out, status, factor, eeq_factor_doubles(nat));
   ++g_eeq_launches;
   return (int)cudaGetLastError();
 }
@@ -448,6 +493,39 @@ int d4b200_eeq_vjp_f32(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbe
                        void* stream) {
   return eeq_launch<float, true>(h, nbatch, nat, numbers_dev, positions_dev, nullptr, cn_cutoff, q_dev,
                                  grad_q_dev, grad_positions_dev, status_dev, stream);
+}
+
+
+// Charges + saved factor / VJP from the saved factor (same geometry): the elimination is not repeated in the
+// backward pass.  factor_dev: nbatch * d4b200_eeq_factor_doubles(nat) doubles (may be NULL: plain call).
+size_t d4b200_eeq_factor_doubles(int nat) { return nat >= 0 && nat <= EEQ_MAX_NAT ? eeq_factor_doubles(nat) : 0; }
+int d4b200_eeq_charges_factor_f64(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                                  const double* positions_dev, const double* charge_dev, double cn_cutoff,
+                                  double* q_dev, double* factor_dev, int* status_dev, void* stream) {
+  return eeq_launch<double, false>(h, nbatch, nat, numbers_dev, positions_dev, charge_dev, cn_cutoff,
+                                   nullptr, nullptr, q_dev, status_dev, stream, factor_dev);
+}
+int d4b200_eeq_charges_factor_f32(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                                  const float* positions_dev, const float* charge_dev, double cn_cutoff,
+                                  float* q_dev, double* factor_dev, int* status_dev, void* stream) {
+  return eeq_launch<float, false>(h, nbatch, nat, numbers_dev, positions_dev, charge_dev, cn_cutoff,
+                                  nullptr, nullptr, q_dev, status_dev, stream, factor_dev);
+}
+int d4b200_eeq_vjp_factor_f64(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                              const double* positions_dev, double cn_cutoff, const double* q_dev,
+                              const double* grad_q_dev, const double* factor_dev, double* grad_positions_dev,
+                              int* status_dev, void* stream) {
+  return eeq_launch<double, true>(h, nbatch, nat, numbers_dev, positions_dev, nullptr, cn_cutoff, q_dev,
+                                  grad_q_dev, grad_positions_dev, status_dev, stream,
+                                  const_cast<double*>(factor_dev));
+}
+int d4b200_eeq_vjp_factor_f32(d4b200_eeq_t h, int nbatch, int nat, const int64_t* numbers_dev,
+                              const float* positions_dev, double cn_cutoff, const float* q_dev,
+                              const float* grad_q_dev, const double* factor_dev, float* grad_positions_dev,
+                              int* status_dev, void* stream) {
+  return eeq_launch<float, true>(h, nbatch, nat, numbers_dev, positions_dev, nullptr, cn_cutoff, q_dev,
+                                 grad_q_dev, grad_positions_dev, status_dev, stream,
+                                 const_cast<double*>(factor_dev));
 }
 
 }  // extern "C"

@@ -76,23 +76,49 @@ class _EeqEngine:
             self.status.zero_()
             raise ValueError("numbers contains an atomic number outside 1..86 (EEQ-2019; 0 = padding).")
 
-    def charges(self, numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: float) -> Tensor:
+    #: the factor of the bordered matrix is kept for the backward pass up to this many bytes per call
+    FACTOR_LIMIT = 4 << 30
+
+    def charges(self, numbers: Tensor, positions: Tensor, charge: Tensor, cutoff: float, keep_factor: bool = False):
+        """Charges; with ``keep_factor`` also the eliminated matrix of every structure (float64, opaque
+        layout of ``d4b200_eeq_charges_factor_*``) for :meth:`vjp` -- or ``None`` when it would not fit."""
         nbatch, nat = numbers.shape
         q = torch.empty((nbatch, nat), dtype=positions.dtype, device=positions.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        fn = self.lib.d4b200_eeq_charges_f64 if positions.dtype == torch.float64 else self.lib.d4b200_eeq_charges_f32
-        _lib.check(fn(self.handle, nbatch, nat, numbers.data_ptr(), positions.data_ptr(), charge.data_ptr(),
-                      float(cutoff), q.data_ptr(), self.status.data_ptr(), stream), "d4b200_eeq_charges")  # fmt: skip
+        f64 = positions.dtype == torch.float64
+        args = (self.handle, nbatch, nat, numbers.data_ptr(), positions.data_ptr(), charge.data_ptr(), float(cutoff),
+                q.data_ptr())  # fmt: skip
+        if not keep_factor:
+            fn = self.lib.d4b200_eeq_charges_f64 if f64 else self.lib.d4b200_eeq_charges_f32
+            _lib.check(fn(*args, self.status.data_ptr(), stream), "d4b200_eeq_charges")
+            self._check()
+            return q
+        per = int(self.lib.d4b200_eeq_factor_doubles(nat))
+        factor = None
+        if 0 < per * nbatch * 8 <= self.FACTOR_LIMIT:
+            factor = torch.empty((nbatch, per), dtype=torch.float64, device=positions.device)
+        fn = self.lib.d4b200_eeq_charges_factor_f64 if f64 else self.lib.d4b200_eeq_charges_factor_f32
+        _lib.check(fn(*args, factor.data_ptr() if factor is not None else None, self.status.data_ptr(), stream),
+                   "d4b200_eeq_charges_factor")  # fmt: skip
         self._check()
-        return q
+        return q, factor
 
-    def vjp(self, numbers: Tensor, positions: Tensor, cutoff: float, q: Tensor, gq: Tensor) -> Tensor:
+    def vjp(self, numbers: Tensor, positions: Tensor, cutoff: float, q: Tensor, gq: Tensor,
+            factor: Tensor | None = None) -> Tensor:  # fmt: skip
+        """``J^T gq``; with the ``factor`` kept by :meth:`charges` for the same geometry the matrix is not
+        eliminated again."""
         nbatch, nat = numbers.shape
         gpos = torch.empty_like(positions)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        fn = self.lib.d4b200_eeq_vjp_f64 if positions.dtype == torch.float64 else self.lib.d4b200_eeq_vjp_f32
-        _lib.check(fn(self.handle, nbatch, nat, numbers.data_ptr(), positions.data_ptr(), float(cutoff),
-                      q.data_ptr(), gq.data_ptr(), gpos.data_ptr(), None, stream), "d4b200_eeq_vjp")  # fmt: skip
+        f64 = positions.dtype == torch.float64
+        head = (self.handle, nbatch, nat, numbers.data_ptr(), positions.data_ptr(), float(cutoff), q.data_ptr(),
+                gq.data_ptr())  # fmt: skip
+        if factor is None:
+            fn = self.lib.d4b200_eeq_vjp_f64 if f64 else self.lib.d4b200_eeq_vjp_f32
+            _lib.check(fn(*head, gpos.data_ptr(), None, stream), "d4b200_eeq_vjp")
+        else:
+            fn = self.lib.d4b200_eeq_vjp_factor_f64 if f64 else self.lib.d4b200_eeq_vjp_factor_f32
+            _lib.check(fn(*head, factor.data_ptr(), gpos.data_ptr(), None, stream), "d4b200_eeq_vjp_factor")
         return gpos
 
 
@@ -101,7 +127,10 @@ class _EeqFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, positions: Tensor, numbers: Tensor, charge: Tensor, cutoff: float, engine: _EeqEngine):
-        q = engine.charges(numbers, positions, charge, cutoff)
+        if ctx.needs_input_grad[0]:  # the backward pass reuses the eliminated matrix
+            q, ctx.factor = engine.charges(numbers, positions, charge, cutoff, keep_factor=True)
+        else:
+            q, ctx.factor = engine.charges(numbers, positions, charge, cutoff), None
         ctx.save_for_backward(positions, numbers, q)
         ctx.cutoff = cutoff
         ctx.engine = engine
@@ -114,7 +143,7 @@ class _EeqFunction(torch.autograd.Function):
         if torch.is_grad_enabled():  # create_graph=True: keep the VJP on the tape (second derivatives)
             return _EeqVjp.apply(gq, positions, numbers, q, ctx.charge, ctx.cutoff, ctx.engine), None, None, None, None
         with torch.no_grad():
-            gpos = ctx.engine.vjp(numbers, positions, ctx.cutoff, q, gq.contiguous())
+            gpos = ctx.engine.vjp(numbers, positions, ctx.cutoff, q, gq.contiguous(), ctx.factor)
         return gpos, None, None, None, None
 
 

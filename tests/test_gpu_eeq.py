@@ -175,3 +175,37 @@ def test_total_charge_argument_types():
     for e in results:
         assert e.shape == numbers.shape and bool((e < 0).all())
         assert torch.allclose(e, results[-1])
+
+
+@pytest.mark.parametrize("dtype,tol", [(F64, 1e-12), (torch.float32, 2e-5)])
+def test_vjp_from_the_saved_factor_equals_the_plain_vjp(dtype, tol):
+    """d4b200_eeq_charges_factor_* / d4b200_eeq_vjp_factor_*: the backward pass substitutes its right-hand side
+    into the matrix the forward pass eliminated; same result as eliminating again."""
+    from tad_dftd4_b200 import eeq as deeq
+
+    numbers, positions, _ = orc.organic_batch([1, 2, 31, 64, 33, 100, 128, 7], seed=11)
+    # padding inside the atom axis of one structure
+    numbers[2, 5] = 0
+    n, p = numbers.to(DEV), positions.to(DEV, dtype)
+    charge = torch.tensor([0.0, 1.0, -1.0, 0.0, 2.0, 0.0, 0.0, -1.0], dtype=dtype, device=DEV)
+    eng = deeq._EeqEngine.get(DEV)
+    q_plain = eng.charges(n, p, charge, 25.0)
+    q, factor = eng.charges(n, p, charge, 25.0, keep_factor=True)
+    assert factor is not None and factor.dtype == F64 and torch.equal(q, q_plain)
+    gq = torch.randn(q.shape, dtype=dtype, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    g_plain = eng.vjp(n, p, 25.0, q, gq)
+    g_fac = eng.vjp(n, p, 25.0, q, gq, factor)
+    scale = max(1.0, g_plain.abs().max().item())
+    assert (g_fac - g_plain).abs().max().item() < tol * scale
+    assert (g_fac[numbers.to(DEV) == 0] == 0).all()
+    # over the memory limit the forward pass keeps nothing and the backward pass eliminates again
+    old = deeq._EeqEngine.FACTOR_LIMIT
+    deeq._EeqEngine.FACTOR_LIMIT = 1024
+    try:
+        q2, none = eng.charges(n, p, charge, 25.0, keep_factor=True)
+        assert none is None and torch.equal(q2, q_plain)
+        pos = p.clone().requires_grad_(True)
+        (g_auto,) = torch.autograd.grad((deeq.get_eeq_charges(n, pos, charge) * gq).sum(), pos)
+        assert (g_auto - g_plain).abs().max().item() < tol * scale
+    finally:
+        deeq._EeqEngine.FACTOR_LIMIT = old

@@ -38,4 +38,10 @@ for name, sizes in (("C2 4096 x 20-60", rng.integers(20, 61, 4096)), ("C3 1024 x
     gq = torch.randn_like(q)
     t1 = timed(lambda: eng.charges(numbers, positions, charge, 25.0))
     t2 = timed(lambda: eng.vjp(numbers, positions, 25.0, q, gq))
-    print(f"{name:18s} charges {t1 * 1e3:8.1f} us   vjp {t2 * 1e3:8.1f} us   sum(q) max {float(q.sum(-1).abs().max()):.1e}")
+    line = f"{name:18s} charges {t1 * 1e3:8.1f} us   vjp {t2 * 1e3:8.1f} us"
+    if hasattr(eng.lib, "d4b200_eeq_vjp_factor_f64"):
+        _, factor = eng.charges(numbers, positions, charge, 25.0, keep_factor=True)
+        t3 = timed(lambda: eng.charges(numbers, positions, charge, 25.0, keep_factor=True))
+        t4 = timed(lambda: eng.vjp(numbers, positions, 25.0, q, gq, factor))
+        line += f"   charges+factor {t3 * 1e3:8.1f} us   vjp from factor {t4 * 1e3:8.1f} us"
+    print(line)

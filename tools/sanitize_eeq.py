@@ -18,5 +18,8 @@ for sizes in ([1, 2, 5, 31, 32, 33, 40, 63, 64], [3, 65, 100, 128, 97], [160, 1,
         eng = eeq._EeqEngine.get(dev)
         q = eng.charges(n, p, charge, 25.0)
         g = eng.vjp(n, p, 25.0, q, torch.ones_like(q))
+        q, factor = eng.charges(n, p, charge, 25.0, keep_factor=True)
+        g2 = eng.vjp(n, p, 25.0, q, torch.ones_like(q), factor)
+        assert float((g - g2).abs().max()) < 1e-4
         print(sizes, dtype, float(q.sum().abs()), float(g.abs().max()))
 torch.cuda.synchronize()
