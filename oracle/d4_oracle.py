@@ -377,10 +377,12 @@ def dftd4(
     centres: Tensor | None = None,
     cn: Tensor | None = None,
     ref_charges: str = "eeq",
+    c9: str = "approx",
 ):
     """``tad_dftd4.dftd4`` (disp.py:44-146 -> dispersion/base.py:285-431) with
     explicit charges: TwoBodyTerm(Rational, q-dependent) + D4ATMApprox(Zero,
-    q-independent, BJ radii, c9 = sqrt|c6 c6 c6|)."""
+    q-independent, BJ radii, c9 = sqrt|c6 c6 c6|).  ``c9="exact"``: ``DispD4Exact``
+    (dispersion/d4.py:67-84) -- the same two-body term + D4ATMExact (Casimir-Polder C9)."""
     t = _tables()
     dtype = positions.dtype
     if numbers.shape != positions.shape[:-1]:
@@ -408,15 +410,28 @@ def dftd4(
     radii = param["a1"] * torch.sqrt(
         torch.clamp(3.0 * r4r2.unsqueeze(-1) * r4r2.unsqueeze(-2), min=eps)
     ) + param["a2"]
-    c9 = torch.sqrt(
-        torch.clamp(
-            torch.abs(c60.unsqueeze(-1) * c60.unsqueeze(-2) * c60.unsqueeze(-3)), min=eps
+    if c9 == "approx":
+        c9t = torch.sqrt(
+            torch.clamp(
+                torch.abs(c60.unsqueeze(-1) * c60.unsqueeze(-2) * c60.unsqueeze(-3)), min=eps
+            )
         )
-    )
+    elif c9 == "exact":
+        # threebody.py:276-302: weighted polarizabilities (model/d4.py:291-307) of the q = 0 weights,
+        # integrated over the 23 nodes (utils.py:155-212, trapzd_atm: same nodes and 3/pi as trapzd)
+        if model != "d4":
+            raise ValueError("exact C9 restated for model='d4' only")
+        w0 = weight_references_d4(numbers, cn, None, ga, gc, wf, ref_charges)
+        aiw = torch.einsum("...nr,...nrw->...nw", w0, reference_alpha(numbers, ga, gc, dtype, ref_charges))
+        tw = torch.tensor(_CP_WEIGHTS, dtype=dtype)
+        thopi = 3.0 / 3.141592653589793238462643383279502884197
+        c9t = thopi * torch.einsum("w,...iw,...jw,...kw->...ijk", tw, aiw, aiw, aiw)
+    else:
+        raise ValueError(f"Unknown C9 flavour '{c9}'.")
     e3 = atm_dispersion(
         numbers,
         positions,
-        c9,
+        c9t,
         radii,
         disp3,
         s9=_p(param, "s9", S9_DEFAULT),

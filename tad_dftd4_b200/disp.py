@@ -54,11 +54,12 @@ def last_launch_count() -> int:
 # per-device engine: tables handle + workspace cache
 # ---------------------------------------------------------------------------
 class _Engine:
-    _cache: dict[tuple[int, float, float, str], "_Engine"] = {}
+    _cache: dict[tuple[int, float, float, str, int | None], "_Engine"] = {}
 
-    def __init__(self, device: torch.device, ga: float, gc: float, ref_charges: str = "eeq"):
+    def __init__(self, device: torch.device, ga: float, gc: float, ref_charges: str = "eeq",
+                 c9_frequency: int | None = None):  # fmt: skip
         lib = _lib.load()
-        tab = build_tables(ga, gc, ref_charges)
+        tab = build_tables(ga, gc, ref_charges, c9_frequency)
         f64 = np.ascontiguousarray(tab.f64_blob())
         i32 = np.ascontiguousarray(tab.i32_blob())
         handle = C.c_void_p()
@@ -77,12 +78,13 @@ class _Engine:
         self._ws_by_stream: dict[int, Tensor] = {}
 
     @classmethod
-    def get(cls, device: torch.device, ga: float, gc: float, ref_charges: str = "eeq") -> "_Engine":
+    def get(cls, device: torch.device, ga: float, gc: float, ref_charges: str = "eeq",
+            c9_frequency: int | None = None) -> "_Engine":  # fmt: skip
         index = device.index if device.index is not None else torch.cuda.current_device()
-        key = (index, float(ga), float(gc), ref_charges)
+        key = (index, float(ga), float(gc), ref_charges, c9_frequency)
         eng = cls._cache.get(key)
         if eng is None:
-            eng = cls._cache[key] = cls(device, ga, gc, ref_charges)
+            eng = cls._cache[key] = cls(device, ga, gc, ref_charges, c9_frequency)
         return eng
 
     def large_workspace(self, need: int) -> Tensor:
@@ -425,13 +427,30 @@ def _flatten_param(param: Param, cutoff: Cutoff | None, model_id: int, wf: float
 
 
 class _ModelSpec(tuple):
-    """(model id, ga, gc, wf) -- unpacks like the plain tuple -- plus ``ref_charges``."""
+    """(model id, ga, gc, wf) -- unpacks like the plain tuple -- plus ``ref_charges`` and ``c9_frequency``."""
 
     ref_charges = "eeq"
+    c9_frequency: int | None = None
+
+
+class _FrequencySlice:
+    """A model restricted to one Casimir-Polder node of the exact C9 (``tables.ElementTables``); used by
+    ``dispersion.D4ATMExact`` only."""
+
+    def __init__(self, model: Any, frequency: int):
+        self.model, self.frequency = model, int(frequency)
 
 
 def _resolve_model(model: Any) -> "_ModelSpec":
-    """-> (model id, ga, gc, wf), with ``.ref_charges`` ("eeq" | "gfn2")"""
+    """-> (model id, ga, gc, wf), with ``.ref_charges`` ("eeq" | "gfn2") and ``.c9_frequency``"""
+    if isinstance(model, _FrequencySlice):
+        spec = _resolve_model(model.model)
+        if spec[0] != 0:
+            # the reference averages the pair-resolved D4S weights over the partners here
+            # (model/d4s.py:292-316); not provided
+            raise NotImplementedError("the exact C9 (D4ATMExact) is accelerated for model='d4' only")
+        spec.c9_frequency = model.frequency
+        return spec
     spec = _ModelSpec(_resolve_model_tuple(model))
     ref = getattr(model, "ref_charges", "eeq") if not isinstance(model, str) else "eeq"
     if ref not in ("eeq", "gfn2"):
@@ -580,7 +599,7 @@ def dftd4(
     if spec.ref_charges == "gfn2" and _CHECKS and numbers.numel() and int(numbers.max()) > 86:
         # the reference indexes its (87, 7) GFN2 tables with the atomic numbers (model/d4.py:154)
         raise IndexError("ref_charges='gfn2' is tabulated for Z <= 86")
-    engine = _Engine.get(positions.device, ga, gc, spec.ref_charges)
+    engine = _Engine.get(positions.device, ga, gc, spec.ref_charges, spec.c9_frequency)
     nat = numbers.shape[-1]
     batch_shape = numbers.shape[:-1]
     num2 = numbers.reshape(-1, nat).to(torch.int64).contiguous()
@@ -607,7 +626,7 @@ def dftd4(
             small = [b for b in range(num2.shape[0]) if b not in set(big)]
             for b in big:
                 rows[b] = dftd4_large(num2[b], pos2[b], param, q2[b], cutoff=cutoff,
-                                      model=(ga, gc, wf, spec.ref_charges))
+                                      model=(ga, gc, wf, spec.ref_charges, spec.c9_frequency))
             if small:
                 # compact the small structures to the front of the atom axis
                 sel = torch.tensor(small, device=num2.device)

@@ -8,8 +8,10 @@ The reference sums ``term.calculate(...)`` over registered terms.  Here the regi
 terms only *select* which parts of the fused kernel contribute: the default pair
 ``TwoBodyTerm(Rational, charge_dependent=True)`` + ``D4ATMApprox(Zero,
 charge_dependent=False)`` runs in one launch; a single registered term maps onto the
-same kernel with the other part switched off (``s9 = 0`` or ``s6 = s8 = 0``).  Any other
-combination is outside the accelerated path and raises ``NotImplementedError``.
+same kernel with the other part switched off (``s9 = 0`` or ``s6 = s8 = 0``).  The exact
+Casimir-Polder C9 (``D4ATMExact`` / ``DispD4Exact``, ``dispersion/d4.py:67-84``) is the sum of 23
+ATM-only launches of the same kernels, one per integration node (``tables.ElementTables``).  Any
+other combination is outside the accelerated path and raises ``NotImplementedError``.
 """
 
 from __future__ import annotations
@@ -19,9 +21,11 @@ from typing import Any
 import torch
 
 from .damping import RationalDamping, ZeroDamping
-from .disp import dftd4
+from .disp import _FrequencySlice, dftd4
+from .tables import NFREQ
 
-__all__ = ["Disp", "DispD4", "DispTerm", "TwoBodyTerm", "D4ATMApprox", "FusedD4Term", "ZeroDamping"]
+__all__ = ["Disp", "DispD4", "DispD4Exact", "DispTerm", "TwoBodyTerm", "D4ATMApprox", "D4ATMExact", "FusedD4Term",
+           "ZeroDamping"]  # fmt: skip
 
 
 class DispTerm:
@@ -96,6 +100,30 @@ class D4ATMApprox(DispTerm):
         super().__init__(damping_fn if damping_fn is not None else ZeroDamping(), charge_dependent)
 
 
+class D4ATMExact(DispTerm):
+    """ATM term with the exact C9 from the Casimir-Polder integral of the three weighted
+    polarizabilities (``dispersion/d4.py:67-68``, ``threebody.py:276-302``, ``utils.py:155-212``):
+
+        C9_ijk = (3/pi) sum_w t_w a_i(w) a_j(w) a_k(w).
+
+    Every node ``w`` has the product form the kernels evaluate for the approximate C9, so the term is the
+    sum of 23 ATM-only launches with single-node polarizability tables (see ``tables.ElementTables``);
+    energies and gradients add up.  Costs 23 times the ATM part of the default term."""
+
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "ZeroDamping", False, {"s6": 0.0, "s8": 0.0, "s10": 0.0}
+
+    def __init__(self, *, damping_fn: Any = None, charge_dependent: bool = False):
+        super().__init__(damping_fn if damping_fn is not None else ZeroDamping(), charge_dependent)
+
+    def calculate(self, numbers, positions, param, cn=None, model="d4", q=None, r4r2=None, rvdw=None,
+                  cutoff=None):  # fmt: skip
+        total = None
+        for w in range(NFREQ):
+            e = super().calculate(numbers, positions, param, cn, _FrequencySlice(model, w), q, r4r2, rvdw, cutoff)
+            total = e if total is None else total + e
+        return total
+
+
 class FusedD4Term(DispTerm):
     """Two-body + ATM in ONE launch (what ``DispD4`` registers as two terms).  Registered with
     the reference's ``Disp`` -- ``Disp(model="d4").register(FusedD4Term())`` -- it makes the
@@ -158,6 +186,25 @@ class Disp:
                 raise NotImplementedError(
                     "only TwoBodyTerm(charge_dependent=True) + D4ATMApprox(charge_dependent=False) is fused"
                 )
+        elif kinds == ["D4ATMExact", "TwoBodyTerm"] or kinds == ["D4ATMExact"]:
+            two = next((t for t in self.terms if isinstance(t, TwoBodyTerm)), None)
+            atm = next(t for t in self.terms if isinstance(t, D4ATMExact))
+            if (two is not None and not two.charge_dependent) or atm.charge_dependent:
+                raise NotImplementedError(
+                    "only TwoBodyTerm(charge_dependent=True) + D4ATMExact(charge_dependent=False) is accelerated"
+                )
+            if two is not None and type(two.damping_fn).__name__ != "RationalDamping":
+                raise NotImplementedError("only RationalDamping is accelerated for the two-body term")
+            if q is None and two is not None:  # one EEQ solve for all launches
+                from .disp import _eeq_charges
+
+                q = _eeq_charges(numbers, positions, charge, cutoff)
+            energy = atm.calculate(numbers, positions, par, None, self.model, q, r4r2, rvdw, cutoff)
+            if two is not None:
+                par["s9"] = 0.0
+                energy = energy + dftd4(numbers, positions, charge, par, model=self.model, rcov=rcov, r4r2=r4r2,
+                                        rvdw=rvdw, q=q, cutoff=cutoff, cn_function=self.cn_fn)  # fmt: skip
+            return energy
         elif kinds == ["TwoBodyTerm"]:
             if not self.terms[0].charge_dependent:
                 raise NotImplementedError("charge-independent two-body term is outside the accelerated path")
@@ -188,4 +235,13 @@ class DispD4(Disp):
     TERMS = [
         (TwoBodyTerm, {"damping_fn": RationalDamping(), "charge_dependent": True}),
         (D4ATMApprox, {"damping_fn": ZeroDamping(), "charge_dependent": False}),
+    ]
+
+
+class DispD4Exact(Disp):
+    """DFT-D4 with the exact C9 coefficients via the Casimir-Polder formula (``dispersion/d4.py:71-84``)."""
+
+    TERMS = [
+        (TwoBodyTerm, {"damping_fn": RationalDamping(), "charge_dependent": True}),
+        (D4ATMExact, {"damping_fn": ZeroDamping(), "charge_dependent": False}),
     ]

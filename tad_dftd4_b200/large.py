@@ -226,19 +226,20 @@ class _Plan:
 
 
 def _kernel_backend(positions: Tensor, param, cutoff, model=None):
-    """``model``: (ga, gc, wf[, ref_charges]) of the caller's D4Model (defaults when None)."""
+    """``model``: (ga, gc, wf[, ref_charges[, c9_frequency]]) of the caller's D4Model (defaults when None)."""
     from . import _lib, defaults
     from .disp import _Engine, _flatten_param, _param_tensors
 
     ga, gc, wf, *rest = model if model is not None else (defaults.GA_DEFAULT, defaults.GC_DEFAULT, defaults.WF_DEFAULT)
     ref_charges = rest[0] if rest else "eeq"
+    c9_frequency = rest[1] if len(rest) > 1 else None
 
     if _param_tensors(param):
         raise NotImplementedError(
             "gradients with respect to the damping parameters are provided for structures of the "
             "one-CTA-per-structure kernels only (detach the parameters for the tiled large-system path)"
         )
-    engine = _Engine.get(positions.device, ga, gc, ref_charges)
+    engine = _Engine.get(positions.device, ga, gc, ref_charges, c9_frequency)
     par = _flatten_param(param, cutoff, 0, wf)
     lib = engine.lib
     gs = int(lib.d4b200_large_group_size())

@@ -92,7 +92,7 @@ class ElementTables:
         ("maxcn_ref", NELEM),  # index of the largest reference CN (NaN fallback)
     )
 
-    def __init__(self, ga: float, gc: float, ref_charges: str = "eeq"):
+    def __init__(self, ga: float, gc: float, ref_charges: str = "eeq", c9_frequency: int | None = None):
         raw = _raw()
         self.ga, self.gc = float(ga), float(gc)
         # reference charges of the model (model/base.py:388-399, model/d4.py:142-149): EEQ (default) or GFN2-xTB
@@ -136,6 +136,21 @@ class ElementTables:
         self.alpha = np.where(alpha > 0.0, alpha, 0.0)  # (104, 7, 23)
         self.alpha0 = self.alpha[..., 0].copy()
         self.alpha_w = self.alpha * np.sqrt(THOPI * CP_WEIGHTS)[None, None, :]
+        self.c9_frequency = c9_frequency
+        if c9_frequency is not None:
+            # One Casimir-Polder node of the EXACT C9 (dispersion/threebody.py:276-302, utils.py:155-212):
+            #   C9_ijk = (3/pi) sum_w t_w a_i(w) a_j(w) a_k(w)
+            # and, all polarizabilities being >= 0, each node is the kernels' own approximate form
+            # sqrt(c_ij c_jk c_ik) with the pair quantity c_ij = b_i b_j, b_i = ((3/pi) t_w)^(1/3) a_i(w).  The
+            # kernels build c_ij as the dot product of the weighted-polarizability vectors, so a table that
+            # keeps only node w, rescaled from sqrt((3/pi) t_w) to the cube root, makes an ATM-only launch
+            # return exactly that node's contribution, gradients and all (dispersion.D4ATMExact sums the 23).
+            w = int(c9_frequency)
+            if not 0 <= w < NFREQ:
+                raise ValueError(f"Casimir-Polder node {w} outside 0..{NFREQ - 1}")
+            node = np.zeros_like(self.alpha_w)
+            node[..., w] = self.alpha_w[..., w] * (THOPI * CP_WEIGHTS[w]) ** (-1.0 / 6.0)
+            self.alpha_w = node
         self.wfpair = raw["wfpair"][:NELEM, :NELEM].copy()
         # rc6[Za, Zb, a, b] = (3/pi) sum_w w_w alpha[Za,a,w] alpha[Zb,b,w]  (utils.py:91-94)
         flat = self.alpha_w.reshape(NELEM * NREF, NFREQ)
@@ -158,6 +173,7 @@ class ElementTables:
         return np.concatenate(parts)
 
 
-@lru_cache(maxsize=8)
-def build_tables(ga: float = 3.0, gc: float = 2.0, ref_charges: str = "eeq") -> ElementTables:
-    return ElementTables(ga, gc, ref_charges)
+@lru_cache(maxsize=64)
+def build_tables(ga: float = 3.0, gc: float = 2.0, ref_charges: str = "eeq",
+                 c9_frequency: int | None = None) -> ElementTables:  # fmt: skip
+    return ElementTables(ga, gc, ref_charges, c9_frequency)

@@ -1,0 +1,91 @@
+"""DispD4Exact / D4ATMExact (dispersion/d4.py:67-84, threebody.py:276-302 of the reference): golden
+vectors from the UNMODIFIED reference (tests/golden/exact, oracle/make_golden_exact.py) against the oracle and the
+single-node tables on the CPU, and against the kernels (23 ATM-only launches + one two-body launch) on the B200."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import d4_oracle as orc
+from helpers import GOLDEN, as_torch, load_golden
+
+CASES = ("single_pbe0", "sih4_tpssh", "organic_33", "ragged_batch", "tight_cutoffs")
+
+
+def _load(name):
+    case = load_golden(name)
+    return case, np.load(GOLDEN / "exact" / f"{name}.npz")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_the_reference_exact_c9(name):
+    case, gold = _load(name)
+    n, p, q = as_torch(case)
+    e, g = orc.energy_and_gradient(n, p, case["param"], q, c9="exact", **case["cutoff"])
+    assert np.abs(e.numpy() - gold["energy"]).max() <= 1e-13 * np.abs(gold["energy"]).max()
+    assert np.abs(g.numpy() - gold["gradient"]).max() < 1e-15
+    _, e3, *_ = orc.dftd4(n, p, case["param"], q, parts=True, c9="exact", **case["cutoff"])
+    assert np.abs(e3.numpy() - gold["energy_atm"]).max() <= 1e-12 * np.abs(gold["energy_atm"]).max()
+
+
+def test_single_node_tables_sum_to_the_exact_c9():
+    """What the 23 launches rely on: with the table of node w the kernels' pair quantity c_ij = A_i . A_j is
+    b_i b_j, sqrt(c_ij c_jk c_ik) = b_i b_j b_k, and the sum over the nodes is the Casimir-Polder integral."""
+    from tad_dftd4_b200.tables import NFREQ, build_tables
+
+    case = load_golden("organic_33")
+    n, p, q = as_torch(case)
+    cn = orc.cn_d4(n, p)
+    w0 = orc.weight_references_d4(n, cn, None).numpy()
+    aiw = np.einsum("nr,nrw->nw", w0, orc.reference_alpha(n).numpy())
+    tw = np.asarray(orc._CP_WEIGHTS)
+    exact = 3.0 / np.pi * np.einsum("w,iw,jw,kw->ijk", tw, aiw, aiw, aiw)
+    total = np.zeros_like(exact)
+    z = n.numpy()
+    for w in range(NFREQ):
+        tab = build_tables(3.0, 2.0, "eeq", w)
+        assert np.count_nonzero(np.abs(tab.alpha_w).sum((0, 1))) == 1
+        a0 = np.einsum("nr,nrw->nw", w0, tab.alpha_w[z])  # the kernels' weighted-polarizability vectors
+        c = a0 @ a0.T
+        total += np.sqrt(np.abs(c[:, :, None] * c[None, :, :] * c[:, None, :]))
+    assert np.abs(total - exact).max() <= 1e-13 * np.abs(exact).max()
+    with pytest.raises(ValueError):
+        build_tables(3.0, 2.0, "eeq", 23)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_kernels_exact_c9(name):
+    import tad_dftd4_b200 as d4
+    from tad_dftd4_b200.dispersion import D4ATMExact, Disp, DispD4Exact
+
+    case, gold = _load(name)
+    dev = torch.device("cuda:0")
+    n, p, q = as_torch(case, dev)
+    cutoff = d4.Cutoff(**case["cutoff"]) if case["cutoff"] else None
+    pos = p.clone().requires_grad_(True)
+    e = DispD4Exact().calculate(n, pos, 0.0, case["param"], q=q, cutoff=cutoff)
+    (g,) = torch.autograd.grad(e.sum(), pos)
+    assert np.abs(e.detach().cpu().numpy() - gold["energy"]).max() <= 1e-10 * np.abs(gold["energy"]).max()
+    assert np.abs(g.cpu().numpy() - gold["gradient"]).max() < 1e-9
+    # the ATM term alone, registered on a bare Disp (test/test_disp/test_variants.py:64-86 of the reference)
+    atm = Disp(model="d4")
+    atm.register(D4ATMExact())
+    pos3 = p.clone().requires_grad_(True)
+    e3 = atm.calculate(n, pos3, 0.0, case["param"], cutoff=cutoff)
+    (g3,) = torch.autograd.grad(e3.sum(), pos3)
+    scale = max(np.abs(gold["energy_atm"]).max(), 1e-300)
+    assert np.abs(e3.detach().cpu().numpy() - gold["energy_atm"]).max() <= 1e-10 * scale
+    assert np.abs(g3.cpu().numpy() - gold["gradient_atm"]).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_exact_c9_is_for_the_d4_model():
+    from tad_dftd4_b200.dispersion import DispD4Exact
+
+    dev = torch.device("cuda:0")
+    case = load_golden("single_pbe0")
+    n, p, q = as_torch(case, dev)
+    with pytest.raises(NotImplementedError):
+        DispD4Exact(model="d4s").calculate(n, p, 0.0, case["param"], q=q)
