@@ -522,6 +522,41 @@ def _eeq_charges(numbers: Tensor, positions: Tensor, charge, cutoff: Cutoff | No
     return get_eeq_charges(numbers, positions, charge, cutoff=cut)
 
 
+def _check_arguments(numbers, positions, model, rcov=None, r4r2=None, rvdw=None, q=None, cn_function=None,
+                     counting_function=None, damping_function=None) -> "_ModelSpec":  # fmt: skip
+    """The argument checks of ``Disp.calculate`` (dispersion/base.py:354-399), in the reference's order: shapes
+    first, then what lies outside the accelerated path.  Returns the resolved model."""
+    if numbers.shape != positions.shape[:-1]:
+        raise ValueError(
+            f"Shape of positions ({positions.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
+    spec = _resolve_model(model)
+    for name, val in (("covalent radii", rcov), ("expectation values r4r2", r4r2)):
+        if val is not None and numbers.shape != val.shape:
+            raise ValueError(
+                f"Shape of {name} ({val.shape}) is not consistent with atomic numbers ({numbers.shape})."
+            )
+    if rvdw is not None and numbers.shape != rvdw.shape[:-1]:
+        raise ValueError(
+            f"Shape of van der Waals radii ({rvdw.shape}) is not "
+            f"consistent with atomic numbers ({numbers.shape}).",
+        )
+    if rcov is not None or r4r2 is not None or rvdw is not None:
+        raise NotImplementedError("custom rcov/r4r2/rvdw are outside the accelerated hot path")
+    for name, fn in (("cn_function", cn_function), ("counting_function", counting_function)):
+        if fn is not None and getattr(fn, "__name__", "") not in ("cn_d4", "erf_count"):
+            raise NotImplementedError(f"custom {name} is outside the accelerated hot path")
+    if damping_function is not None and type(damping_function).__name__ != "RationalDamping":
+        raise NotImplementedError("only RationalDamping is accelerated")
+    if q is not None and numbers.shape != q.shape:
+        raise ValueError(
+            f"Shape of atomic charges ({q.shape}) is not consistent "
+            f"with atomic numbers ({numbers.shape}).",
+        )
+    return spec
+
+
 def dftd4(
     numbers: Tensor,
     positions: Tensor,
@@ -546,35 +581,9 @@ def dftd4(
     radii, approximate C9, default element radii); any other plugin raises
     ``NotImplementedError`` instead of silently falling back.
     """
-    if numbers.shape != positions.shape[:-1]:
-        raise ValueError(
-            f"Shape of positions ({positions.shape}) is not consistent "
-            f"with atomic numbers ({numbers.shape}).",
-        )
-    spec = _resolve_model(model)
+    spec = _check_arguments(numbers, positions, model, rcov, r4r2, rvdw, q, cn_function, counting_function,
+                            damping_function)  # fmt: skip
     model_id, ga, gc, wf = spec
-    for name, val in (("covalent radii", rcov), ("expectation values r4r2", r4r2)):
-        if val is not None and numbers.shape != val.shape:
-            raise ValueError(
-                f"Shape of {name} ({val.shape}) is not consistent with atomic numbers ({numbers.shape})."
-            )
-    if rvdw is not None and numbers.shape != rvdw.shape[:-1]:
-        raise ValueError(
-            f"Shape of van der Waals radii ({rvdw.shape}) is not "
-            f"consistent with atomic numbers ({numbers.shape}).",
-        )
-    if rcov is not None or r4r2 is not None or rvdw is not None:
-        raise NotImplementedError("custom rcov/r4r2/rvdw are outside the accelerated hot path")
-    for name, fn in (("cn_function", cn_function), ("counting_function", counting_function)):
-        if fn is not None and getattr(fn, "__name__", "") not in ("cn_d4", "erf_count"):
-            raise NotImplementedError(f"custom {name} is outside the accelerated hot path")
-    if damping_function is not None and type(damping_function).__name__ != "RationalDamping":
-        raise NotImplementedError("only RationalDamping is accelerated")
-    if q is not None and numbers.shape != q.shape:
-        raise ValueError(
-            f"Shape of atomic charges ({q.shape}) is not consistent "
-            f"with atomic numbers ({numbers.shape}).",
-        )
     if param.get("a1") is None or param.get("a2") is None:
         # raised by the reference's RationalDamping on any device (damping/functions.py:255-259)
         missing = [k for k in ("a1", "a2") if param.get(k) is None]

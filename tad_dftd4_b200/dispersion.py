@@ -20,8 +20,9 @@ from typing import Any
 
 import torch
 
+from . import defaults
 from .damping import RationalDamping, ZeroDamping
-from .disp import _FrequencySlice, dftd4
+from .disp import _check_arguments, _FrequencySlice, dftd4
 from .tables import NFREQ
 
 __all__ = ["Disp", "DispD4", "DispD4Exact", "DispTerm", "TwoBodyTerm", "D4ATMApprox", "D4ATMExact", "FusedD4Term",
@@ -46,6 +47,20 @@ class DispTerm:
     # which part of the fused kernel this term stands for: parameters that are switched off
     _OFF: dict[str, float] = {}
 
+    def _validate(self, param) -> None:
+        """What the term cannot do, and the parameter check of its damping function
+        (damping/functions.py:95-113), before anything is computed."""
+        if type(self.damping_fn).__name__ != self._DAMPING:
+            raise NotImplementedError(f"only {self._DAMPING} is accelerated for {type(self).__name__}")
+        if self.charge_dependent not in self._CHARGE_DEPENDENT:
+            raise NotImplementedError(
+                f"{type(self).__name__}(charge_dependent={self.charge_dependent}) is outside the accelerated path"
+            )
+        if self._DAMPING == "RationalDamping":
+            missing = [k for k in ("a1", "a2") if param.get(k) is None]
+            if missing:
+                raise TypeError(f"RationalDamping (order 6) requires keyword(s): {', '.join(missing)}")
+
     def calculate(self, numbers, positions, param, cn=None, model="d4", q=None, r4r2=None, rvdw=None,
                   cutoff=None):  # fmt: skip
         """Atom-resolved energy of this term: the plugin interface of the reference
@@ -60,15 +75,13 @@ class DispTerm:
         be the defaults (the reference always passes the gathered default tables here, so they
         are not checked); ``model`` may be a model name, this package's ``D4Model`` /
         ``D4SModel`` or the reference's (read through ``ga``, ``gc``, ``wf``)."""
-        if type(self.damping_fn).__name__ != self._DAMPING:
-            raise NotImplementedError(f"only {self._DAMPING} is accelerated for {type(self).__name__}")
-        if self.charge_dependent != self._CHARGE_DEPENDENT:
-            raise NotImplementedError(
-                f"{type(self).__name__}(charge_dependent={self.charge_dependent}) is outside the accelerated path"
-            )
+        self._validate(param)
         par = dict(param)
         for key, val in self._OFF.items():
             par[key] = val
+        if self._DAMPING == "ZeroDamping":  # BJ radii of the ATM terms fall back to the defaults (threebody.py:244-256)
+            par.setdefault("a1", defaults.A1)
+            par.setdefault("a2", defaults.A2)
         if "s10" in self._OFF:
             par.pop("s10")
         if q is None:
@@ -84,7 +97,7 @@ class TwoBodyTerm(DispTerm):
     """Two-body term with rational damping (``dispersion/twobody.py:89-201``): the fused kernel
     with the ATM part switched off."""
 
-    _DAMPING, _CHARGE_DEPENDENT, _OFF = "RationalDamping", True, {"s9": 0.0}
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "RationalDamping", (True, False), {"s9": 0.0}
 
     def __init__(self, *, damping_fn: Any = None, charge_dependent: bool = True):
         super().__init__(damping_fn if damping_fn is not None else RationalDamping(), charge_dependent)
@@ -94,7 +107,7 @@ class D4ATMApprox(DispTerm):
     """ATM term with the approximate C9 (``dispersion/d4.py:29-45``, ``threebody.py:210-256``):
     the fused kernel with the two-body part switched off."""
 
-    _DAMPING, _CHARGE_DEPENDENT, _OFF = "ZeroDamping", False, {"s6": 0.0, "s8": 0.0, "s10": 0.0}
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "ZeroDamping", (False,), {"s6": 0.0, "s8": 0.0, "s10": 0.0}
 
     def __init__(self, *, damping_fn: Any = None, charge_dependent: bool = False):
         super().__init__(damping_fn if damping_fn is not None else ZeroDamping(), charge_dependent)
@@ -110,7 +123,7 @@ class D4ATMExact(DispTerm):
     sum of 23 ATM-only launches with single-node polarizability tables (see ``tables.ElementTables``);
     energies and gradients add up.  Costs 23 times the ATM part of the default term."""
 
-    _DAMPING, _CHARGE_DEPENDENT, _OFF = "ZeroDamping", False, {"s6": 0.0, "s8": 0.0, "s10": 0.0}
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "ZeroDamping", (False,), {"s6": 0.0, "s8": 0.0, "s10": 0.0}
 
     def __init__(self, *, damping_fn: Any = None, charge_dependent: bool = False):
         super().__init__(damping_fn if damping_fn is not None else ZeroDamping(), charge_dependent)
@@ -129,7 +142,7 @@ class FusedD4Term(DispTerm):
     the reference's ``Disp`` -- ``Disp(model="d4").register(FusedD4Term())`` -- it makes the
     reference's own class-based driver run on the kernels."""
 
-    _DAMPING, _CHARGE_DEPENDENT, _OFF = "RationalDamping", True, {}
+    _DAMPING, _CHARGE_DEPENDENT, _OFF = "RationalDamping", (True,), {}
 
     def __init__(self):
         super().__init__(RationalDamping(), True)
@@ -177,56 +190,31 @@ class Disp:
                 "requires them. Please remove the `q` argument or "
                 "provide a term that requires atomic charges.",
             )
-        kinds = sorted(type(t).__name__ for t in self.terms)
-        par = dict(param)
-        if kinds == ["D4ATMApprox", "TwoBodyTerm"] or kinds == ["FusedD4Term"]:
-            two = next((t for t in self.terms if isinstance(t, (TwoBodyTerm, FusedD4Term))))
-            atm = next((t for t in self.terms if isinstance(t, D4ATMApprox)), None)
-            if not two.charge_dependent or (atm is not None and atm.charge_dependent):
-                raise NotImplementedError(
-                    "only TwoBodyTerm(charge_dependent=True) + D4ATMApprox(charge_dependent=False) is fused"
-                )
-        elif kinds == ["D4ATMExact", "TwoBodyTerm"] or kinds == ["D4ATMExact"]:
-            two = next((t for t in self.terms if isinstance(t, TwoBodyTerm)), None)
-            atm = next(t for t in self.terms if isinstance(t, D4ATMExact))
-            if (two is not None and not two.charge_dependent) or atm.charge_dependent:
-                raise NotImplementedError(
-                    "only TwoBodyTerm(charge_dependent=True) + D4ATMExact(charge_dependent=False) is accelerated"
-                )
-            if two is not None and type(two.damping_fn).__name__ != "RationalDamping":
-                raise NotImplementedError("only RationalDamping is accelerated for the two-body term")
-            if q is None and two is not None:  # one EEQ solve for all launches
-                from .disp import _eeq_charges
-
-                q = _eeq_charges(numbers, positions, charge, cutoff)
-            energy = atm.calculate(numbers, positions, par, None, self.model, q, r4r2, rvdw, cutoff)
-            if two is not None:
-                par["s9"] = 0.0
-                energy = energy + dftd4(numbers, positions, charge, par, model=self.model, rcov=rcov, r4r2=r4r2,
-                                        rvdw=rvdw, q=q, cutoff=cutoff, cn_function=self.cn_fn)  # fmt: skip
-            return energy
-        elif kinds == ["TwoBodyTerm"]:
-            if not self.terms[0].charge_dependent:
-                raise NotImplementedError("charge-independent two-body term is outside the accelerated path")
-            par["s9"] = 0.0
-        elif kinds == ["D4ATMApprox"]:
-            if self.terms[0].charge_dependent:
-                raise NotImplementedError("charge-dependent ATM term is outside the accelerated path")
-            par["s6"], par["s8"] = 0.0, 0.0
-            par.pop("s10", None)
-            if q is None:  # the ATM term does not use charges
-                q = torch.zeros(numbers.shape, dtype=positions.dtype, device=positions.device)
-        elif not kinds:
+        if not self.terms:
             return torch.zeros(numbers.shape, dtype=positions.dtype, device=positions.device)
-        else:
-            raise NotImplementedError(f"term combination {kinds} is outside the accelerated D4 hot path")
+        kinds = sorted(type(t).__name__ for t in self.terms)
+        fused = kinds == ["FusedD4Term"] or (
+            kinds == ["D4ATMApprox", "TwoBodyTerm"]
+            and all(t.charge_dependent == isinstance(t, TwoBodyTerm) for t in self.terms)
+            and all(type(t.damping_fn).__name__ == t._DAMPING for t in self.terms)
+        )
+        if fused:  # the default combination (dispersion/d4.py:48-61): ONE launch
+            return dftd4(numbers, positions, charge, param, model=self.model, rcov=rcov, r4r2=r4r2, rvdw=rvdw,
+                         q=q, cutoff=cutoff, cn_function=self.cn_fn)  # fmt: skip
+        # any other registered combination: the sum of the terms, as in the reference (base.py:409-431); every
+        # term is the fused kernel with the other part switched off (D4ATMExact: 23 such launches)
+        _check_arguments(numbers, positions, self.model, rcov, r4r2, rvdw, q, self.cn_fn)
         for t in self.terms:
-            if isinstance(t, (TwoBodyTerm, FusedD4Term)) and type(t.damping_fn).__name__ != "RationalDamping":
-                raise NotImplementedError("only RationalDamping is accelerated for the two-body term")
-            if isinstance(t, D4ATMApprox) and type(t.damping_fn).__name__ != "ZeroDamping":
-                raise NotImplementedError("only ZeroDamping is accelerated for the ATM term")
-        return dftd4(numbers, positions, charge, par, model=self.model, rcov=rcov, r4r2=r4r2, rvdw=rvdw,
-                     q=q, cutoff=cutoff, cn_function=self.cn_fn)  # fmt: skip
+            t._validate(param)
+        if q is None and is_c_dep:  # one EEQ solve for all terms (base.py:401-407)
+            from .disp import _eeq_charges
+
+            q = _eeq_charges(numbers, positions, charge, cutoff)
+        energy = None
+        for t in self.terms:
+            e = t.calculate(numbers, positions, param, None, self.model, q, r4r2, rvdw, cutoff)
+            energy = e if energy is None else energy + e
+        return energy
 
 
 class DispD4(Disp):

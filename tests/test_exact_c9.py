@@ -89,3 +89,41 @@ def test_exact_c9_is_for_the_d4_model():
     n, p, q = as_torch(case, dev)
     with pytest.raises(NotImplementedError):
         DispD4Exact(model="d4s").calculate(n, p, 0.0, case["param"], q=q)
+
+
+@pytest.mark.gpu
+def test_registered_term_combinations_are_sums_of_launches():
+    """Disp.calculate beyond the fused default (dispersion/base.py:409-431): every registered term is one launch
+    (or 23) with the other part switched off; the oracle evaluates the same combinations."""
+    from tad_dftd4_b200.dispersion import D4ATMApprox, D4ATMExact, Disp, TwoBodyTerm
+
+    dev = torch.device("cuda:0")
+    case = load_golden("ragged_batch")
+    n, p, q = as_torch(case)
+    par = case["param"]
+    e2q, e3, *_ = orc.dftd4(n, p, par, q, parts=True)
+    e20, *_ = orc.dftd4(n, p, par, torch.zeros_like(q), parts=True)
+    _, e3x, *_ = orc.dftd4(n, p, par, q, parts=True, c9="exact")
+    nd, pd, qd = n.to(dev), p.to(dev), q.to(dev)
+
+    def run(terms, **kw):
+        disp = Disp(model="d4")
+        for t in terms:
+            disp.register(t)
+        return disp.calculate(nd, pd, 0.0, par, **kw).cpu()
+
+    def close(a, b):
+        return (a - b).abs().max().item() <= 1e-10 * b.abs().max().item()
+
+    assert close(run([TwoBodyTerm(charge_dependent=False)]), e20)
+    assert close(run([TwoBodyTerm(charge_dependent=False), D4ATMApprox()]), e20 + e3)
+    assert close(run([TwoBodyTerm(), D4ATMExact()], q=qd), e2q + e3x)
+    assert close(run([D4ATMApprox(), D4ATMExact()]), e3 + e3x)
+    # the ATM terms take their BJ radii from the defaults when a1/a2 are not given (threebody.py:244-256)
+    nopar = {k: v for k, v in par.items() if k not in ("a1", "a2")}
+    _, e3d, *_ = orc.dftd4(n, p, dict(nopar, a1=0.4, a2=5.0), q, parts=True)
+    disp = Disp(model="d4")
+    disp.register(D4ATMApprox())
+    assert close(disp.calculate(nd, pd, 0.0, nopar).cpu(), e3d)
+    with pytest.raises(NotImplementedError):
+        run([TwoBodyTerm(), D4ATMApprox(charge_dependent=True)], q=qd)

@@ -99,7 +99,11 @@ def test_fused_term_driven_by_a_reference_style_disp_loop():
                 energy = energy + term.calculate(numbers=numbers, positions=positions, param=param, cn=cn, model="d4",
                                                  q=q, r4r2=None, rvdw=None, cutoff=None)  # fmt: skip
             assert torch.allclose(energy, want, rtol=1e-12, atol=1e-16)
+        # a charge-independent two-body term is the same kernel with zeta(q = 0) (twobody.py:76-80)
+        e0 = dispersion.TwoBodyTerm(charge_dependent=False).calculate(numbers, positions, param, cn, "d4", q)
+        want0, *_ = orc.dftd4(numbers, positions, param, torch.zeros_like(q), parts=True)
+        assert torch.allclose(e0, want0, rtol=1e-12, atol=1e-16)
         with pytest.raises(NotImplementedError):
-            dispersion.TwoBodyTerm(charge_dependent=False).calculate(numbers, positions, param, cn, "d4", q)
+            dispersion.D4ATMApprox(charge_dependent=True).calculate(numbers, positions, param, cn, "d4", q)
         with pytest.raises(ValueError):
             dispersion.FusedD4Term().calculate(numbers, positions, param, cn, "d4", None)
