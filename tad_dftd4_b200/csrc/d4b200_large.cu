@@ -638,6 +638,23 @@ __global__ void __launch_bounds__(128) large_cn_chain(LargeArgs<T> A, int ncolch
 // ATM gradient, centre groups.  512 threads: warp w owns rows 2w, 2w+1 of the X tile,
 // lanes own the columns of the Y tile; loop order centre -> row so that the centre's
 // accumulators are four registers reduced once per (tile, centre).
+// Four warp-wide sums for the price of two: a transposing butterfly.  After the call the lanes with
+// (lane & 7) == 0 hold the totals: lane 0 -> v0, lane 8 -> v1, lane 16 -> v2, lane 24 -> v3 (the other
+// lanes hold the same totals of their group of eight).  12 + 6 instead of 40 + 20 shuffle / add instructions.
+template <typename T>
+__device__ __forceinline__ T warp_sum4(T v0, T v1, T v2, T v3, int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8;
+  T k0 = h16 ? v2 : v0, k1 = h16 ? v3 : v1;
+  k0 += __shfl_xor_sync(0xffffffffu, h16 ? v0 : v2, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, h16 ? v1 : v3, 16);
+  T k = h8 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
 constexpr int GSTASH = 5;  // r^2, P, u, D^(j)_jx, D^(x)_xj
 template <typename T>
 __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
@@ -841,24 +858,21 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
               jdc += We * (TST(0, j, 3, row) + Djk);           // D^(j)_ji + D^(j)_jk
             }
           }
-          jfx = warp_sum(jfx), jfy = warp_sum(jfy), jfz = warp_sum(jfz), jdc = warp_sum(jdc);
-          if (lane == 0 && (jfx != T(0) || jfy != T(0) || jfz != T(0) || jdc != T(0))) {
-            const int jj = g * GROUP + j;
-            atomicAdd(&A.force[3 * jj], jfx);
-            atomicAdd(&A.force[3 * jj + 1], jfy);
-            atomicAdd(&A.force[3 * jj + 2], jfz);
-            atomicAdd(&A.dcn[jj], jdc);
+          {  // x, y, z, dcn of the centre end up in the lanes 0, 8, 16, 24
+            const T tot = warp_sum4(jfx, jfy, jfz, jdc, lane);
+            if ((lane & 7) == 0 && tot != T(0)) {
+              const int jj = g * GROUP + j, which = lane >> 3;
+              atomicAdd(which < 3 ? &A.force[3 * jj + which] : &A.dcn[jj], tot);
+            }
           }
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-          const T sx_ = warp_sum(ifx[rr]), sy_ = warp_sum(ify[rr]), sz_ = warp_sum(ifz[rr]), sc_ = warp_sum(idc[rr]);
+          const T tot = warp_sum4(ifx[rr], ify[rr], ifz[rr], idc[rr], lane);
           const int ii = tidx[warp * 2 + rr];
-          if (lane == 0 && ii >= 0 && (sx_ != T(0) || sy_ != T(0) || sz_ != T(0) || sc_ != T(0))) {
-            atomicAdd(&A.force[3 * ii], sx_);
-            atomicAdd(&A.force[3 * ii + 1], sy_);
-            atomicAdd(&A.force[3 * ii + 2], sz_);
-            atomicAdd(&A.dcn[ii], sc_);
+          if ((lane & 7) == 0 && ii >= 0 && tot != T(0)) {
+            const int which = lane >> 3;
+            atomicAdd(which < 3 ? &A.force[3 * ii + which] : &A.dcn[ii], tot);
           }
           if (A.energy) {
             const T se_ = warp_sum(ie[rr]);
