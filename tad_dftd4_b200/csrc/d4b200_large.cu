@@ -827,28 +827,32 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
           const T Djk = TST(1, j, 3, lane), Dkj = TST(1, j, 4, lane);
           const T cx = cpx[j], cy = cpy[j], cz = cpz[j];
           const bool kin = mk >> j & 1u;
+          // both rows of the lane as ONE straight-line block (masked instead of branched): two independent
+          // dependency chains in flight
+          const bool in0 = tmask[warp * 2] >> j & 1u, in1 = tmask[warp * 2 + 1] >> j & 1u;  // warp-uniform
+          if (in0 | in1) {
 #pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            const int row = warp * 2 + rr;
-            if (pv[rr] && kin && (tmask[row] >> j & 1u)) {
-              const T a = TST(0, j, 0, row), c = fc_[rr];
-              const T X = a + b - c, Y = a - b + c, Z = b + c - a;
+            for (int rr = 0; rr < 2; ++rr) {
+              const int row = warp * 2 + rr;
+              const bool act = pv[rr] && kin && (rr ? in1 : in0);
+              // masked lanes run on a unit triangle (finite everywhere) and contribute psf = 0
+              const T a = act ? TST(0, j, 0, row) : T(1), c = act ? fc_[rr] : T(1), bm = act ? b : T(1);
+              const T X = a + bm - c, Y = a - bm + c, Z = bm + c - a;
               const T s = X * Y * Z;
-              const T abc = a * b * c;
+              const T abc = a * bm * c;
               const T t = TST(0, j, 2, row) * ub * fu[rr];
               const T d = T(1) + T(6) * t;
               const T inv = d4_rcp(abc * d);
               const T Q = inv * d, f = inv * abc;
-              const T psf = TST(0, j, 1, row) * Pb * fP[rr] * f;
+              const T psf = act ? TST(0, j, 1, row) * Pb * fP[rr] * f : T(0);
               const T e = (T(0.375) * s * Q + T(1)) * psf;
               const T W = tg[row] + gk;
               const T common = e * (T(-2.5) + T(3) * P.alp3 * f * t) + psf;
               const T k3 = T(0.375) * psf * Q;
               const T yz = Y * Z, xz = X * Z, xy = X * Y;
-              // dL/d(r^2) of the three edges, times 2 for d r^2/dR
-              const T da = T(2) * W * (common * (Q * b * c) + k3 * (yz + xz - xy));   // (j,i)
+              const T da = T(2) * W * (common * (Q * bm * c) + k3 * (yz + xz - xy));   // (j,i)
               const T db = T(2) * W * (common * (Q * a * c) + k3 * (yz - xz + xy));   // (j,k)
-              const T dc = T(2) * W * (common * (Q * a * b) + k3 * (xz + xy - yz));   // (i,k)
+              const T dc = T(2) * W * (common * (Q * a * bm) + k3 * (xz + xy - yz));   // (i,k)
               isa[rr] += da;
               iax[rr] = fma(da, cx, iax[rr]), iay[rr] = fma(da, cy, iay[rr]), iaz[rr] = fma(da, cz, iaz[rr]);
               isc[rr] += dc;
@@ -861,9 +865,9 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
               const T We = W * e;
               ie[rr] += e;
               ke += e;
-              idc[rr] += We * (TST(0, j, 4, row) + fDi[rr]);   // D^(i)_ij + D^(i)_ik
-              kdc += We * (Dkj + fDk[rr]);                      // D^(k)_kj + D^(k)_ki
-              jdc += We * (TST(0, j, 3, row) + Djk);           // D^(j)_ji + D^(j)_jk
+              idc[rr] += We * (TST(0, j, 4, row) + fDi[rr]);
+              kdc += We * (Dkj + fDk[rr]);
+              jdc += We * (TST(0, j, 3, row) + Djk);
             }
           }
           {  // x, y, z, dcn of the centre end up in the lanes 0, 8, 16, 24
