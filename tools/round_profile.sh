@@ -9,7 +9,7 @@ timeout 1500 python -m pytest tests -m gpu -q > $out/r02_pytest_gpu.log 2>&1; ec
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/r02_smoke.log 2>&1; tail -2 $out/r02_smoke.log
 rm -f $out/r02_ab_r01_final.txt
 for w in "c3" "c2" "c5" "c5 --dtype f32" "c3 --dtype f32" "c2 --dtype f32"; do
-  bash tools/ab.sh "--workload $w --steps 30 --warmup 5 --no-subs --no-e2e" build_ab/*.so 2>&1 | tee -a $out/r02_ab_r01_final.txt
+  bash tools/ab.sh "--workload $w --steps 30 --warmup 5 --no-subs --no-e2e" build_ab/r01.so build_ab/final.so 2>&1 | tee -a $out/r02_ab_r01_final.txt
 done
 b() { name=$1; shift; timeout 600 python bench.py "$@" > $out/r02_bench_$name.json 2> $out/r02_bench_$name.err; cut -c1-200 $out/r02_bench_$name.json; }
 b default --steps 20 --warmup 3
