@@ -99,13 +99,23 @@ def install(device: str | torch.device | int | None = None, name: str = "tad_dft
             _set(sub, "dftd4", dftd4)
             _set(sub, "get_properties", get_properties)
         rdisp = getattr(ref, "dispersion", None)
-        if rdisp is not None and hasattr(rdisp, "DispD4"):
-            fused = disp_mod.DispD4()
+        for cls_name in ("DispD4", "DispD4Exact"):  # DispD4Exact lives in dispersion.d4 of the reference
+            owner = rdisp if hasattr(rdisp, cls_name) else getattr(rdisp, "d4", None)
+            if owner is None or not hasattr(owner, cls_name):
+                continue
+            mine_cls = getattr(disp_mod, cls_name)
 
-            def calculate(self, numbers, positions, charge, param, **kw):
-                return placed(fused.calculate, device)(numbers, positions, charge, param, **kw)
+            def calculate(self, numbers, positions, charge, param, _cls=mine_cls, **kw):
+                # the reference instance keeps its model as a key (+ kwargs) or as an instance (base.py:152-178)
+                inst = getattr(self, "_model_instance", None)
+                if inst is not None:
+                    mine = _cls(model=inst)
+                else:
+                    mine = _cls(model=getattr(self, "_model_key", "d4"),
+                                model_kwargs=getattr(self, "_model_kwargs", None) or None)
+                return placed(mine.calculate, device)(numbers, positions, charge, param, **kw)
 
-            _set(rdisp.DispD4, "calculate", calculate)
+            _set(getattr(owner, cls_name), "calculate", calculate)
         return "rebound"
     alias = types.ModuleType(name)
     alias.__d4b200_alias__ = True
@@ -124,7 +134,11 @@ def install(device: str | torch.device | int | None = None, name: str = "tad_dft
             def calculate(self, *a, **kw):  # noqa: D102
                 return placed(super().calculate, device)(*a, **kw)
 
-        dsp.DispD4 = DispD4
+        class DispD4Exact(disp_mod.DispD4Exact):
+            def calculate(self, *a, **kw):  # noqa: D102
+                return placed(super().calculate, device)(*a, **kw)
+
+        dsp.DispD4, dsp.DispD4Exact = DispD4, DispD4Exact
         alias.dispersion = dsp
         sys.modules[name + ".dispersion"] = dsp
     dmod = types.ModuleType(name + ".disp")

@@ -107,3 +107,41 @@ def test_fused_term_driven_by_a_reference_style_disp_loop():
             dispersion.D4ATMApprox(charge_dependent=True).calculate(numbers, positions, param, cn, "d4", q)
         with pytest.raises(ValueError):
             dispersion.FusedD4Term().calculate(numbers, positions, param, cn, "d4", None)
+
+
+REF_SRC = Path("/root/reference/src")
+
+
+@pytest.mark.skipif(not REF_SRC.is_dir(), reason="reference tree not present on this box")
+def test_install_rebinds_an_importable_reference_and_its_disp_drives_the_terms():
+    """With the reference importable (here: its unmodified sources on top of oracle/mctc_shim) ``install()`` rebinds its
+    entry points instead of registering an alias, a reference ``DispD4`` instance keeps its model, and the reference's
+    OWN ``Disp.calculate`` loop (dispersion/base.py:409-431) drives a registered ``FusedD4Term``."""
+    numbers, positions, q = orc.organic_batch([9, 14], seed=29)
+    param = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)
+    charge = torch.zeros(2, dtype=torch.float64)
+    sys.path[:0] = [str(SHIM), str(REF_SRC)]
+    try:
+        with patch.object(d4, "dftd4", _oracle_dftd4), patch.object(dispersion, "dftd4", _oracle_dftd4):
+            assert d4.install() == "rebound"
+            import tad_dftd4 as ref
+            from tad_dftd4.dispersion.base import Disp as RefDisp
+
+            assert ref.__file__.startswith(str(REF_SRC)) and ref.dftd4 is _oracle_dftd4 and ref.disp.dftd4 is _oracle_dftd4
+            tpar = {k: torch.tensor(v, dtype=torch.float64) for k, v in param.items()}
+            for model in ("d4", "d4s"):
+                want = orc.dftd4(numbers, positions, param, q, model=model)
+                got = ref.dispersion.DispD4(model=model, dtype=torch.float64).calculate(numbers, positions, charge, tpar, q=q)
+                assert torch.allclose(got, want, rtol=1e-12, atol=1e-16)
+                driver = RefDisp(model=model, dtype=torch.float64)  # the reference's class, the reference's loop
+                driver.register(dispersion.FusedD4Term())
+                got = driver.calculate(numbers, positions, charge, tpar, q=q)
+                assert torch.allclose(got, want, rtol=1e-12, atol=1e-16)
+            d4.uninstall()
+            assert ref.dftd4 is not _oracle_dftd4  # the reference's own function is back
+    finally:
+        d4.uninstall()
+        sys.path.remove(str(SHIM))
+        sys.path.remove(str(REF_SRC))
+        for key in [k for k in sys.modules if k.split(".")[0] in ("tad_mctc", "tad_dftd4")]:
+            del sys.modules[key]
