@@ -25,7 +25,10 @@
 
 namespace d4b200 {
 
-constexpr int GROUP = 16;   // centres per ATM group
+#ifndef D4_LARGE_GROUP
+#define D4_LARGE_GROUP 16
+#endif
+constexpr int GROUP = D4_LARGE_GROUP;   // centres per ATM group (<= 32: one mask bit each)
 constexpr int TILE = 32;    // atoms per tile of the union list
 constexpr int AVEC = 24;    // padded length of a polarizability vector
 
