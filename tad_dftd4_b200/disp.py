@@ -692,7 +692,7 @@ def dftd4_host(
     model_id, ga, gc, wf = spec
     par = _flatten_param(param, cutoff, model_id, wf)
     dev = torch.device("cuda", device) if isinstance(device, int) else device
-    engine = _Engine.get(dev, ga, gc, spec.ref_charges)
+    engine = _Engine.get(dev, ga, gc, spec.ref_charges, spec.c9_frequency)
     nat = numbers.shape[-1]
     if nat > _small_limit(engine, positions.dtype, bool(with_gradient), model_id):
         raise NotImplementedError("dftd4_host handles batches of small structures; use dftd4 for large ones")

@@ -127,3 +127,27 @@ def test_registered_term_combinations_are_sums_of_launches():
     assert close(disp.calculate(nd, pd, 0.0, nopar).cpu(), e3d)
     with pytest.raises(NotImplementedError):
         run([TwoBodyTerm(), D4ATMApprox(charge_dependent=True)], q=qd)
+
+
+@pytest.mark.gpu
+def test_exact_c9_and_gfn2_charges_in_the_tiled_large_system_family():
+    """Structures beyond the one-CTA-per-structure kernels take the tiled family; the single-node tables (exact C9)
+    and the GFN2 reference charges reach it through the model tuple (large.py)."""
+    import tad_dftd4_b200 as d4
+    from tad_dftd4_b200.dispersion import DispD4Exact
+
+    dev = torch.device("cuda:0")
+    n, p, q = orc.organic_batch([150], seed=41)
+    n, p, q = n[0], p[0], q[0]
+    par = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)
+    for kind in ("exact", "gfn2"):
+        okw = dict(c9="exact") if kind == "exact" else dict(ref_charges="gfn2")
+        e_ref, g_ref = orc.energy_and_gradient(n, p, par, q, **okw)
+        pos = p.to(dev).requires_grad_(True)
+        if kind == "exact":
+            e = DispD4Exact().calculate(n.to(dev), pos, 0.0, par, q=q.to(dev))
+        else:
+            e = d4.dftd4(n.to(dev), pos, 0.0, par, q=q.to(dev), model=d4.D4Model(n.to(dev), ref_charges="gfn2"))
+        (g,) = torch.autograd.grad(e.sum(), pos)
+        assert ((e.detach().cpu() - e_ref).abs().max() / e_ref.abs().max()).item() < 1e-10, kind
+        assert (g.cpu() - g_ref).abs().max().item() < 1e-9, kind
