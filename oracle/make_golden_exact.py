@@ -31,7 +31,7 @@ import d4_oracle as orc  # noqa: E402
 GOLDEN = HERE.parent / "tests" / "golden"
 OUT = GOLDEN / "exact"
 F64 = torch.float64
-CASES = ("single_pbe0", "sih4_tpssh", "organic_33", "ragged_batch", "tight_cutoffs")
+CASES = ("single_pbe0", "sih4_tpssh", "organic_33", "ragged_batch", "tight_cutoffs", "all_elements")
 
 
 def main() -> None:

@@ -10,7 +10,7 @@ import torch
 import d4_oracle as orc
 from helpers import GOLDEN, as_torch, load_golden
 
-CASES = ("single_pbe0", "sih4_tpssh", "organic_33", "ragged_batch", "tight_cutoffs")
+CASES = ("single_pbe0", "sih4_tpssh", "organic_33", "ragged_batch", "tight_cutoffs", "all_elements")
 
 
 def _load(name):
