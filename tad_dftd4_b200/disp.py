@@ -622,11 +622,6 @@ def dftd4(
         counts = (num2 != 0).sum(-1)
         big = torch.nonzero(counts > limit).flatten().tolist()
         if big:
-            if ptens:
-                raise NotImplementedError(
-                    "gradients with respect to the damping parameters are provided for structures "
-                    "of the one-CTA-per-structure kernels only"
-                )
             if model_id != 0:
                 raise NotImplementedError("the tiled large-system path supports model='d4' only")
             from .large import dftd4_large

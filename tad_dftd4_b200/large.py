@@ -173,7 +173,10 @@ def _kernel_compute(engine, par, numbers, positions, q, rows, groups, want_cost)
 # row / centre-group ranges.  Any atom order is correct and the ranges only balance the load,
 # so both are reused for as long as the SAME ``numbers`` tensor comes back (a geometry
 # optimisation or MD run moves the atoms a little per step); a call with another tensor,
-# another world size or an in-place change of ``numbers`` builds a new plan.
+# another world size or an in-place change of ``numbers`` builds a new plan.  The key is the
+# tensor's address + version (no reference is kept), so a hit is confirmed against a copy of the
+# atomic numbers the plan was made for: the caching allocator hands the address of a freed
+# tensor to the next structure of the same size.
 _PLAN_CACHE: dict[tuple, tuple] = {}
 _PLAN_CACHE_SIZE = 4
 
@@ -192,9 +195,13 @@ class _Plan:
         key = (numbers.data_ptr(), numbers._version, tuple(numbers.shape), str(numbers.device), self.world,
                self.rank, id(group), gs)  # fmt: skip
         hit = _PLAN_CACHE.get(key)
+        if hit is not None and not torch.equal(hit[4], numbers):
+            # the address of a freed tensor came back with another structure of the same size (or the tensor was
+            # changed behind the version counter): the key matches, the plan does not
+            hit = None
         with _section("plan"):
             if hit is not None:
-                self.order, self.numbers, self.rows, self.groups = hit
+                self.order, self.numbers, self.rows, self.groups = hit[:4]
             else:
                 keep = torch.nonzero(numbers != 0).flatten()
                 self.order = keep[morton_order(positions[keep])]
@@ -216,7 +223,8 @@ class _Plan:
                 self.rows, self.groups = (r0, r1), (g0, g1)
                 while len(_PLAN_CACHE) >= _PLAN_CACHE_SIZE:
                     _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-                _PLAN_CACHE[key] = (self.order, self.numbers, self.rows, self.groups)
+                _PLAN_CACHE.pop(key, None)
+                _PLAN_CACHE[key] = (self.order, self.numbers, self.rows, self.groups, numbers.detach().clone())
 
     def all_reduce(self, t: Tensor) -> Tensor:
         if self.world > 1:
@@ -228,17 +236,12 @@ class _Plan:
 def _kernel_backend(positions: Tensor, param, cutoff, model=None):
     """``model``: (ga, gc, wf[, ref_charges[, c9_frequency]]) of the caller's D4Model (defaults when None)."""
     from . import _lib, defaults
-    from .disp import _Engine, _flatten_param, _param_tensors
+    from .disp import _Engine, _flatten_param
 
     ga, gc, wf, *rest = model if model is not None else (defaults.GA_DEFAULT, defaults.GC_DEFAULT, defaults.WF_DEFAULT)
     ref_charges = rest[0] if rest else "eeq"
     c9_frequency = rest[1] if len(rest) > 1 else None
 
-    if _param_tensors(param):
-        raise NotImplementedError(
-            "gradients with respect to the damping parameters are provided for structures of the "
-            "one-CTA-per-structure kernels only (detach the parameters for the tiled large-system path)"
-        )
     engine = _Engine.get(positions.device, ga, gc, ref_charges, c9_frequency)
     par = _flatten_param(param, cutoff, 0, wf)
     lib = engine.lib
@@ -350,11 +353,78 @@ def dftd4_large_vjp(numbers, positions, param, q, gout, *, cutoff=None, group=No
     return gpos, gq
 
 
+def _plain_param(param) -> dict:
+    """The damping parameters as plain floats (the kernels take them by value)."""
+    return {k: (float(v.detach()) if isinstance(v, Tensor) else v) for k, v in param.items()}
+
+
+# fourth-order central differences (multiples of the step, weights)
+_FD4 = ((-2.0, 1.0 / 12.0), (-1.0, -8.0 / 12.0), (1.0, 8.0 / 12.0), (2.0, -1.0 / 12.0))
+
+
+def large_param_vjp(numbers, positions, param, q, gout, need, *, cutoff=None, group=None, model=None) -> list:
+    """``d(sum_i gout_i E_i)/d(s6, s8, s9, s10, a1, a2, alp)`` of ONE large structure (entries of ``need``).
+
+    The reference differentiates its dense tape (``test/test_grad/test_param.py:40-100``); the one-CTA family has
+    analytic kernels for this (``csrc/d4b200_param.cu``).  Here the tiled energy kernels are re-run instead: the
+    energy is LINEAR in the scaling factors, so ``dE/ds6``, ``dE/ds8``, ``dE/ds10`` and ``dE/ds9`` are the energies of
+    the corresponding part alone (the other factors switched off -- exact), and ``a1``, ``a2``, ``alp`` enter smoothly
+    through the damping radii / exponent, where fourth-order central differences of the weighted energy (relative step
+    1e-3) are accurate to ~1e-11 relative.  Up to 3 two-body + 1 ATM launches for the factors, 8 full and 4 ATM-only
+    energy evaluations for the rest; every evaluation is all-reduced like the energy itself, so all ranks agree."""
+    from . import defaults
+
+    base = _plain_param(param)
+    g = None if gout is None else gout.detach()
+
+    def weighted(par) -> Tensor:
+        e = large_energy(numbers, positions.detach(), par, q.detach(), cutoff=cutoff, group=group, model=model)
+        return (e.sum() if g is None else (e * g).sum()).double()
+
+    def part(**on) -> Tensor:  # one linear part: its factor = 1, the others = 0
+        par = dict(base, s6=0.0, s8=0.0, s9=0.0)
+        par.pop("s10", None)
+        par.update(on)
+        return weighted(par)
+
+    def fd(key: str, default: float, atm_only: bool) -> Tensor:
+        x = float(base.get(key, default) if base.get(key) is not None else default)
+        h = 1e-3 * max(abs(x), 1.0)
+        total = torch.zeros((), dtype=torch.float64, device=positions.device)
+        for mult, coef in _FD4:
+            par = dict(base)
+            par[key] = x + mult * h
+            if atm_only:  # the two-body part does not depend on this parameter
+                par.update(s6=0.0, s8=0.0)
+                par.pop("s10", None)
+            total = total + coef * weighted(par)
+        return total / h
+
+    s9 = float(base.get("s9", defaults.S9) if base.get("s9") is not None else defaults.S9)
+    out: list = [None] * 7
+    if need[0]:
+        out[0] = part(s6=1.0)
+    if need[1]:
+        out[1] = part(s8=1.0)
+    if need[2]:
+        out[2] = part(s9=1.0)
+    if need[3]:
+        out[3] = part(s10=1.0)
+    if need[4]:
+        out[4] = fd("a1", defaults.A1, False)
+    if need[5]:
+        out[5] = fd("a2", defaults.A2, False)
+    if need[6]:
+        out[6] = fd("alp", defaults.ALP, True) if s9 != 0.0 else torch.zeros((), dtype=torch.float64, device=positions.device)
+    return out
+
+
 class _LargeFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, positions, q, numbers, param, cutoff, group, model):
+    def forward(ctx, positions, q, numbers, param, cutoff, group, model, *ptens):
         ctx.save_for_backward(positions, q, numbers)
         ctx.param, ctx.cutoff, ctx.group, ctx.model = param, cutoff, group, model
+        ctx.ptens = ptens
         ctx.cached = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             # inputs on the tape: energies AND the gradient of sum(E) from one set of launches (the
@@ -370,12 +440,24 @@ class _LargeFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         positions, q, numbers = ctx.saved_tensors
-        if ctx.cached is not None and all(s == 0 for s in gout.stride()):
-            c = gout.reshape(-1)[0]
-            return ctx.cached[0] * c, ctx.cached[1] * c, None, None, None, None, None
-        gpos, gq = dftd4_large_vjp(numbers, positions, ctx.param, q, gout.contiguous(),
-                                   cutoff=ctx.cutoff, group=ctx.group, model=ctx.model)  # fmt: skip
-        return gpos, gq, None, None, None, None, None
+        need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gpos = gq = None
+        if need_in:
+            if ctx.cached is not None and all(s == 0 for s in gout.stride()):
+                c = gout.reshape(-1)[0]
+                gpos, gq = ctx.cached[0] * c, ctx.cached[1] * c
+            else:
+                gpos, gq = dftd4_large_vjp(numbers, positions, ctx.param, q, gout.contiguous(),
+                                           cutoff=ctx.cutoff, group=ctx.group, model=ctx.model)  # fmt: skip
+        gpar: list = [None] * len(ctx.ptens)
+        need = [k < len(ctx.ptens) and ctx.ptens[k] is not None and ctx.needs_input_grad[7 + k] for k in range(7)]
+        if any(need):
+            vals = large_param_vjp(numbers, positions, ctx.param, q, gout.contiguous(), need, cutoff=ctx.cutoff,
+                                   group=ctx.group, model=ctx.model)  # fmt: skip
+            for k, v in enumerate(vals):
+                if v is not None:
+                    gpar[k] = v.to(ctx.ptens[k].dtype).reshape(ctx.ptens[k].shape)
+        return (gpos, gq, None, None, None, None, None, *gpar)
 
 
 def dftd4_large(
@@ -404,4 +486,8 @@ def dftd4_large(
     if compute is not None:
         be = dict(energy=compute, group_size=group_size or 16)
         return large_energy(numbers, positions, param, q, cutoff=cutoff, group=group, backend=be)
-    return _LargeFunction.apply(positions, q, numbers, param, cutoff, group, model)
+    from .disp import _param_tensors
+
+    ptens = _param_tensors(param)  # damping parameters on the tape (tensors with requires_grad)
+    return _LargeFunction.apply(positions, q, numbers, _plain_param(param) if ptens else param, cutoff, group, model,
+                                *ptens)  # fmt: skip

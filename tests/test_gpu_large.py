@@ -179,3 +179,26 @@ def test_cross_rank_equals_single_rank():
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert res["ranks"] == n and res["max_rel_energy_diff"] < 1e-12 and res["max_abs_gradient_diff"] < 1e-12
+
+
+def test_plan_cache_is_confirmed_against_the_atomic_numbers():
+    """Two different structures of the same size behind the same address / version (what the caching allocator
+    produces when the first one is freed): the cached plan of the first must not be used for the second."""
+    from tad_dftd4_b200 import large
+
+    dev = torch.device("cuda:0")
+    large.clear_plan_cache()
+    n1, p1, q1 = _cluster(150, seed=1)
+    n2, p2, q2 = _cluster(150, seed=2)
+    assert not torch.equal(n1, n2)
+    numbers = n1.to(dev)
+    e1 = large.dftd4_large(numbers, p1.to(dev), PBE0, q1.to(dev)).cpu()
+    numbers.data.copy_(n2.to(dev))  # same address, same version counter, other structure
+    e2 = large.dftd4_large(numbers, p2.to(dev), PBE0, q2.to(dev)).cpu()
+    for e, (n, p, q) in ((e1, (n1, p1, q1)), (e2, (n2, p2, q2))):
+        ref = orc.dftd4(n, p, PBE0, q)
+        assert (e - ref).abs().max() / ref.abs().max() < 1e-10
+    # and an unchanged tensor still hits
+    before = len(large._PLAN_CACHE)
+    large.dftd4_large(numbers, p2.to(dev) + 0.01, PBE0, q2.to(dev))
+    assert len(large._PLAN_CACHE) == before

@@ -178,3 +178,21 @@ def test_param_gradient_reference_golden(name, model):
     assert keys == list(KEYS)
     for k, r, v in zip(keys, case[f"grad_param_{model}"], got):
         assert abs(v - r) <= 1e-12 + 1e-9 * abs(r), (k, float(v), float(r))
+
+
+def test_param_gradients_in_the_tiled_large_system_family():
+    """A structure beyond the one-CTA kernels (150 atoms): parameter gradients from re-run tiled energy kernels
+    (large.large_param_vjp: exact parts for the scaling factors, 4th-order differences for a1 / a2 / alp), together
+    with the position gradient of the same weighted sum, against autograd of the float64 oracle."""
+    numbers, positions, q = orc.organic_batch([150], seed=43)
+    case = {"numbers": numbers[0].numpy(), "positions": positions[0].numpy(), "q": q[0].numpy(), "cutoff": {}}
+    base = dict(TPSS0, s10=0.3)
+    g = _upstream(case, seed=9)
+    keys, want = _oracle(case, base, "d4", g, with_pos=True)
+    keys2, got = _cuda(case, base, "d4", g, with_pos=True)
+    assert keys == keys2
+    for k, w, v in zip(keys + ["positions"], want, got):
+        if k == "positions":
+            assert np.abs(v - w).max() < 1e-9, k
+        else:
+            assert abs(v - w) <= 1e-8 * abs(w) + 1e-12, (k, float(v), float(w))
