@@ -21,10 +21,16 @@
 #include <math.h>
 
 #include "d4b200_handle.cuh"
+#include <cstdint>
+#include <cstdlib>
+
 #include "d4b200_small.cuh"  // math shims, d4_rcp, d4_zero_damp_arg, warp_sum
 
 namespace d4b200 {
 
+#ifndef D4_LARGE_PIPE_DEFAULT
+#define D4_LARGE_PIPE_DEFAULT true  // large_atm_grad_pipe instead of large_atm_grad (D4B200_LARGE_PIPE=0/1 overrides)
+#endif
 #ifndef D4_LARGE_GROUP
 #define D4_LARGE_GROUP 16
 #endif
@@ -913,6 +919,345 @@ __global__ void __launch_bounds__(512, 1) large_atm_grad(LargeArgs<T> A) {
 #undef TST
 }
 
+// The same kernel as a double-buffered pipeline: everything a tile pair needs sits in per-CTA global scratch in
+// the layout of the shared-memory arrays (written once per centre group by the prologue), and one thread moves
+// the NEXT pair into the other buffer with bulk-async copies (cp.async.bulk + mbarrier, UBLKCP in SASS) while
+// the CTA evaluates the current one: one block barrier per pair, no load latency on the path.
+template <typename T>
+__host__ __device__ constexpr size_t atm_pipe_buffer_bytes() {
+  return sizeof(T) * (2 * 2 * TILE * (AVEC + 1) + 5 * 2 * TILE + 2 * GROUP * GSTASH * TILE) + sizeof(int) * 4 * TILE;
+}
+template <typename T>
+__host__ __device__ constexpr size_t atm_pipe_smem() {
+  return sizeof(T) * (2 * GROUP * AVEC + 5 * GROUP) + 2 * atm_pipe_buffer_bytes<T>() + sizeof(int) * (GROUP + 4) + 32;
+}
+// per-CTA scratch of the pipeline, in tiles of TILE list atoms
+template <typename T>
+__host__ __device__ constexpr size_t atm_pipe_tile_bytes() {
+  return sizeof(T) * (GROUP * GSTASH * TILE + 2 * TILE * (AVEC + 1) + 5 * TILE) + sizeof(int) * 2 * TILE;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1) large_atm_grad_pipe(LargeArgs<T> A) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  T* p = reinterpret_cast<T*>(dsm);
+  T* const cA0 = p;                 p += GROUP * AVEC;         // centres: A0
+  T* const cdA = p;                 p += GROUP * AVEC;         // centres: dA0/dcn
+  T* const cpx = p;                 p += GROUP;
+  T* const cpy = p;                 p += GROUP;
+  T* const cpz = p;                 p += GROUP;
+  T* const csq = p;                 p += GROUP;
+  T* const cg = p;                  p += GROUP;
+  unsigned char* const buf0 = reinterpret_cast<unsigned char*>(p);
+  int* const creal = reinterpret_cast<int*>(buf0 + 2 * atm_pipe_buffer_bytes<T>());
+  int* const gcur = creal + GROUP;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(gcur + 4) + 7) & ~uintptr_t(7));
+  // arrays of the CURRENT buffer (same names and layouts as in large_atm_grad)
+  T *tA0, *tdA, *tpx, *tpy, *tpz, *tsq, *tg, *tst;
+  int* tidx;
+  unsigned* tmask;
+  auto select = [&](int b) {
+    T* q = reinterpret_cast<T*>(buf0 + (size_t)b * atm_pipe_buffer_bytes<T>());
+    tA0 = q, q += 2 * TILE * (AVEC + 1);
+    tdA = q, q += 2 * TILE * (AVEC + 1);
+    tpx = q, q += 2 * TILE;
+    tpy = q, q += 2 * TILE;
+    tpz = q, q += 2 * TILE;
+    tsq = q, q += 2 * TILE;
+    tg = q, q += 2 * TILE;
+    tst = q, q += 2 * GROUP * GSTASH * TILE;
+    tidx = reinterpret_cast<int*>(q);
+    tmask = reinterpret_cast<unsigned*>(tidx + 2 * TILE);
+  };
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Par<T>& P = A.par;
+  // scratch of this CTA: [tile] x { stash [GROUP][GSTASH][TILE], A0 [TILE][AVEC+1], dA0 [TILE][AVEC+1],
+  // x, y, z, sqrt_r4r2, g [TILE] each, index [TILE], mask [TILE] }
+  const int ntmax = (A.ucap + TILE - 1) / TILE;
+  unsigned char* const scr = reinterpret_cast<unsigned char*>(A.cstash) + (size_t)blockIdx.x * ntmax * atm_pipe_tile_bytes<T>();
+  constexpr size_t O_A0 = sizeof(T) * GROUP * GSTASH * TILE, O_DA = O_A0 + sizeof(T) * TILE * (AVEC + 1),
+                   O_AT = O_DA + sizeof(T) * TILE * (AVEC + 1), O_IX = O_AT + sizeof(T) * 5 * TILE,
+                   O_MK = O_IX + sizeof(int) * TILE;
+  auto tile_ptr = [&](int tile) { return scr + (size_t)tile * atm_pipe_tile_bytes<T>(); };
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
+  unsigned parity0 = 0, parity1 = 0;
+  // thread 0: bring tile pair (tx, ty) into buffer b
+  auto issue = [&](int b, int tx, int ty) {
+    unsigned char* dst = buf0 + (size_t)b * atm_pipe_buffer_bytes<T>();
+    T* q = reinterpret_cast<T*>(dst);
+    T* const dA0 = q;  q += 2 * TILE * (AVEC + 1);
+    T* const ddA = q;  q += 2 * TILE * (AVEC + 1);
+    T* const dat = q;  q += 5 * 2 * TILE;
+    T* const dst_st = q;  q += 2 * GROUP * GSTASH * TILE;
+    int* const dix = reinterpret_cast<int*>(q);
+    unsigned* const dmk = reinterpret_cast<unsigned*>(dix + 2 * TILE);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of this buffer are done
+    mbar_expect_tx(&bars[b], (unsigned)(2 * atm_pipe_tile_bytes<T>()));
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const unsigned char* src = tile_ptr(side == 0 ? tx : ty);
+      bulk_g2s(dst_st + side * GROUP * GSTASH * TILE, src, sizeof(T) * GROUP * GSTASH * TILE, &bars[b]);
+      bulk_g2s(dA0 + side * TILE * (AVEC + 1), src + O_A0, sizeof(T) * TILE * (AVEC + 1), &bars[b]);
+      bulk_g2s(ddA + side * TILE * (AVEC + 1), src + O_DA, sizeof(T) * TILE * (AVEC + 1), &bars[b]);
+#pragma unroll
+      for (int c = 0; c < 5; ++c)
+        bulk_g2s(dat + (c * 2 + side) * TILE, src + O_AT + sizeof(T) * c * TILE, sizeof(T) * TILE, &bars[b]);
+      bulk_g2s(dix + side * TILE, src + O_IX, sizeof(int) * TILE, &bars[b]);
+      bulk_g2s(dmk + side * TILE, src + O_MK, sizeof(unsigned) * TILE, &bars[b]);
+    }
+  };
+#define TST(side, j, comp, l) tst[(((side) * GROUP + (j)) * GSTASH + (comp)) * TILE + (l)]
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) *gcur = atomicAdd(A.queue, 1);
+    __syncthreads();
+    const int g = A.group_begin + *gcur / A.nslice, slice = *gcur % A.nslice;
+    if (g >= A.group_end) break;
+    const int nU = A.ucount[g];
+    const int* list = A.ulist + (size_t)g * A.ucap;
+    const unsigned* masks = A.umask + (size_t)g * A.ucap;
+    for (int t = tid; t < GROUP * AVEC; t += 512) {
+      const int j = g * GROUP + t / AVEC;
+      cA0[t] = j < A.nat ? A.a0[(size_t)j * AVEC + (t % AVEC)] : T(0);
+      cdA[t] = j < A.nat ? A.da0_cn[(size_t)j * AVEC + (t % AVEC)] : T(0);
+    }
+    if (tid < GROUP) {
+      const int j = g * GROUP + tid;
+      const int zj = j < A.nat ? (int)A.numbers[j] : 0;
+      creal[tid] = zj > 0 && zj < NELEM;
+      cpx[tid] = j < A.nat ? A.pos[3 * j] : T(0);
+      cpy[tid] = j < A.nat ? A.pos[3 * j + 1] : T(0);
+      cpz[tid] = j < A.nat ? A.pos[3 * j + 2] : T(0);
+      csq[tid] = creal[tid] ? A.tab.sqrt_r4r2[zj] : T(0);
+      cg[tid] = creal[tid] ? (A.gin ? A.gin[j] : T(1)) : T(0);
+    }
+    __syncthreads();
+    // ---- prologue: centre stash (5 values) for the whole list
+    for (int t = tid; t < GROUP * nU; t += 512) {
+      const int j = t / nU, u = t - j * nU;
+      const int x = list[u];
+      T a = T(1), Pv = T(0), uv = T(0), Dj = T(0), Dx = T(0);
+      if (masks[u] >> j & 1u) {
+        const T dx = A.pos[3 * x] - cpx[j], dy = A.pos[3 * x + 1] - cpy[j], dz = A.pos[3 * x + 2] - cpz[j];
+        const T r2 = dx * dx + dy * dy + dz * dz;
+        const T rinv = d4_rcp(d4_sqrt(r2));
+        T c6 = T(0), dj = T(0), dxv = T(0);
+        const T* ax = A.a0 + (size_t)x * AVEC;
+        const T* dax = A.da0_cn + (size_t)x * AVEC;
+#pragma unroll
+        for (int w = 0; w < NFREQ; ++w) {
+          c6 += cA0[j * AVEC + w] * ax[w];
+          dj += cdA[j * AVEC + w] * ax[w];
+          dxv += dax[w] * cA0[j * AVEC + w];
+        }
+        const T R0 = P.a1 * csq[j] * A.tab.sqrt_r4r2[(int)A.numbers[x]] + P.a2;
+        a = r2;
+        Pv = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+        uv = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
+        const T h = c6 != T(0) ? T(0.5) * d4_rcp(c6) : T(0);
+        Dj = dj * h;
+        Dx = dxv * h;
+      }
+      {
+        T* const st = reinterpret_cast<T*>(tile_ptr(u / TILE)) + (size_t)j * GSTASH * TILE + (u % TILE);
+        st[0 * TILE] = a;
+        st[1 * TILE] = Pv;
+        st[2 * TILE] = uv;
+        st[3 * TILE] = Dj;
+        st[4 * TILE] = Dx;
+      }
+    }
+    const int ntile = (nU + TILE - 1) / TILE;
+    // padding of the last tile, and the tile atoms themselves (what large_atm_grad gathers per pair)
+    for (int t = tid; t < GROUP * GSTASH * (ntile * TILE - nU); t += 512) {
+      const int jc = t / (ntile * TILE - nU), u = nU + t % (ntile * TILE - nU);
+      reinterpret_cast<T*>(tile_ptr(u / TILE))[(size_t)jc * TILE + (u % TILE)] = T(0);
+    }
+    for (int u = tid; u < ntile * TILE; u += 512) {
+      unsigned char* tp = tile_ptr(u / TILE);
+      const int l = u % TILE;
+      const bool ok = u < nU;
+      const int x = ok ? list[u] : 0;
+      T* at = reinterpret_cast<T*>(tp + O_AT);
+      at[0 * TILE + l] = ok ? A.pos[3 * x] : T(0);
+      at[1 * TILE + l] = ok ? A.pos[3 * x + 1] : T(0);
+      at[2 * TILE + l] = ok ? A.pos[3 * x + 2] : T(0);
+      at[3 * TILE + l] = ok ? A.tab.sqrt_r4r2[(int)A.numbers[x]] : T(0);
+      at[4 * TILE + l] = ok ? (A.gin ? A.gin[x] : T(1)) : T(0);
+      reinterpret_cast<int*>(tp + O_IX)[l] = ok ? x : -1;
+      reinterpret_cast<unsigned*>(tp + O_MK)[l] = ok ? masks[u] : 0u;
+    }
+    for (int t = tid; t < ntile * TILE * (AVEC + 1); t += 512) {
+      const int u = t / (AVEC + 1), w = t - u * (AVEC + 1);
+      const bool ok = u < nU && w < AVEC;
+      const size_t src = ok ? (size_t)list[u] * AVEC + w : 0;
+      unsigned char* tp = tile_ptr(u / TILE);
+      reinterpret_cast<T*>(tp + O_A0)[(u % TILE) * (AVEC + 1) + w] = ok ? A.a0[src] : T(0);
+      reinterpret_cast<T*>(tp + O_DA)[(u % TILE) * (AVEC + 1) + w] = ok ? A.da0_cn[src] : T(0);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // the scratch is read through the async proxy
+    __syncthreads();
+
+    // ---- tile pairs (tx <= ty, tx = slice, slice + nslice, ...) as one sequence, one pair in flight ahead
+    int tx = slice, ty = slice, nb = 0;
+    if (tx < ntile && tid == 0) issue(0, tx, ty);
+    while (tx < ntile) {
+      int nx = tx, ny = ty + 1;
+      if (ny >= ntile) nx = tx + A.nslice, ny = nx;
+      if (nx < ntile && tid == 0) issue(nb ^ 1, nx, ny);
+      select(nb);
+      if (nb == 0) {
+        mbar_wait(&bars[0], parity0);
+        parity0 ^= 1u;
+      } else {
+        mbar_wait(&bars[1], parity1);
+        parity1 ^= 1u;
+      }
+      {
+        {
+        // ---- faces of this lane: rows 2w, 2w+1 x column `lane`
+        const int kk = tidx[TILE + lane];
+        const unsigned mk = tmask[TILE + lane];
+        const T gk = tg[TILE + lane];
+        const T kx = tpx[TILE + lane], ky = tpy[TILE + lane], kz = tpz[TILE + lane];
+        T fc_[2], fP[2], fu[2], fDi[2], fDk[2];
+        bool pv[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = warp * 2 + rr;
+          const int ii = tidx[row];
+          pv[rr] = ii >= 0 && kk >= 0 && ii != kk && (tx != ty || row < lane) && (tmask[row] & mk) != 0u;
+          fc_[rr] = T(1), fP[rr] = T(0), fu[rr] = T(0), fDi[rr] = T(0), fDk[rr] = T(0);
+          const T rx = tpx[row] - kx, ry = tpy[row] - ky, rz = tpz[row] - kz;  // R_i - R_k
+          if (pv[rr]) {
+            const T c = rx * rx + ry * ry + rz * rz;
+            const T rinv = d4_rcp(d4_sqrt(c));
+            T c6 = T(0), di = T(0), dk = T(0);
+            const T* ai = &tA0[row * (AVEC + 1)];
+            const T* ak = &tA0[(TILE + lane) * (AVEC + 1)];
+            const T* dai = &tdA[row * (AVEC + 1)];
+            const T* dak = &tdA[(TILE + lane) * (AVEC + 1)];
+#pragma unroll
+            for (int w = 0; w < NFREQ; ++w) {
+              c6 += ai[w] * ak[w];
+              di += dai[w] * ak[w];
+              dk += dak[w] * ai[w];
+            }
+            const T R0 = P.a1 * tsq[row] * tsq[TILE + lane] + P.a2;
+            const T h = c6 != T(0) ? T(0.5) * d4_rcp(c6) : T(0);
+            fc_[rr] = c;
+            fP[rr] = P.fac9 * d4_sqrt(fabs(c6)) * (rinv * rinv * rinv);
+            fu[rr] = d4_zero_damp_arg(R0 * rinv, P.alp3, P.alp16 != 0);
+            fDi[rr] = di * h;
+            fDk[rr] = dk * h;
+          }
+        }
+        // Forces without per-visit difference vectors: with the edge derivatives da (j,i), db (j,k), dc (i,k)
+        //   F_i = R_i sum_j da - sum_j da R_j + (R_i - R_k) sum_j dc      per (row, lane)
+        //   F_k = R_k sum db - sum db R_j - sum_rows (R_i - R_k) sum_j dc  per lane
+        //   F_j = R_j sum (da + db) - sum (da R_i + db R_k)               per centre
+        // i.e. 17 instead of 30 FP64 operations per visit for the force part.
+        T ksb = T(0), kbx = T(0), kby = T(0), kbz = T(0), kdc = T(0);   // column atom k
+        T isa[2] = {T(0), T(0)}, iax[2] = {T(0), T(0)}, iay[2] = {T(0), T(0)}, iaz[2] = {T(0), T(0)};
+        T isc[2] = {T(0), T(0)}, idc[2] = {T(0), T(0)};
+        T ie[2] = {T(0), T(0)}, ke = T(0);  // fused energy + gradient call: E_i += e, E_k += e per centre (large_atm)
+        for (int j = 0; j < GROUP; ++j) {
+          T jvx = T(0), jvy = T(0), jvz = T(0), js = T(0), jdc = T(0);   // centre j
+          const T b = TST(1, j, 0, lane), Pb = TST(1, j, 1, lane), ub = TST(1, j, 2, lane);
+          const T Djk = TST(1, j, 3, lane), Dkj = TST(1, j, 4, lane);
+          const T cx = cpx[j], cy = cpy[j], cz = cpz[j];
+          const bool kin = mk >> j & 1u;
+          // both rows of the lane as ONE straight-line block (masked instead of branched): two independent
+          // dependency chains in flight
+          const bool in0 = tmask[warp * 2] >> j & 1u, in1 = tmask[warp * 2 + 1] >> j & 1u;  // warp-uniform
+          if (in0 | in1) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int row = warp * 2 + rr;
+              const bool act = pv[rr] && kin && (rr ? in1 : in0);
+              // masked lanes run on a unit triangle (finite everywhere) and contribute psf = 0
+              const T a = act ? TST(0, j, 0, row) : T(1), c = act ? fc_[rr] : T(1), bm = act ? b : T(1);
+              const T X = a + bm - c, Y = a - bm + c, Z = bm + c - a;
+              const T s = X * Y * Z;
+              const T abc = a * bm * c;
+              const T t = TST(0, j, 2, row) * ub * fu[rr];
+              const T d = T(1) + T(6) * t;
+              const T inv = d4_rcp(abc * d);
+              const T Q = inv * d, f = inv * abc;
+              const T psf = act ? TST(0, j, 1, row) * Pb * fP[rr] * f : T(0);
+              const T e = (T(0.375) * s * Q + T(1)) * psf;
+              const T W = tg[row] + gk;
+              const T common = e * (T(-2.5) + T(3) * P.alp3 * f * t) + psf;
+              const T k3 = T(0.375) * psf * Q;
+              const T yz = Y * Z, xz = X * Z, xy = X * Y;
+              const T da = T(2) * W * (common * (Q * bm * c) + k3 * (yz + xz - xy));   // (j,i)
+              const T db = T(2) * W * (common * (Q * a * c) + k3 * (yz - xz + xy));   // (j,k)
+              const T dc = T(2) * W * (common * (Q * a * bm) + k3 * (xz + xy - yz));   // (i,k)
+              isa[rr] += da;
+              iax[rr] = fma(da, cx, iax[rr]), iay[rr] = fma(da, cy, iay[rr]), iaz[rr] = fma(da, cz, iaz[rr]);
+              isc[rr] += dc;
+              ksb += db;
+              kbx = fma(db, cx, kbx), kby = fma(db, cy, kby), kbz = fma(db, cz, kbz);
+              jvx = fma(da, tpx[row], fma(db, kx, jvx));
+              jvy = fma(da, tpy[row], fma(db, ky, jvy));
+              jvz = fma(da, tpz[row], fma(db, kz, jvz));
+              js += da + db;
+              const T We = W * e;
+              ie[rr] += e;
+              ke += e;
+              idc[rr] += We * (TST(0, j, 4, row) + fDi[rr]);
+              kdc += We * (Dkj + fDk[rr]);
+              jdc += We * (TST(0, j, 3, row) + Djk);
+            }
+          }
+          {  // x, y, z, dcn of the centre end up in the lanes 0, 8, 16, 24
+            const T tot = warp_sum4(fma(js, cx, -jvx), fma(js, cy, -jvy), fma(js, cz, -jvz), jdc, lane);
+            if ((lane & 7) == 0 && tot != T(0)) {
+              const int jj = g * GROUP + j, which = lane >> 3;
+              atomicAdd(which < 3 ? &A.force[3 * jj + which] : &A.dcn[jj], tot);
+            }
+          }
+        }
+        T kfx = fma(ksb, kx, -kbx), kfy = fma(ksb, ky, -kby), kfz = fma(ksb, kz, -kbz);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = warp * 2 + rr;
+          const T px = tpx[row], py = tpy[row], pz = tpz[row];
+          const T cxk = isc[rr] * (px - kx), cyk = isc[rr] * (py - ky), czk = isc[rr] * (pz - kz);  // (i,k) edge
+          kfx -= cxk, kfy -= cyk, kfz -= czk;
+          const T tot = warp_sum4(fma(isa[rr], px, -iax[rr]) + cxk, fma(isa[rr], py, -iay[rr]) + cyk,
+                                  fma(isa[rr], pz, -iaz[rr]) + czk, idc[rr], lane);
+          const int ii = tidx[row];
+          if ((lane & 7) == 0 && ii >= 0 && tot != T(0)) {
+            const int which = lane >> 3;
+            atomicAdd(which < 3 ? &A.force[3 * ii + which] : &A.dcn[ii], tot);
+          }
+          if (A.energy) {
+            const T se_ = warp_sum(ie[rr]);
+            if (lane == 0 && ii >= 0 && se_ != T(0)) atomicAdd(&A.energy[ii], se_);
+          }
+        }
+        if (A.energy && kk >= 0 && ke != T(0)) atomicAdd(&A.energy[kk], ke);
+        if (kk >= 0 && (kfx != T(0) || kfy != T(0) || kfz != T(0) || kdc != T(0))) {
+          atomicAdd(&A.force[3 * kk], kfx);
+          atomicAdd(&A.force[3 * kk + 1], kfy);
+          atomicAdd(&A.force[3 * kk + 2], kfz);
+          atomicAdd(&A.dcn[kk], kdc);
+        }
+        }
+      }
+      __syncthreads();  // everybody is done with this buffer: it may be refilled
+      tx = nx, ty = ny, nb ^= 1;
+    }
+  }
+#undef TST
+}
+
 template <typename T>
 constexpr size_t atm_grad_smem() {
   return sizeof(T) * (2 * GROUP * AVEC + 5 * GROUP + 2 * 2 * TILE * (AVEC + 1) + 5 * 2 * TILE +
@@ -950,7 +1295,15 @@ LargeCarve large_carve(int nat, size_t elem, int nctas, bool grad = false) {
   c.ucount = o, o += al256(ng * sizeof(int));
   c.ulist = o, o += al256(ng * nat * sizeof(int));
   c.umask = o, o += al256(ng * nat * sizeof(unsigned));
-  c.cstash = o, o += al256((size_t)nctas * GROUP * (grad ? GSTASH : 3) * nat * elem);
+  {
+    size_t per_cta = (size_t)GROUP * (grad ? GSTASH : 3) * nat * elem;
+    if (grad) {  // large_atm_grad_pipe: tiles of TILE list atoms with everything a tile pair needs
+      const size_t nt = (nat + TILE - 1) / TILE;
+      const size_t tile = elem == 8 ? atm_pipe_tile_bytes<double>() : atm_pipe_tile_bytes<float>();
+      if (nt * tile > per_cta) per_cta = nt * tile;
+    }
+    c.cstash = o, o += al256((size_t)nctas * per_cta);
+  }
   c.zgd = c.z0gd = c.dzg = c.daq_cn = c.da0_cn = c.daq_q = 0;
   if (grad) {
     c.zgd = o, o += al256((size_t)nat * NREF * elem);
@@ -1132,6 +1485,7 @@ int run_large_grad(d4b200_tables* h, const d4b200_params* par, int nat, const in
   constexpr int dt = sizeof(T) == 8 ? 0 : 1;
   if (!configured[dt]) {
     cudaFuncSetAttribute(large_atm_grad<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atm_grad_smem<T>());
+    cudaFuncSetAttribute(large_atm_grad_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)atm_pipe_smem<T>());
     cudaFuncSetAttribute(large_twobody_grad<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)twobody_grad_smem<T>());
     configured[dt] = true;
   }
@@ -1152,7 +1506,14 @@ int run_large_grad(d4b200_tables* h, const d4b200_params* par, int nat, const in
     if (A.nslice > 16) A.nslice = 16;
     int grid = nctas;
     if (grid > ngl * A.nslice) grid = ngl * A.nslice;
-    large_atm_grad<T><<<grid, 512, atm_grad_smem<T>(), st>>>(A);
+    static const bool pipe = [] {
+      const char* v = getenv("D4B200_LARGE_PIPE");
+      return v ? v[0] != '0' : D4_LARGE_PIPE_DEFAULT;
+    }();
+    if (pipe)
+      large_atm_grad_pipe<T><<<grid, 512, atm_pipe_smem<T>(), st>>>(A);
+    else
+      large_atm_grad<T><<<grid, 512, atm_grad_smem<T>(), st>>>(A);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
