@@ -362,7 +362,8 @@ def _plain_param(param) -> dict:
 _FD4 = ((-2.0, 1.0 / 12.0), (-1.0, -8.0 / 12.0), (1.0, 8.0 / 12.0), (2.0, -1.0 / 12.0))
 
 
-def large_param_vjp(numbers, positions, param, q, gout, need, *, cutoff=None, group=None, model=None) -> list:
+def large_param_vjp(numbers, positions, param, q, gout, need, *, cutoff=None, group=None, model=None,
+                    backend_factory: Callable | None = None) -> list:  # fmt: skip
     """``d(sum_i gout_i E_i)/d(s6, s8, s9, s10, a1, a2, alp)`` of ONE large structure (entries of ``need``).
 
     The reference differentiates its dense tape (``test/test_grad/test_param.py:40-100``); the one-CTA family has
@@ -378,7 +379,9 @@ def large_param_vjp(numbers, positions, param, q, gout, need, *, cutoff=None, gr
     g = None if gout is None else gout.detach()
 
     def weighted(par) -> Tensor:
-        e = large_energy(numbers, positions.detach(), par, q.detach(), cutoff=cutoff, group=group, model=model)
+        be = backend_factory(par) if backend_factory is not None else None  # CPU tests: oracle in place of the kernels
+        e = large_energy(numbers, positions.detach(), par, q.detach(), cutoff=cutoff, group=group, model=model,
+                         backend=be)  # fmt: skip
         return (e.sum() if g is None else (e * g).sum()).double()
 
     def part(**on) -> Tensor:  # one linear part: its factor = 1, the others = 0

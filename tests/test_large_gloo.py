@@ -180,3 +180,36 @@ def test_rowblock_two_ranks(tmp_path):
     port = 31500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_large_param_vjp_host_logic_against_oracle_autograd():
+    """large.large_param_vjp (exact parts for s6 / s8 / s9 / s10, fourth-order differences for a1 / a2 / alp) with the
+    oracle standing in for the tiled energy kernels, against autograd of the oracle through the parameters."""
+    sys.path[:0] = [str(ROOT), str(ROOT / "oracle")]
+    import d4_oracle as orc
+    from tad_dftd4_b200 import large
+
+    numbers, positions, q = orc.organic_batch([28], seed=13)
+    numbers, positions, q = numbers[0], positions[0], q[0]
+    base = {"s6": 1.0, "s8": 0.78981345, "s9": 1.0, "s10": 0.3, "a1": 0.49484001, "a2": 5.73083694, "alp": 16.0}
+    g = torch.randn(28, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in base.items()}
+    keys = ("s6", "s8", "s9", "s10", "a1", "a2", "alp")
+    want = torch.autograd.grad((orc.dftd4(numbers, positions, tp, q) * g).sum(), [tp[k] for k in keys])
+
+    def factory(par):
+        def energy(n, p, qq, rows, groups, want_cost):
+            if want_cost:
+                return None, torch.ones((n.shape[0] + GS - 1) // GS, dtype=torch.float64)
+            return orc.dftd4(n, p, {k: v for k, v in par.items() if v is not None}, qq), None
+
+        return dict(energy=energy, group_size=GS)
+
+    large.clear_plan_cache()
+    got = large.large_param_vjp(numbers, positions, base, q, g, [True] * 7, backend_factory=factory)
+    for k, w, v in zip(keys, want, got):
+        assert abs(float(v) - float(w)) <= 1e-8 * abs(float(w)) + 1e-13, (k, float(v), float(w))
+    # parameters that are not asked for cost nothing and come back as None
+    some = large.large_param_vjp(numbers, positions, base, q, None, [False, True, False, False, False, False, False],
+                                 backend_factory=factory)
+    assert [x is not None for x in some] == [False, True, False, False, False, False, False]
