@@ -83,6 +83,35 @@ def test_large_gradient_f64(nat, cut):
     assert (gq.cpu() - gq_ref).abs().max() < 1e-9
 
 
+@pytest.mark.parametrize("nat,cut", [(200, {}), (230, dict(disp2=22.0, disp3=13.0))])
+def test_large_gradient_f32(nat, cut):
+    """FP32 mode of the tiled family (float instantiations of the gradient kernels incl. the bulk-async tile
+    pipeline) against the float64 oracle: north_star's 1e-5 relative; fused energies and a weighted upstream."""
+    import tad_dftd4_b200 as d4
+    from tad_dftd4_b200.large import dftd4_large
+
+    numbers, positions, q = _cluster(nat, seed=300 + nat)
+    g = torch.from_numpy(np.random.default_rng(2).normal(size=nat))
+    pos = positions.clone().requires_grad_(True)
+    e_ref = orc.dftd4(numbers, pos, PBE0, q, **cut)
+    (gp_ref,) = torch.autograd.grad((e_ref * g).sum(), pos)
+    (gs_ref,) = torch.autograd.grad(orc.dftd4(numbers, pos, PBE0, q, **cut).sum(), pos)
+
+    dev = torch.device("cuda:0")
+    f32 = torch.float32
+    cutoff = d4.Cutoff(**cut, device=dev, dtype=f32) if cut else None
+    pd = positions.to(dev, f32).requires_grad_(True)
+    e = dftd4_large(numbers.to(dev), pd, PBE0, q.to(dev, f32), cutoff=cutoff)
+    assert e.dtype == f32
+    (gp,) = torch.autograd.grad((e * g.to(dev, f32)).sum(), pd, retain_graph=True)
+    (gs,) = torch.autograd.grad(e.sum(), pd)
+    er = e_ref.detach()
+    assert abs(e.double().sum().item() - er.sum().item()) <= 1e-5 * abs(er.sum().item())
+    assert (e.detach().cpu().double() - er).abs().max() / er.abs().max() < 5e-5
+    assert (gp.cpu().double() - gp_ref).abs().max() < 5e-5 * max(gp_ref.abs().max().item(), 1e-3)
+    assert (gs.cpu().double() - gs_ref).abs().max() < 5e-5 * max(gs_ref.abs().max().item(), 1e-3)
+
+
 def test_dftd4_large_gradient_through_public_api():
     import tad_dftd4_b200 as d4
 
