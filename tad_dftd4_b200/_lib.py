@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import atexit
 import os
+import threading
 import time
 from pathlib import Path
 
@@ -118,9 +119,33 @@ def load() -> C.CDLL:
             raise D4B200Error(f"{LIB_PATH} does not export {name}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         fn.restype = res
         fn.argtypes = args
+        if name not in _LOCK_FREE:
+            setattr(lib, name, _serialised(fn))
     _lib = lib
     atexit.register(_let_autograd_workers_finish)
     return lib
+
+
+# Entry points that only read constants: no lock.
+_LOCK_FREE = frozenset({"d4b200_version", "d4b200_error_string", "d4b200_eeq_limit", "d4b200_large_group_size",
+                        "d4b200_workspace_bytes", "d4b200_eeq_factor_doubles"})  # fmt: skip
+_CALL_LOCK = threading.RLock()
+
+
+def _serialised(fn):
+    """One library call at a time per process.  A tables handle owns ONE set of fork / join events and class streams
+    (csrc/d4b200_handle.cuh); ctypes releases the GIL during a call, so two Python threads could otherwise interleave
+    their event records and stream waits on the same handle.  Calls only ENQUEUE work (a few microseconds), so the lock
+    costs nothing measurable; calls from one thread on different CUDA streams were never a problem (workspaces are kept
+    per stream, `disp._Engine`).  C callers: serialise the calls on one handle, or use one handle per thread."""
+
+    def call(*args):
+        with _CALL_LOCK:
+            return fn(*args)
+
+    call.__name__ = getattr(fn, "__name__", "d4b200_call")
+    call.__wrapped__ = fn
+    return call
 
 
 def _let_autograd_workers_finish() -> None:

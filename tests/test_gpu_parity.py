@@ -314,3 +314,44 @@ def test_unaligned_views_and_odd_width_are_bitwise_consistent(dtype):
         part = run(sl)
         for a, b in zip(part, full):
             assert torch.equal(a, b[sl])
+
+
+def test_calls_from_two_host_threads_on_their_own_streams():
+    """ctypes releases the GIL during a library call; the calls on one tables handle are serialised (_lib._serialised)
+    and workspaces are kept per stream, so two threads get the results of a single-threaded run."""
+    import threading
+
+    import tad_dftd4_b200 as d4
+
+    dev = torch.device("cuda:0")
+    cases = []
+    for seed, sizes in ((1, [12, 33, 60, 7] * 8), (2, [100, 80, 64] * 6)):
+        n, p, q = orc.organic_batch(sizes, seed=seed)
+        cases.append((n.to(dev), p.to(dev), q.to(dev)))
+    par = dict(s8=1.20065498, a1=0.40085597, a2=5.02928789)
+
+    def run(case):
+        n, p, q = case
+        pos = p.clone().requires_grad_(True)
+        e = d4.dftd4(n, pos, 0.0, par, q=q)
+        (g,) = torch.autograd.grad(e.sum(), pos)
+        return e.detach(), g
+
+    want = [run(c) for c in cases]
+    torch.cuda.synchronize()
+    out: dict = {}
+
+    def worker(k):
+        with torch.cuda.stream(torch.cuda.Stream(dev)):
+            res = [run(cases[k]) for _ in range(25)]
+            torch.cuda.current_stream().synchronize()
+        out[k] = res
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(2):
+        for e, g in out[k]:
+            assert torch.equal(e, want[k][0]) and torch.equal(g, want[k][1])
