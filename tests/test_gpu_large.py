@@ -231,3 +231,36 @@ def test_plan_cache_is_confirmed_against_the_atomic_numbers():
     before = len(large._PLAN_CACHE)
     large.dftd4_large(numbers, p2.to(dev) + 0.01, PBE0, q2.to(dev))
     assert len(large._PLAN_CACHE) == before
+
+
+def test_previous_gradient_kernel_stays_selectable():
+    """D4B200_LARGE_PIPE=0 (read once per process) selects large_atm_grad instead of the bulk-async pipeline: kept for
+    same-box A/B timing, so it has to stay correct."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys, torch, numpy as np\n"
+        f"sys.path[:0] = [{str(root)!r}, {str(root / 'oracle')!r}, {str(root / 'tests')!r}]\n"
+        "import d4_oracle as orc\n"
+        "from test_gpu_large import _cluster, PBE0\n"
+        "from tad_dftd4_b200.large import dftd4_large\n"
+        "n, p, q = _cluster(150, seed=77)\n"
+        "pr = p.clone().requires_grad_(True)\n"
+        "er = orc.dftd4(n, pr, PBE0, q)\n"
+        "(gr,) = torch.autograd.grad(er.sum(), pr)\n"
+        "dev = torch.device('cuda:0')\n"
+        "pd = p.to(dev).requires_grad_(True)\n"
+        "e = dftd4_large(n.to(dev), pd, PBE0, q.to(dev))\n"
+        "(g,) = torch.autograd.grad(e.sum(), pd)\n"
+        "de = ((e.detach().cpu() - er.detach()).abs().max() / er.detach().abs().max()).item()\n"
+        "dg = (g.cpu() - gr).abs().max().item()\n"
+        "print('RESULT', de, dg)\n"
+        "assert de < 1e-10 and dg < 1e-9\n"
+    )
+    env = dict(os.environ, D4B200_LARGE_PIPE="0")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "RESULT" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
